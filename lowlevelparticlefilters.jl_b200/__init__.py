@@ -1,0 +1,15 @@
+"""llpf_b200 — B200-native particle-filter hot path (host-side mirror of the reference API).
+
+Import as `import llpf_b200` (see the shim `llpf_b200.py` at the repo root).  The numerical work
+happens in `csrc/libllpf_b200.so` (hand-written sm_100a CUDA behind the C-ABI of include/llpf.h);
+nothing here falls back to a CPU implementation.
+"""
+from . import _abi  # noqa: F401
+from ._abi import LLPFError, load_library  # noqa: F401
+from .filters import (  # noqa: F401
+    AbstractParticleFilter, AdvancedParticleFilter, AuxiliaryParticleFilter, GaussianLikelihood,
+    LinearDynamics, LinearMeasurement, MvNormal, ParticleFilter, ParticleFilteringSolution, QuadtankRK4,
+    ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, correct,
+    effective_particles, expweights, forward_trajectory, index, last_run_ms, launch_count, loglik, logsumexp,
+    mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
+    shouldresample, state, update, weighted_mean, weights)

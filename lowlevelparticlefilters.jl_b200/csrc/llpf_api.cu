@@ -1,0 +1,1065 @@
+// llpf_api.cu — host side of libllpf_b200.so: the C-ABI of include/llpf.h on top of the persistent
+// sm_100a engine (llpf_engine.cuh).  No torch types, no CPU fallback: without a CUDA device every
+// entry point fails with LLPF_ERR_NO_DEVICE / LLPF_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/llpf.h"
+#include "llpf_engine.cuh"
+
+using namespace llpf;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      const int code_ = (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver)        \
+                            ? LLPF_ERR_NO_DEVICE : LLPF_ERR_CUDA;                             \
+      return fail(code_, std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
+    }                                                                                         \
+  } while (0)
+#define OKR(expr)              \
+  do {                         \
+    const int rc_ = (expr);    \
+    if (rc_ != LLPF_OK) return rc_; \
+  } while (0)
+
+extern "C" const char* llpf_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// small host linear algebra (column-major in, as the C-ABI delivers it)
+// ------------------------------------------------------------------------------------------------
+#define CMH(M, r, c, ld) ((M)[(size_t)(c) * (ld) + (r)])
+static bool chol_lower(const double* S, int n, std::vector<double>& L) {
+  L.assign((size_t)n * n, 0.0);
+  for (int jc = 0; jc < n; ++jc) {
+    double d = CMH(S, jc, jc, n);
+    for (int k = 0; k < jc; ++k) d -= CMH(L, jc, k, n) * CMH(L, jc, k, n);
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d);
+    CMH(L, jc, jc, n) = d;
+    for (int i = jc + 1; i < n; ++i) {
+      double v = CMH(S, i, jc, n);
+      for (int k = 0; k < jc; ++k) v -= CMH(L, i, k, n) * CMH(L, jc, k, n);
+      CMH(L, i, jc, n) = v / d;
+    }
+  }
+  return true;
+}
+// inverse of a lower-triangular matrix (column-major)
+static void inv_lower(const std::vector<double>& L, int n, std::vector<double>& W) {
+  W.assign((size_t)n * n, 0.0);
+  for (int c = 0; c < n; ++c) {
+    CMH(W, c, c, n) = 1.0 / CMH(L, c, c, n);
+    for (int r = c + 1; r < n; ++r) {
+      double acc = 0.0;
+      for (int k = c; k < r; ++k) acc += CMH(L, r, k, n) * CMH(W, k, c, n);
+      CMH(W, r, c, n) = -acc / CMH(L, r, r, n);
+    }
+  }
+}
+
+struct HostModel {
+  int nx = 0, nu = 0, ny = 0, dyn = 0;
+  std::vector<double> A, B, C, mu0, L0, L1, L2, W, G;  // column-major
+  double c0 = 0;
+  double dynp[8] = {0}, t_switch = 0, a1_factor = 1, integ_Ts = 1;
+  int supersample = 1;
+};
+
+static int build_host_model(const llpf_model* m, HostModel& H) {
+  if (!m) return fail(LLPF_ERR_BAD_ARG, "model is null");
+  const int nx = m->nx, nu = m->nu, ny = m->ny;
+  if (nx < 1 || nx > MAX_NX || ny < 1 || ny > 8 || nu < 0 || nu > MAX_NU)
+    return fail(LLPF_ERR_UNSUPPORTED, "supported dimensions: 1<=nx<=8, 1<=ny<=8, 0<=nu<=8");
+  if (!m->C || !m->R1 || !m->R2 || !m->mu0 || !m->Sigma0) return fail(LLPF_ERR_BAD_ARG, "null model matrix");
+  H.nx = nx; H.nu = nu; H.ny = ny; H.dyn = m->dynamics;
+  if (m->dynamics == LLPF_DYN_LINEAR) {
+    if (!m->A || (nu > 0 && !m->B)) return fail(LLPF_ERR_BAD_ARG, "linear dynamics need A (and B)");
+    H.A.assign(m->A, m->A + (size_t)nx * nx);
+    if (nu > 0) H.B.assign(m->B, m->B + (size_t)nx * nu); else H.B.clear();
+  } else if (m->dynamics == LLPF_DYN_QUADTANK_RK4) {
+    if (nx != 4 || nu != 2) return fail(LLPF_ERR_BAD_ARG, "quadtank needs nx=4, nu=2");
+    if (m->supersample < 1) return fail(LLPF_ERR_BAD_ARG, "supersample must be positive");
+  } else {
+    return fail(LLPF_ERR_BAD_ARG, "unknown dynamics kind");
+  }
+  H.C.assign(m->C, m->C + (size_t)ny * nx);
+  H.mu0.assign(m->mu0, m->mu0 + nx);
+  if (!chol_lower(m->R1, nx, H.L1)) return fail(LLPF_ERR_NOT_POSDEF, "R1 is not positive definite");
+  if (!chol_lower(m->R2, ny, H.L2)) return fail(LLPF_ERR_NOT_POSDEF, "R2 is not positive definite");
+  if (!chol_lower(m->Sigma0, nx, H.L0)) return fail(LLPF_ERR_NOT_POSDEF, "Sigma0 is not positive definite");
+  inv_lower(H.L2, ny, H.W);
+  H.G.assign((size_t)ny * nx, 0.0);
+  for (int a = 0; a < ny; ++a)
+    for (int c = 0; c < nx; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k <= a; ++k) acc += CMH(H.W, a, k, ny) * CMH(H.C, k, c, ny);
+      CMH(H.G, a, c, ny) = acc;
+    }
+  double ld = 0.0;
+  for (int i = 0; i < ny; ++i) ld += std::log(CMH(H.L2, i, i, ny));
+  ld *= 2;
+  H.c0 = -((double)ny * std::log(2 * M_PI) + ld) / 2;  // mvnormal_c0, utils.jl:254-257
+  std::memcpy(H.dynp, m->dyn_params, sizeof(H.dynp));
+  H.t_switch = m->t_switch; H.a1_factor = m->a1_factor; H.integ_Ts = m->integ_Ts;
+  H.supersample = m->supersample;
+  return LLPF_OK;
+}
+
+template <int NX, int NY>
+static void fill_modelp(const HostModel& H, ModelP<NX, NY>& M) {
+  std::memset(&M, 0, sizeof(M));
+  for (int r = 0; r < NX; ++r)
+    for (int c = 0; c < NX; ++c) {
+      if (!H.A.empty()) M.A[r * NX + c] = CMH(H.A, r, c, NX);
+      M.L1[r * NX + c] = CMH(H.L1, r, c, NX);
+    }
+  for (int a = 0; a < NY; ++a) {
+    for (int c = 0; c < NX; ++c) M.G[a * NX + c] = CMH(H.G, a, c, NY);
+    for (int c = 0; c < NY; ++c) M.W[a * NY + c] = CMH(H.W, a, c, NY);
+  }
+  for (int r = 0; r < NX; ++r)
+    for (int c = 0; c < H.nu; ++c)
+      if (!H.B.empty()) M.B[r * MAX_NU + c] = CMH(H.B, r, c, NX);
+  M.c0 = H.c0;
+  if (H.dyn == LLPF_DYN_QUADTANK_RK4) {
+    // p = {kc,k1,k2,A,a,gamma}  example_quadtank.jl:91-97 ; coefficients in the reference's evaluation order
+    const double k1 = H.dynp[1], k2 = H.dynp[2], Aa = H.dynp[3], a = H.dynp[4], g = H.dynp[5];
+    M.qt[0] = -a / Aa;
+    M.qt[1] = -(a * H.a1_factor) / Aa;
+    M.qt[2] = a / Aa;
+    M.qt[3] = 2 * 9.81;
+    M.qt[4] = g * k1 / Aa;
+    M.qt[5] = g * k2 / Aa;
+    M.qt[6] = (1 - g) * k2 / Aa;
+    M.qt[7] = (1 - g) * k1 / Aa;
+  }
+  M.t_switch = H.t_switch;
+  M.integ_h = H.integ_Ts / (double)H.supersample;
+  M.supersample = H.supersample;
+  M.nu = H.nu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// utility kernels (reset!, import/export between the AoS C-ABI layout and the SoA HBM layout)
+// ------------------------------------------------------------------------------------------------
+struct InitP {
+  double mu0[MAX_NX];
+  double L0[MAX_NX * MAX_NX];  // row-major lower
+};
+
+// reset!(pf)  filtering.jl:4-14: x = xprev ~ initial_density ; (weights handled by Scalars.uniform)
+template <int NX>
+__global__ void k_init(double* x, long long ld, long long n, long long first, RngKey key, InitP ip) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double z[NX];
+    normals<NX>(key, ST_INIT, 0u, (unsigned long long)(first + i), z);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c <= r; ++c) acc = fma(ip.L0[r * MAX_NX + c], z[c], acc);
+      x[(size_t)r * ld + i] = ip.mu0[r] + acc;
+    }
+  }
+}
+
+__global__ void k_export_x(const double* x, long long ld, long long n, int nx, double* out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    for (int d = 0; d < nx; ++d) out[(size_t)i * nx + d] = x[(size_t)d * ld + i];
+}
+__global__ void k_import_x(double* x, long long ld, long long n, int nx, const double* in) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    for (int d = 0; d < nx; ++d) x[(size_t)d * ld + i] = in[(size_t)i * nx + d];
+}
+// weights(pf) / expweights(pf) from the lazy state
+__global__ void k_materialise(const double* w, const Scalars* scp, long long n, long long N,
+                              double* out_w, double* out_we) {
+  const Scalars sc = *scp;
+  const double lwN = -log((double)N), lw1N = log(1.0 / (double)N);
+  const double inv_s = sc.pend ? 1.0 / sc.pend_s : 1.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double wn, we;
+    if (sc.uniform) {
+      wn = (sc.uniform == 1) ? lwN : lw1N;
+      we = 1.0 / (double)N;
+    } else if (sc.pend || sc.stats_ahead) {
+      const double wr = w[i];
+      if (sc.stats_ahead) {   // APF between predict! and correct!: w is raw, `we` aliases λ in the
+        wn = wr;              // reference (filtering.jl:200); we report exp-normalised weights instead
+        we = exp(wr - sc.pend_m) * (1.0 / sc.pend_s);
+      } else {
+        wn = (wr - sc.pend_m) - sc.pend_ls;
+        we = exp(wr - sc.pend_m) * inv_s;
+      }
+    } else {
+      wn = w[i];
+      we = exp(wn);
+    }
+    if (out_w) out_w[i] = wn;
+    if (out_we) out_we[i] = we;
+  }
+}
+__global__ void k_export_j(const int* j, int identity, long long n, long long first, long long* out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = identity ? (first + i + 1) : ((long long)j[i] + 1);
+}
+// block partials of (sum we, sum we^2, sum we*x[d]); finished on the host in block order
+__global__ void k_wstats(const double* we, const double* x, long long ld, long long n, int nx,
+                         double* part /*[grid][2+MAX_NX]*/) {
+  __shared__ double sm[NWARP * (2 + MAX_NX)];
+  double v[2 + MAX_NX];
+  for (int k = 0; k < 2 + MAX_NX; ++k) v[k] = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double e = we[i];
+    v[0] += e;
+    v[1] = fma(e, e, v[1]);
+    for (int d = 0; d < nx; ++d) v[2 + d] = fma(e, x[(size_t)d * ld + i], v[2 + d]);
+  }
+  for (int k = 0; k < 2 + MAX_NX; ++k)
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 2 + MAX_NX; ++k) sm[(threadIdx.x >> 5) * (2 + MAX_NX) + k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < 2 + MAX_NX) {
+    double r = 0.0;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) r += sm[wq * (2 + MAX_NX) + threadIdx.x];
+    part[(size_t)blockIdx.x * (2 + MAX_NX) + threadIdx.x] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone cooperative kernels at the reference's function boundaries
+// ------------------------------------------------------------------------------------------------
+// resample(strategy, we, j, bins, M)  resample.jl:17-61 ; we -> bins (scan) -> j (search), M output slots
+__global__ void __launch_bounds__(BLOCK)
+k_resample(const __grid_constant__ EngineP P, const double* we, double u01, const double* u_slots,
+           long long M, long long* j_inout) {
+  __shared__ Shared sh;
+  unsigned bar_target = 0;
+  long long beg = (long long)blockIdx.x * P.chunk, end = beg + P.chunk;
+  if (end > P.n) end = P.n;
+  if (beg > P.n) beg = P.n;
+  scan_stage1(P, sh, beg, end, [=](long long i) { return we[i]; });
+  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  if (P.scan_mode != 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
+    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+    load_block_table(P, sh);
+  } else {
+    scan_stage2(P, sh, beg, end, 0ull);
+    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  }
+  const double total = sh.offd[P.nblocks];
+  const Thresholds th = make_thresholds(P, total, u01, (double)M, u_slots);
+  for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < M; i += (long long)gridDim.x * BLOCK) {
+    const double s = threshold(th, P.key, 0u, i);
+    if (s < total) j_inout[i] = upper_bound_bins(P, sh, s) + 1;  // else: keep the caller's value (stale)
+  }
+}
+
+// logsumexp!(w, we)  utils.jl:18-27 on caller-provided arrays
+__global__ void __launch_bounds__(BLOCK)
+k_logsumexp(const __grid_constant__ EngineP P, double* w, double* we, double* ll_out) {
+  __shared__ Shared sh;
+  unsigned bar_target = 0;
+  long long beg = (long long)blockIdx.x * P.chunk, end = beg + P.chunk;
+  if (end > P.n) end = P.n;
+  if (beg > P.n) beg = P.n;
+  Online<1> acc;
+  acc.init();
+  const double dummy[1] = {0.0};
+  for (long long i = beg + threadIdx.x; i < end; i += BLOCK) acc.add(w[i], dummy, false);
+  const Stats st = reduce_stats<1>(P, sh, acc, false, bar_target);
+  const double ls = log(st.s), inv = 1.0 / st.s;
+  for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
+    const double wr = w[i];
+    we[i] = exp(wr - st.m) * inv;
+    w[i] = (wr - st.m) - ls;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ll_out = st.m + ls;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the filter handle
+// ------------------------------------------------------------------------------------------------
+struct llpf_filter;
+typedef cudaError_t (*launch_fn)(llpf_filter*, const EngineP&);
+typedef cudaError_t (*init_fn)(llpf_filter*, uint64_t epoch);
+typedef int (*occ_fn)();
+
+struct llpf_filter {
+  llpf_config cfg;
+  HostModel hm;
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  long long N = 0, n = 0, first = 0, ld = 0;
+  // device arena
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  double *x[2] = {nullptr, nullptr}, *w = nullptr, *lam = nullptr, *bins = nullptr;
+  int* j = nullptr;
+  double* partials = nullptr;
+  u64* tots = nullptr;
+  unsigned* bar = nullptr;
+  Scalars* sc = nullptr;
+  double *stage_u = nullptr, *stage_y = nullptr, *wstat = nullptr, *scratch = nullptr;
+  // per-run buffers (grow-only)
+  double *d_u = nullptr, *d_y = nullptr, *d_ll = nullptr, *d_ess = nullptr, *d_xhat = nullptr;
+  int* d_res = nullptr;
+  long long cap_T = 0;
+  // host mirror
+  Scalars hsc;
+  Scalars* pin_sc = nullptr;  // pinned staging
+  uint64_t epoch = 0;
+  long long launches = 0;
+  float last_ms = 0.f;
+  int max_blocks = 1;
+  launch_fn launch = nullptr;
+  init_fn init = nullptr;
+};
+
+template <int NX, int NY, int DYN>
+static cudaError_t launch_engine(llpf_filter* f, const EngineP& P) {
+  ModelP<NX, NY> M;
+  fill_modelp<NX, NY>(f->hm, M);
+  EngineP Pc = P;
+  void* args[] = {(void*)&Pc, (void*)&M};
+  return cudaLaunchCooperativeKernel((const void*)k_engine<NX, NY, DYN>, dim3(P.nblocks), dim3(BLOCK),
+                                     args, 0, f->stream);
+}
+template <int NX, int NY, int DYN>
+static int occupancy_engine() {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine<NX, NY, DYN>, BLOCK, 0) != cudaSuccess)
+    return 0;
+  return occ;
+}
+template <int NX>
+static cudaError_t launch_init(llpf_filter* f, uint64_t epoch) {
+  InitP ip;
+  std::memset(&ip, 0, sizeof(ip));
+  for (int r = 0; r < NX; ++r) {
+    ip.mu0[r] = f->hm.mu0[r];
+    for (int c = 0; c <= r; ++c) ip.L0[r * MAX_NX + c] = CMH(f->hm.L0, r, c, NX);
+  }
+  RngKey key{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)epoch << 8};
+  const int grid = (int)std::min<long long>((f->n + 255) / 256, (long long)f->num_sms * 8);
+  k_init<NX><<<grid > 0 ? grid : 1, 256, 0, f->stream>>>(f->x[0], f->ld, f->n, f->first, key, ip);
+  return cudaGetLastError();
+}
+
+struct Dispatch {
+  int nx, ny, dyn;
+  launch_fn launch;
+  init_fn init;
+  occ_fn occ;
+};
+#define DISP(NX, NY, DYN) \
+  { NX, NY, DYN, launch_engine<NX, NY, DYN>, launch_init<NX>, occupancy_engine<NX, NY, DYN> }
+static const Dispatch g_dispatch[] = {
+    DISP(1, 1, 0), DISP(2, 1, 0), DISP(2, 2, 0), DISP(3, 1, 0), DISP(3, 2, 0), DISP(3, 3, 0),
+    DISP(4, 1, 0), DISP(4, 2, 0), DISP(4, 3, 0), DISP(4, 4, 0), DISP(6, 2, 0), DISP(6, 3, 0),
+    DISP(8, 2, 0), DISP(8, 4, 0), DISP(4, 2, 1),
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int check_handle(llpf_handle h) {
+  if (!h) return fail(LLPF_ERR_BAD_ARG, "null handle");
+  return LLPF_OK;
+}
+
+static int sync_scalars(llpf_filter* f) {  // device -> host mirror
+  CU(cudaMemcpyAsync(f->pin_sc, f->sc, sizeof(Scalars), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  f->hsc = *f->pin_sc;
+  return LLPF_OK;
+}
+static int push_scalars(llpf_filter* f) {  // host mirror -> device
+  CU(cudaStreamSynchronize(f->stream));
+  *f->pin_sc = f->hsc;
+  CU(cudaMemcpyAsync(f->sc, f->pin_sc, sizeof(Scalars), cudaMemcpyHostToDevice, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  return LLPF_OK;
+}
+
+extern "C" int llpf_device_count(int* count) {
+  if (!count) return fail(LLPF_ERR_BAD_ARG, "null");
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return fail(LLPF_ERR_NO_DEVICE, cudaGetErrorString(e));
+  }
+  *count = c;
+  return LLPF_OK;
+}
+
+extern "C" int llpf_destroy(llpf_handle h) {
+  if (!h) return LLPF_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->arena);
+  cudaFree(h->d_u); cudaFree(h->d_y); cudaFree(h->d_ll); cudaFree(h->d_ess); cudaFree(h->d_xhat);
+  cudaFree(h->d_res);
+  if (h->pin_sc) cudaFreeHost(h->pin_sc);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LLPF_OK;
+}
+
+extern "C" int llpf_set_model(llpf_handle h, const llpf_model* model) {
+  OKR(check_handle(h));
+  HostModel hm;
+  OKR(build_host_model(model, hm));
+  if (hm.nx != h->hm.nx || hm.ny != h->hm.ny || hm.nu != h->hm.nu || hm.dyn != h->hm.dyn)
+    return fail(LLPF_ERR_BAD_ARG, "llpf_set_model cannot change dimensions or dynamics kind");
+  h->hm = hm;
+  return LLPF_OK;
+}
+
+extern "C" int llpf_reset(llpf_handle h, uint64_t epoch);
+
+extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf_handle* out) {
+  if (!cfg || !model || !out) return fail(LLPF_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->N < 1 || cfg->N >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "need 1 <= N < 2^31");
+  if (cfg->filter < 0 || cfg->filter > 3) return fail(LLPF_ERR_BAD_ARG, "unknown filter kind");
+  if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED)
+    return fail(LLPF_ERR_UNSUPPORTED, "in-loop resampling: systematic or stratified");
+  const int world = cfg->world < 1 ? 1 : cfg->world;
+  if (world > 1) return fail(LLPF_ERR_UNSUPPORTED, "sharded filters: see llpf_shard_* (not in this build)");
+  int ndev = 0;
+  OKR(llpf_device_count(&ndev));
+  if (ndev < 1) return fail(LLPF_ERR_NO_DEVICE, "no CUDA device; the product path has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(LLPF_ERR_BAD_ARG, "bad device ordinal");
+
+  llpf_filter* f = new llpf_filter();
+  f->cfg = *cfg;
+  f->cfg.world = world;
+  int rc = build_host_model(model, f->hm);
+  if (rc) { delete f; return rc; }
+  const Dispatch* d = nullptr;
+  for (const Dispatch& e : g_dispatch)
+    if (e.nx == f->hm.nx && e.ny == f->hm.ny && e.dyn == f->hm.dyn) d = &e;
+  if (!d) {
+    delete f;
+    return fail(LLPF_ERR_UNSUPPORTED, "no kernel instantiated for this (nx, ny, dynamics)");
+  }
+  f->launch = d->launch;
+  f->init = d->init;
+  f->device = cfg->device;
+#define CUF(expr)                                                                       \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      llpf_destroy(f);                                                                  \
+      return fail(LLPF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));   \
+    }                                                                                   \
+  } while (0)
+  CUF(cudaSetDevice(f->device));
+  cudaDeviceProp prop;
+  CUF(cudaGetDeviceProperties(&prop, f->device));
+  f->num_sms = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) {
+    llpf_destroy(f);
+    return fail(LLPF_ERR_UNSUPPORTED, "device lacks cooperative launch");
+  }
+  const int occ = d->occ();
+  if (occ < 1) {
+    llpf_destroy(f);
+    return fail(LLPF_ERR_CUDA, "engine kernel does not fit on an SM (is this an sm_100a device?)");
+  }
+  f->max_blocks = std::min(occ * f->num_sms, MAX_BLOCKS - 1);
+  CUF(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+  CUF(cudaEventCreate(&f->ev0));
+  CUF(cudaEventCreate(&f->ev1));
+  CUF(cudaMallocHost(&f->pin_sc, sizeof(Scalars)));
+
+  f->N = cfg->N;
+  f->n = cfg->N;
+  f->first = 0;
+  f->ld = (long long)align_up((size_t)f->n, 32);
+  const int nx = f->hm.nx;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_x0 = take((size_t)nx * f->ld * 8), o_x1 = take((size_t)nx * f->ld * 8);
+  const size_t o_w = take((size_t)f->ld * 8), o_lam = take((size_t)f->ld * 8), o_bins = take((size_t)f->ld * 8);
+  const size_t o_j = take((size_t)f->ld * 4);
+  const size_t o_part = take((size_t)MAX_BLOCKS * PS * 8), o_tots = take((size_t)MAX_BLOCKS * 8);
+  const size_t o_bar = take(256), o_sc = take(sizeof(Scalars));
+  const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + MAX_NX) * 8);
+  const size_t o_scr = take((size_t)(nx + 2) * f->ld * 8);
+  f->arena_bytes = off;
+  CUF(cudaMalloc(&f->arena, f->arena_bytes));
+  CUF(cudaMemsetAsync(f->arena, 0, f->arena_bytes, f->stream));
+  f->x[0] = (double*)(f->arena + o_x0); f->x[1] = (double*)(f->arena + o_x1);
+  f->w = (double*)(f->arena + o_w); f->lam = (double*)(f->arena + o_lam);
+  f->bins = (double*)(f->arena + o_bins); f->j = (int*)(f->arena + o_j);
+  f->partials = (double*)(f->arena + o_part); f->tots = (u64*)(f->arena + o_tots);
+  f->bar = (unsigned*)(f->arena + o_bar); f->sc = (Scalars*)(f->arena + o_sc);
+  f->stage_u = (double*)(f->arena + o_su); f->stage_y = (double*)(f->arena + o_sy);
+  f->wstat = (double*)(f->arena + o_ws); f->scratch = (double*)(f->arena + o_scr);
+#undef CUF
+  rc = llpf_reset(f, 0);
+  if (rc) { llpf_destroy(f); return rc; }
+  f->hsc.t_index = 0;  // PFstate(...,Ref(0)) PFtypes.jl:70 ; reset! sets 1
+  rc = push_scalars(f);
+  if (rc) { llpf_destroy(f); return rc; }
+  *out = f;
+  return LLPF_OK;
+}
+
+extern "C" int llpf_reset(llpf_handle h, uint64_t epoch) {
+  OKR(check_handle(h));
+  CU(cudaSetDevice(h->device));
+  h->epoch = epoch;
+  CU(h->init(h, epoch));
+  h->launches += 1;
+  Scalars s;
+  std::memset(&s, 0, sizeof(s));
+  s.t_index = 1;          // filtering.jl:13
+  s.cur = 0;
+  s.uniform = 1;          // w = -log N, we = 1/N   filtering.jl:11-12
+  s.stats_valid = 1;
+  s.ess = (double)h->N;
+  s.j_identity = 1;
+  h->hsc = s;
+  return push_scalars(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launching the engine
+// ------------------------------------------------------------------------------------------------
+static void base_params(llpf_filter* f, EngineP& P) {
+  std::memset(&P, 0, sizeof(P));
+  P.x[0] = f->x[0]; P.x[1] = f->x[1]; P.ld = f->ld;
+  P.w = f->w; P.lam = f->lam; P.bins = f->bins; P.j = f->j;
+  P.bar = f->bar; P.partials = f->partials; P.tots = f->tots; P.sc = f->sc;
+  P.N = f->N; P.n = f->n; P.first = f->first;
+  P.filter = f->cfg.filter;
+  P.Ts = f->cfg.Ts;
+  P.thr = f->cfg.resample_threshold;
+  P.strategy = f->cfg.resampling;
+  P.scan_mode = f->cfg.scan_mode;
+  long long nb = (f->n + BLOCK - 1) / BLOCK;
+  if (nb > f->max_blocks) nb = f->max_blocks;
+  if (nb < 1) nb = 1;
+  P.nblocks = (int)nb;
+  P.chunk = (f->n + nb - 1) / nb;
+  P.key = RngKey{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)f->epoch << 8};
+  P.rank = 0; P.world = 1;
+  P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
+}
+
+static int launch(llpf_filter* f, const EngineP& P, bool timed) {
+  CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned), f->stream));
+  if (timed) CU(cudaEventRecord(f->ev0, f->stream));
+  CU(f->launch(f, P));
+  f->launches += 1;
+  if (timed) CU(cudaEventRecord(f->ev1, f->stream));
+  OKR(sync_scalars(f));
+  if (timed) CU(cudaEventElapsedTime(&f->last_ms, f->ev0, f->ev1));
+  return LLPF_OK;
+}
+
+static int stage_inputs(llpf_filter* f, const double* u, const double* y0, const double* y1) {
+  const int nu = f->hm.nu, ny = f->hm.ny;
+  if (nu > 0) {
+    if (!u) return fail(LLPF_ERR_BAD_ARG, "u is null");
+    CU(cudaMemcpyAsync(f->stage_u, u, sizeof(double) * nu, cudaMemcpyHostToDevice, f->stream));
+  }
+  if (y0) CU(cudaMemcpyAsync(f->stage_y, y0, sizeof(double) * ny, cudaMemcpyHostToDevice, f->stream));
+  if (y1) CU(cudaMemcpyAsync(f->stage_y + ny, y1, sizeof(double) * ny, cudaMemcpyHostToDevice, f->stream));
+  return LLPF_OK;
+}
+
+static bool is_aux(const llpf_filter* f) { return f->cfg.filter >= LLPF_FILTER_AUX; }
+
+static int finish_ll(llpf_filter* f, double* ll) {
+  if (ll) *ll = f->hsc.ll_last;
+  if (f->hsc.nonfinite) {
+    f->hsc.nonfinite = 0;
+    OKR(push_scalars(f));
+    return fail(LLPF_ERR_NONFINITE, "log-likelihood is not finite (weight collapse)");
+  }
+  return LLPF_OK;
+}
+
+extern "C" int llpf_correct(llpf_handle h, const double* u, const double* y, double t, double* ll) {
+  OKR(check_handle(h));
+  if (!y) return fail(LLPF_ERR_BAD_ARG, "y is null");
+  CU(cudaSetDevice(h->device));
+  OKR(stage_inputs(h, u, y, nullptr));
+  EngineP P;
+  base_params(h, P);
+  P.u = h->stage_u; P.y = h->stage_y;
+  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
+  if (is_aux(h)) { P.prog = 2; } else { P.prog = 0; P.lead_w = 1; P.trail_p = 0; }
+  OKR(launch(h, P, false));
+  return finish_ll(h, ll);
+}
+
+extern "C" int llpf_predict(llpf_handle h, const double* u, double t) {
+  OKR(check_handle(h));
+  if (is_aux(h)) return fail(LLPF_ERR_BAD_ARG, "AuxiliaryParticleFilter: use llpf_predict_aux(u, y1, t)");
+  CU(cudaSetDevice(h->device));
+  OKR(stage_inputs(h, u, nullptr, nullptr));
+  EngineP P;
+  base_params(h, P);
+  P.u = h->stage_u; P.y = h->stage_y;
+  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 0;
+  P.prog = 0; P.trail_p = 1;
+  if (!h->hsc.stats_valid) { P.lead_w = 1; P.lead_skip = 1; }  // refresh ESS (shouldresample, resample.jl:5-10)
+  return launch(h, P, false);
+}
+
+extern "C" int llpf_predict_aux(llpf_handle h, const double* u, const double* y1, double t) {
+  OKR(check_handle(h));
+  if (!is_aux(h)) return fail(LLPF_ERR_BAD_ARG, "llpf_predict_aux needs an AuxiliaryParticleFilter");
+  if (!y1) return fail(LLPF_ERR_BAD_ARG, "y1 is null");
+  CU(cudaSetDevice(h->device));
+  OKR(stage_inputs(h, u, y1, nullptr));
+  EngineP P;
+  base_params(h, P);
+  P.u = h->stage_u; P.y = h->stage_y;
+  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
+  P.prog = 3;
+  return launch(h, P, false);
+}
+
+extern "C" int llpf_update(llpf_handle h, const double* u, const double* y, const double* y1, double t,
+                           double* ll) {
+  OKR(check_handle(h));
+  if (!y) return fail(LLPF_ERR_BAD_ARG, "y is null");
+  CU(cudaSetDevice(h->device));
+  EngineP P;
+  base_params(h, P);
+  P.u = h->stage_u; P.y = h->stage_y;
+  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
+  if (is_aux(h)) {
+    if (!y1) return fail(LLPF_ERR_BAD_ARG, "update!(pfa,u,y,y1): y1 is null");
+    OKR(stage_inputs(h, u, y, y1));
+    P.prog = 4;
+  } else {
+    OKR(stage_inputs(h, u, y, nullptr));
+    P.prog = 0; P.lead_w = 1; P.trail_p = 1;
+  }
+  OKR(launch(h, P, false));
+  return finish_ll(h, ll);
+}
+
+// ------------------------------------------------------------------------------------------------
+// trajectory drivers
+// ------------------------------------------------------------------------------------------------
+static int ensure_run_buffers(llpf_filter* f, long long T) {
+  if (T <= f->cap_T) return LLPF_OK;
+  cudaFree(f->d_u); cudaFree(f->d_y); cudaFree(f->d_ll); cudaFree(f->d_ess); cudaFree(f->d_xhat);
+  cudaFree(f->d_res);
+  f->d_u = f->d_y = f->d_ll = f->d_ess = f->d_xhat = nullptr; f->d_res = nullptr; f->cap_T = 0;
+  const int nu = f->hm.nu > 0 ? f->hm.nu : 1;
+  CU(cudaMalloc(&f->d_u, sizeof(double) * T * nu));
+  CU(cudaMalloc(&f->d_y, sizeof(double) * T * f->hm.ny));
+  CU(cudaMalloc(&f->d_ll, sizeof(double) * T));
+  CU(cudaMalloc(&f->d_ess, sizeof(double) * T));
+  CU(cudaMalloc(&f->d_xhat, sizeof(double) * T * f->hm.nx));
+  CU(cudaMalloc(&f->d_res, sizeof(int) * T));
+  f->cap_T = T;
+  return LLPF_OK;
+}
+
+static int run_impl(llpf_filter* f, long long T, const double* u_dev, const double* y_dev,
+                    int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out) {
+  if (T < 1 || T > (1ll << 30)) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  OKR(llpf_reset(f, epoch));
+  EngineP P;
+  base_params(f, P);
+  P.u = u_dev; P.y = y_dev;
+  P.T = (int)T;
+  // APF passes t=(k-1)*Ts explicitly in both drivers (filtering.jl:376, smoothing.jl:234-235)
+  P.time_conv = is_aux(f) ? 0 : (time_convention == LLPF_TIME_LOGLIK ? 1 : 0);
+  if (is_aux(f)) {
+    P.prog = 1;
+    P.aux_tail_pf = (time_convention == LLPF_TIME_LOGLIK) ? 1 : 0;
+  } else {
+    P.prog = 0; P.lead_w = 1; P.trail_p = 1;
+  }
+  double *xh = nullptr, *wh = nullptr, *weh = nullptr;
+  const size_t NT = (size_t)f->N * (size_t)T;
+  if (out) {
+    P.ll_steps = out->ll_steps ? f->d_ll : nullptr;
+    P.ess_steps = out->ess_steps ? f->d_ess : nullptr;
+    P.resampled = out->resampled ? f->d_res : nullptr;
+    P.xhat = out->xhat ? f->d_xhat : nullptr;
+    P.want_xhat = out->xhat ? 1 : 0;
+    if (out->x_hist) { CU(cudaMalloc(&xh, NT * f->hm.nx * 8)); P.x_hist = xh; }
+    if (out->w_hist || out->we_hist) {
+      CU(cudaMalloc(&wh, NT * 8));
+      CU(cudaMalloc(&weh, NT * 8));
+      P.w_hist = wh; P.we_hist = weh;
+    }
+    if (P.resampled) CU(cudaMemsetAsync(f->d_res, 0, sizeof(int) * T, f->stream));
+  }
+  int rc = launch(f, P, true);
+  if (rc == LLPF_OK && out) {
+    cudaError_t e = cudaSuccess;
+    if (out->ll_steps) e = cudaMemcpyAsync(out->ll_steps, f->d_ll, 8 * T, cudaMemcpyDeviceToHost, f->stream);
+    if (!e && out->ess_steps) e = cudaMemcpyAsync(out->ess_steps, f->d_ess, 8 * T, cudaMemcpyDeviceToHost, f->stream);
+    if (!e && out->resampled) e = cudaMemcpyAsync(out->resampled, f->d_res, 4 * T, cudaMemcpyDeviceToHost, f->stream);
+    if (!e && out->xhat) e = cudaMemcpyAsync(out->xhat, f->d_xhat, 8 * T * f->hm.nx, cudaMemcpyDeviceToHost, f->stream);
+    if (!e && out->x_hist) e = cudaMemcpyAsync(out->x_hist, xh, NT * f->hm.nx * 8, cudaMemcpyDeviceToHost, f->stream);
+    if (!e && out->w_hist) e = cudaMemcpyAsync(out->w_hist, wh, NT * 8, cudaMemcpyDeviceToHost, f->stream);
+    if (!e && out->we_hist) e = cudaMemcpyAsync(out->we_hist, weh, NT * 8, cudaMemcpyDeviceToHost, f->stream);
+    if (!e) e = cudaStreamSynchronize(f->stream);
+    if (e) rc = fail(LLPF_ERR_CUDA, std::string("copying run outputs: ") + cudaGetErrorString(e));
+  }
+  cudaFree(xh); cudaFree(wh); cudaFree(weh);
+  if (rc) return rc;
+  if (ll) *ll = f->hsc.ll_total;
+  if (f->hsc.nonfinite) return fail(LLPF_ERR_NONFINITE, "log-likelihood is not finite (weight collapse)");
+  return LLPF_OK;
+}
+
+extern "C" int llpf_run(llpf_handle h, int64_t T, const double* u, const double* y,
+                        int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out) {
+  OKR(check_handle(h));
+  if (!y || (h->hm.nu > 0 && !u)) return fail(LLPF_ERR_BAD_ARG, "u / y is null");
+  if (T < 1) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  CU(cudaSetDevice(h->device));
+  OKR(ensure_run_buffers(h, T));
+  if (h->hm.nu > 0)
+    CU(cudaMemcpyAsync(h->d_u, u, sizeof(double) * T * h->hm.nu, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_y, y, sizeof(double) * T * h->hm.ny, cudaMemcpyHostToDevice, h->stream));
+  return run_impl(h, T, h->d_u, h->d_y, time_convention, epoch, ll, out);
+}
+
+extern "C" int llpf_run_dev(llpf_handle h, int64_t T, const double* u_dev, const double* y_dev,
+                            int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out) {
+  OKR(check_handle(h));
+  if (!y_dev || (h->hm.nu > 0 && !u_dev)) return fail(LLPF_ERR_BAD_ARG, "u_dev / y_dev is null");
+  if (T < 1) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  CU(cudaSetDevice(h->device));
+  OKR(ensure_run_buffers(h, T));
+  return run_impl(h, T, u_dev, y_dev, time_convention, epoch, ll, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// accessors
+// ------------------------------------------------------------------------------------------------
+static int grid_for(long long n, int sms) {
+  long long g = (n + 255) / 256;
+  if (g > (long long)sms * 8) g = (long long)sms * 8;
+  return g < 1 ? 1 : (int)g;
+}
+
+extern "C" int llpf_num_particles(llpf_handle h, int64_t* N) {
+  OKR(check_handle(h));
+  if (!N) return fail(LLPF_ERR_BAD_ARG, "null");
+  *N = h->N;
+  return LLPF_OK;
+}
+extern "C" int llpf_local_particles(llpf_handle h, int64_t* n, int64_t* first) {
+  OKR(check_handle(h));
+  if (n) *n = h->n;
+  if (first) *first = h->first;
+  return LLPF_OK;
+}
+extern "C" int llpf_index(llpf_handle h, int64_t* t) {
+  OKR(check_handle(h));
+  if (!t) return fail(LLPF_ERR_BAD_ARG, "null");
+  *t = h->hsc.t_index;
+  return LLPF_OK;
+}
+extern "C" int llpf_get_particles(llpf_handle h, double* x) {
+  OKR(check_handle(h));
+  if (!x) return fail(LLPF_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  k_export_x<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->scratch);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaMemcpyAsync(x, h->scratch, sizeof(double) * h->n * h->hm.nx, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LLPF_OK;
+}
+// at every API boundary xprev == x (copyto!(xprev,x) closes predict!, filtering.jl:151; reset! :8-9)
+extern "C" int llpf_get_xprev(llpf_handle h, double* x) { return llpf_get_particles(h, x); }
+
+static int materialise(llpf_filter* h, double* w_host, double* we_host) {
+  CU(cudaSetDevice(h->device));
+  double* dw = h->scratch;
+  double* dwe = h->scratch + h->ld;
+  k_materialise<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->w, h->sc, h->n, h->N, dw, dwe);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  if (w_host) CU(cudaMemcpyAsync(w_host, dw, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (we_host) CU(cudaMemcpyAsync(we_host, dwe, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LLPF_OK;
+}
+extern "C" int llpf_get_weights(llpf_handle h, double* w) {
+  OKR(check_handle(h));
+  if (!w) return fail(LLPF_ERR_BAD_ARG, "null");
+  return materialise(h, w, nullptr);
+}
+extern "C" int llpf_get_expweights(llpf_handle h, double* we) {
+  OKR(check_handle(h));
+  if (!we) return fail(LLPF_ERR_BAD_ARG, "null");
+  return materialise(h, nullptr, we);
+}
+extern "C" int llpf_get_ancestors(llpf_handle h, int64_t* j) {
+  OKR(check_handle(h));
+  if (!j) return fail(LLPF_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  long long* dj = reinterpret_cast<long long*>(h->scratch);
+  k_export_j<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->j, h->hsc.j_identity, h->n, h->first, dj);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaMemcpyAsync(j, dj, sizeof(long long) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LLPF_OK;
+}
+extern "C" int llpf_get_bins(llpf_handle h, double* bins) {
+  OKR(check_handle(h));
+  if (!bins) return fail(LLPF_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(bins, h->bins, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return LLPF_OK;
+}
+extern "C" int llpf_set_state(llpf_handle h, const double* x, const double* w, int64_t t) {
+  OKR(check_handle(h));
+  if (!x || !w) return fail(LLPF_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->scratch, x, sizeof(double) * h->n * h->hm.nx, cudaMemcpyHostToDevice, h->stream));
+  k_import_x<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->scratch);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaMemcpyAsync(h->w, w, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+  h->hsc.uniform = 0; h->hsc.pend = 0; h->hsc.stats_ahead = 0; h->hsc.stats_valid = 0;
+  h->hsc.j_identity = 1; h->hsc.t_index = t;
+  return push_scalars(h);
+}
+
+// (sum we, sum we^2, sum we*x) on the materialised expweights, block partials finished on the host
+static int weight_stats(llpf_filter* h, double* s, double* q, double* sx) {
+  CU(cudaSetDevice(h->device));
+  double* dwe = h->scratch + h->ld;
+  k_materialise<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->w, h->sc, h->n, h->N, nullptr, dwe);
+  const int grid = std::min(grid_for(h->n, h->num_sms), 256);
+  k_wstats<<<grid, 256, 0, h->stream>>>(dwe, h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->wstat);
+  CU(cudaGetLastError());
+  h->launches += 2;
+  std::vector<double> part((size_t)grid * (2 + MAX_NX));
+  CU(cudaMemcpyAsync(part.data(), h->wstat, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  double acc[2 + MAX_NX] = {0};
+  for (int b = 0; b < grid; ++b)
+    for (int k = 0; k < 2 + MAX_NX; ++k) acc[k] += part[(size_t)b * (2 + MAX_NX) + k];
+  if (s) *s = acc[0];
+  if (q) *q = acc[1];
+  if (sx) for (int d = 0; d < h->hm.nx; ++d) sx[d] = acc[2 + d];
+  return LLPF_OK;
+}
+extern "C" int llpf_effective_particles(llpf_handle h, double* ess) {
+  OKR(check_handle(h));
+  if (!ess) return fail(LLPF_ERR_BAD_ARG, "null");
+  double q = 0;
+  OKR(weight_stats(h, nullptr, &q, nullptr));
+  *ess = 1.0 / q;  // 1/sum(abs2, we)  resample.jl:2
+  return LLPF_OK;
+}
+extern "C" int llpf_shouldresample(llpf_handle h, int32_t* yes) {
+  OKR(check_handle(h));
+  if (!yes) return fail(LLPF_ERR_BAD_ARG, "null");
+  if (h->cfg.resample_threshold == 1.0) { *yes = 1; return LLPF_OK; }
+  double ess = 0;
+  OKR(llpf_effective_particles(h, &ess));
+  *yes = ess < (double)h->N * h->cfg.resample_threshold ? 1 : 0;
+  return LLPF_OK;
+}
+extern "C" int llpf_weighted_mean(llpf_handle h, double* xhat) {
+  OKR(check_handle(h));
+  if (!xhat) return fail(LLPF_ERR_BAD_ARG, "null");
+  double s = 0;
+  OKR(weight_stats(h, &s, nullptr, xhat));
+  // @assert sum(we) ≈ 1  filtering.jl:542
+  if (!(std::fabs(s - 1.0) <= 1e-6)) return fail(LLPF_ERR_NONFINITE, "weights do not sum to one");
+  return LLPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone numerics
+// ------------------------------------------------------------------------------------------------
+struct Scratchpad {  // tiny RAII arena for the stand-alone calls
+  std::vector<void*> ptrs;
+  ~Scratchpad() { for (void* p : ptrs) cudaFree(p); }
+  template <class T>
+  cudaError_t alloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
+static int standalone_geometry(int device, long long n, EngineP& P, const void* kernel) {
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  int occ = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BLOCK, 0));
+  if (occ < 1) return fail(LLPF_ERR_CUDA, "stand-alone kernel does not fit");
+  long long nb = (n + BLOCK - 1) / BLOCK;
+  const long long cap = std::min<long long>((long long)occ * prop.multiProcessorCount, MAX_BLOCKS - 1);
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  P.nblocks = (int)nb;
+  P.chunk = (n + nb - 1) / nb;
+  return LLPF_OK;
+}
+
+static int resample_standalone(int strategy, int64_t N, const double* we, double u01, const double* u_slots,
+                               int64_t M, int64_t* j_inout, double* bins_out, int32_t scan_mode, int32_t device) {
+  if (N < 1 || M < 1 || !we || !j_inout) return fail(LLPF_ERR_BAD_ARG, "bad argument");
+  if (N >= (1ll << 31) || M >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "N, M < 2^31");
+  int ndev = 0;
+  OKR(llpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(LLPF_ERR_NO_DEVICE, "no such CUDA device");
+  EngineP P;
+  std::memset(&P, 0, sizeof(P));
+  OKR(standalone_geometry(device, N, P, (const void*)k_resample));
+  Scratchpad sp;
+  double *d_we = nullptr, *d_bins = nullptr, *d_part = nullptr, *d_us = nullptr;
+  u64* d_tots = nullptr;
+  unsigned* d_bar = nullptr;
+  long long* d_j = nullptr;
+  CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_bins, (size_t)N)); CU(sp.alloc(&d_part, (size_t)MAX_BLOCKS * PS));
+  CU(sp.alloc(&d_tots, (size_t)MAX_BLOCKS)); CU(sp.alloc(&d_bar, 64)); CU(sp.alloc(&d_j, (size_t)M));
+  CU(cudaMemcpy(d_we, we, sizeof(double) * N, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_j, j_inout, sizeof(long long) * M, cudaMemcpyHostToDevice));
+  CU(cudaMemset(d_bar, 0, 64 * sizeof(unsigned)));
+  if (u_slots) {
+    CU(sp.alloc(&d_us, (size_t)M));
+    CU(cudaMemcpy(d_us, u_slots, sizeof(double) * M, cudaMemcpyHostToDevice));
+  }
+  // power-of-two fixed-point scale so that sum(we)*scale stays below 2^62 (exact for normalised weights)
+  double sum = 0.0;
+  for (int64_t i = 0; i < N; ++i) sum += (we[i] > 0 ? we[i] : 0.0);
+  int e = 0;
+  if (sum > 0 && std::isfinite(sum)) std::frexp(sum * (1.0 + 1e-9), &e);   // sum < 2^e
+  if (e < 0) e = 0;
+  P.fix_scale = std::ldexp(1.0, 62 - e);
+  P.fix_inv = std::ldexp(1.0, e - 62);
+  P.bins = d_bins; P.partials = d_part; P.tots = d_tots; P.bar = d_bar;
+  P.N = N; P.n = N; P.first = 0; P.strategy = strategy; P.scan_mode = scan_mode;
+  P.world = 1;
+  const double* d_us_c = d_us;
+  long long Mll = M;
+  void* args[] = {(void*)&P, (void*)&d_we, (void*)&u01, (void*)&d_us_c, (void*)&Mll, (void*)&d_j};
+  CU(cudaLaunchCooperativeKernel((const void*)k_resample, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(j_inout, d_j, sizeof(long long) * M, cudaMemcpyDeviceToHost));
+  if (bins_out) CU(cudaMemcpy(bins_out, d_bins, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  return LLPF_OK;
+}
+
+extern "C" int llpf_resample_systematic(int64_t N, const double* we, double u01, int64_t M, int64_t* j_inout,
+                                        double* bins_out, int32_t scan_mode, int32_t device) {
+  return resample_standalone(LLPF_RESAMPLE_SYSTEMATIC, N, we, u01, nullptr, M, j_inout, bins_out, scan_mode, device);
+}
+extern "C" int llpf_resample_stratified(int64_t N, const double* we, const double* u01, int64_t M,
+                                        int64_t* j_inout, double* bins_out, int32_t scan_mode, int32_t device) {
+  if (!u01) return fail(LLPF_ERR_BAD_ARG, "u01 is null");
+  return resample_standalone(LLPF_RESAMPLE_STRATIFIED, N, we, 0.0, u01, M, j_inout, bins_out, scan_mode, device);
+}
+
+extern "C" int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int32_t device) {
+  if (N < 1 || !w || !we || !ll) return fail(LLPF_ERR_BAD_ARG, "bad argument");
+  int ndev = 0;
+  OKR(llpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(LLPF_ERR_NO_DEVICE, "no such CUDA device");
+  EngineP P;
+  std::memset(&P, 0, sizeof(P));
+  OKR(standalone_geometry(device, N, P, (const void*)k_logsumexp));
+  Scratchpad sp;
+  double *d_w = nullptr, *d_we = nullptr, *d_part = nullptr, *d_ll = nullptr;
+  unsigned* d_bar = nullptr;
+  CU(sp.alloc(&d_w, (size_t)N)); CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_part, (size_t)MAX_BLOCKS * PS));
+  CU(sp.alloc(&d_ll, 1)); CU(sp.alloc(&d_bar, 64));
+  CU(cudaMemcpy(d_w, w, sizeof(double) * N, cudaMemcpyHostToDevice));
+  CU(cudaMemset(d_bar, 0, 64 * sizeof(unsigned)));
+  P.partials = d_part; P.bar = d_bar; P.N = N; P.n = N; P.world = 1;
+  void* args[] = {(void*)&P, (void*)&d_w, (void*)&d_we, (void*)&d_ll};
+  CU(cudaLaunchCooperativeKernel((const void*)k_logsumexp, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(w, d_w, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(we, d_we, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(ll, d_ll, sizeof(double), cudaMemcpyDeviceToHost));
+  return LLPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU (peer-memory exchange) — filled in by llpf_shard.cu once enabled
+// ------------------------------------------------------------------------------------------------
+extern "C" int llpf_shard_blob_size(size_t* bytes) {
+  if (!bytes) return fail(LLPF_ERR_BAD_ARG, "null");
+  *bytes = 256;
+  return LLPF_OK;
+}
+extern "C" int llpf_shard_export(llpf_handle h, void* blob) {
+  OKR(check_handle(h));
+  (void)blob;
+  return fail(LLPF_ERR_UNSUPPORTED, "sharded filters are not available in this build");
+}
+extern "C" int llpf_shard_connect(llpf_handle h, const void* blobs) {
+  OKR(check_handle(h));
+  (void)blobs;
+  return fail(LLPF_ERR_UNSUPPORTED, "sharded filters are not available in this build");
+}
+
+// ------------------------------------------------------------------------------------------------
+// instrumentation
+// ------------------------------------------------------------------------------------------------
+extern "C" int llpf_launch_count(llpf_handle h, int64_t* launches) {
+  OKR(check_handle(h));
+  if (!launches) return fail(LLPF_ERR_BAD_ARG, "null");
+  *launches = h->launches;
+  return LLPF_OK;
+}
+extern "C" int llpf_last_run_ms(llpf_handle h, float* ms) {
+  OKR(check_handle(h));
+  if (!ms) return fail(LLPF_ERR_BAD_ARG, "null");
+  *ms = h->last_ms;
+  return LLPF_OK;
+}
+extern "C" int llpf_device_pointers(llpf_handle h, void** x_dev, void** w_dev, void** stream) {
+  OKR(check_handle(h));
+  if (x_dev) *x_dev = h->x[h->hsc.cur];
+  if (w_dev) *w_dev = h->w;
+  if (stream) *stream = (void*)h->stream;
+  return LLPF_OK;
+}

@@ -1,0 +1,538 @@
+"""Host-side mirror of the reference's particle-filter API for the accelerated path.
+
+Same names, argument order and return conventions as LowLevelParticleFilters.jl (Julia `f!` -> `f`):
+
+    ParticleFilter(N, dynamics, measurement, dynamics_density, measurement_density, initial_density; kw...)
+        src/PFtypes.jl:65-75        kw: resample_threshold=0.1, resampling_strategy=ResampleSystematic, Ts=1.0
+    AdvancedParticleFilter(N, dynamics, measurement, measurement_likelihood, dynamics_density, initial_density; kw...)
+        src/PFtypes.jl:200-210      kw: resample_threshold=0.5
+    AuxiliaryParticleFilter(pf | args...)                         src/PFtypes.jl:38-49
+    reset(pf) predict(pf,u,p,t) correct(pf,u,y,p,t) update(pf,u,y,p,t) pf(u,y)   src/filtering.jl:4-14,140-191,238-240
+    forward_trajectory(pf,u,y) -> ParticleFilteringSolution       src/filtering.jl:343-384, src/solutions.jl:334-345
+    loglik(pf,u,y)                                                src/smoothing.jl:227-236
+    particles weights expweights num_particles effective_particles shouldresample weighted_mean index
+                                                                  src/PFtypes.jl:296-334, src/resample.jl:1-10
+
+User closures cannot cross the C-ABI, so `dynamics`, `measurement`, the densities and
+`measurement_likelihood` are *descriptors* (LinearDynamics, QuadtankRK4, LinearMeasurement, MvNormal,
+GaussianLikelihood).  `rng=` is replaced by `seed=` (counter-based Philox streams).
+Everything runs through libllpf_b200.so; there is no CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+from ._abi import (DYN_LINEAR, DYN_QUADTANK_RK4, FILTER_ADVANCED, FILTER_AUX, FILTER_AUX_ADVANCED,
+                   FILTER_PF, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC, SCAN_FAST, SCAN_SERIAL,
+                   TIME_FORWARD_TRAJECTORY, TIME_LOGLIK, check)
+
+dp = _abi.c_double_p
+
+
+# ---------------------------------------------------------------------------------------------
+# descriptors
+# ---------------------------------------------------------------------------------------------
+class ResamplingStrategy:  # src/LowLevelParticleFilters.jl:43-46
+    code = None
+
+
+class ResampleSystematic(ResamplingStrategy):
+    code = RESAMPLE_SYSTEMATIC
+
+
+class ResampleStratified(ResamplingStrategy):
+    code = RESAMPLE_STRATIFIED
+
+
+class ResampleResidual(ResamplingStrategy):
+    code = _abi.RESAMPLE_RESIDUAL
+
+
+@dataclass
+class MvNormal:
+    """MvNormal(mu, Sigma) / MvNormal(Sigma) — Distributions.MvNormal or SimpleMvNormal (src/utils.jl:241-273)."""
+    mu: np.ndarray
+    Sigma: np.ndarray = None
+
+    def __post_init__(self):
+        if self.Sigma is None:
+            self.Sigma = np.atleast_2d(np.asarray(self.mu, dtype=np.float64))
+            self.mu = np.zeros(self.Sigma.shape[0])
+        self.mu = np.asarray(self.mu, dtype=np.float64).reshape(-1)
+        S = np.asarray(self.Sigma, dtype=np.float64)
+        if S.ndim == 0:
+            S = float(S) * np.eye(self.mu.size)
+        elif S.ndim == 1:
+            S = np.diag(S)
+        self.Sigma = S
+
+    def __len__(self):
+        return self.mu.size
+
+
+@dataclass
+class LinearDynamics:
+    """dynamics(x,u,p,t) = A*x .+ B*u   (examples/example_lineargaussian.jl:27)"""
+    A: np.ndarray
+    B: np.ndarray = None
+
+
+@dataclass
+class QuadtankRK4:
+    """rk4(quadtank, Ts; supersample) — examples/example_quadtank.jl:91-106,35 ; src/utils.jl:220-237.
+    p = [kc, k1, k2, A, a, gamma]; t_switch/a1_factor reproduce `if t > 500; a1 *= 2` (:15-17)."""
+    p: tuple = (0.5, 1.6, 1.6, 4.9, 0.03, 0.2)
+    Ts: float = 1.0
+    supersample: int = 2
+    t_switch: float = float("inf")
+    a1_factor: float = 1.0
+
+
+@dataclass
+class LinearMeasurement:
+    """measurement(x,u,p,t) = C*x"""
+    C: np.ndarray
+
+
+@dataclass
+class GaussianLikelihood:
+    """measurement_likelihood(x,u,y,p,t) = logpdf(MvNormal(R2), C*x - y)  (example_lineargaussian.jl:238-240)"""
+    C: np.ndarray
+    R2: np.ndarray
+
+
+@dataclass
+class ParticleFilteringSolution:  # src/solutions.jl:334-345
+    f: object
+    u: np.ndarray
+    y: np.ndarray
+    x: np.ndarray      # [T][N][nx]  (reference: N x T Matrix{SVector}; same memory order)
+    w: np.ndarray      # [T][N]
+    we: np.ndarray     # [T][N]
+    ll: float
+    t: np.ndarray
+    extra: dict = field(default_factory=dict)
+
+
+def _colmajor(M, shape):
+    return np.asfortranarray(np.asarray(M, dtype=np.float64).reshape(shape))
+
+
+class _ModelBuffers:
+    """Keeps the column-major arrays alive for as long as the ctypes struct points at them."""
+
+    def __init__(self, dynamics, C_, R1, R2, d0):
+        C_ = np.atleast_2d(np.asarray(C_, dtype=np.float64))
+        ny, nx = C_.shape
+        m = _abi.Model()
+        self.keep = []
+        null = C.cast(None, dp)
+
+        def put(M, shape):
+            a = _colmajor(M, shape)
+            self.keep.append(a)
+            return a.ctypes.data_as(dp)
+
+        if isinstance(dynamics, LinearDynamics):
+            A = np.atleast_2d(np.asarray(dynamics.A, dtype=np.float64))
+            nu = 0 if dynamics.B is None else np.atleast_2d(np.asarray(dynamics.B)).reshape(nx, -1).shape[1]
+            m.dynamics = DYN_LINEAR
+            m.A = put(A, (nx, nx))
+            m.B = put(dynamics.B, (nx, nu)) if nu > 0 else null
+        elif isinstance(dynamics, QuadtankRK4):
+            nu = 2
+            m.dynamics = DYN_QUADTANK_RK4
+            m.A, m.B = null, null
+            for k, v in enumerate(dynamics.p):
+                m.dyn_params[k] = float(v)
+            m.t_switch, m.a1_factor = float(dynamics.t_switch), float(dynamics.a1_factor)
+            m.integ_Ts, m.supersample = float(dynamics.Ts), int(dynamics.supersample)
+        else:
+            raise TypeError("dynamics must be a descriptor (LinearDynamics | QuadtankRK4); closures cannot cross the C-ABI")
+        m.nx, m.nu, m.ny = nx, nu, ny
+        m.C = put(C_, (ny, nx))
+        m.R1 = put(R1, (nx, nx))
+        m.R2 = put(R2, (ny, ny))
+        m.mu0 = put(d0.mu, (nx,))
+        m.Sigma0 = put(d0.Sigma, (nx, nx))
+        self.struct = m
+        self.nx, self.nu, self.ny = nx, nu, ny
+
+
+# ---------------------------------------------------------------------------------------------
+# filters
+# ---------------------------------------------------------------------------------------------
+class AbstractParticleFilter:
+    _filter_code = FILTER_PF
+
+    def _create(self, N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device,
+                rank=0, world=1):
+        self._lib = _abi.load_library()
+        self._model = model
+        cfg = _abi.Config()
+        cfg.N = int(N)
+        cfg.filter = self._filter_code
+        cfg.resampling = resampling_strategy.code
+        cfg.resample_threshold = float(resample_threshold)
+        cfg.Ts = float(Ts)
+        cfg.seed = int(seed)
+        cfg.scan_mode = SCAN_SERIAL if scan_mode in (SCAN_SERIAL, "serial") else SCAN_FAST
+        cfg.device, cfg.rank, cfg.world = int(device), int(rank), int(world)
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        check(self._lib, self._lib.llpf_create(C.byref(cfg), C.byref(model.struct), C.byref(self._h)))
+        self.N = int(N)
+        self.nx, self.nu, self.ny = model.nx, model.nu, model.ny
+        self.Ts = float(Ts)
+        self.resample_threshold = float(resample_threshold)
+        self.resampling_strategy = resampling_strategy
+        self.seed = int(seed)
+        self._epoch = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.llpf_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- helpers
+    def _vec(self, v, n, name):
+        if n == 0:
+            return None, C.cast(None, dp)
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+        if a.size != n:
+            raise ValueError(f"{name} has length {a.size}, expected {n}")
+        return a, a.ctypes.data_as(dp)
+
+    def _default_t(self, t):
+        return index(self) * self.Ts if t is None else float(t)
+
+    def __call__(self, u, y, p=None, t=None):  # (pf::ParticleFilter)(u,y,p,t) filtering.jl:238
+        return update(self, u, y, p, t)
+
+
+class ParticleFilter(AbstractParticleFilter):
+    _filter_code = FILTER_PF
+
+    def __init__(self, N, dynamics, measurement, dynamics_density, measurement_density, initial_density, *,
+                 resample_threshold=0.1, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
+                 scan_mode="fast", device=0, p=None, **_ignored):
+        if not isinstance(measurement, LinearMeasurement):
+            raise TypeError("measurement must be a LinearMeasurement descriptor")
+        self.dynamics, self.measurement = dynamics, measurement
+        self.dynamics_density, self.measurement_density = dynamics_density, measurement_density
+        self.initial_density = initial_density
+        model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
+                              initial_density)
+        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device)
+
+
+class AdvancedParticleFilter(AbstractParticleFilter):
+    _filter_code = FILTER_ADVANCED
+
+    def __init__(self, N, dynamics, measurement, measurement_likelihood, dynamics_density, initial_density, *,
+                 resample_threshold=0.5, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
+                 scan_mode="fast", device=0, p=None, **_ignored):
+        if not isinstance(measurement_likelihood, GaussianLikelihood):
+            raise TypeError("measurement_likelihood must be a GaussianLikelihood descriptor")
+        self.dynamics, self.measurement = dynamics, measurement
+        self.measurement_likelihood = measurement_likelihood
+        self.dynamics_density, self.initial_density = dynamics_density, initial_density
+        model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
+                              measurement_likelihood.R2, initial_density)
+        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device)
+
+
+class AuxiliaryParticleFilter(AbstractParticleFilter):
+    """AuxiliaryParticleFilter(pf) or AuxiliaryParticleFilter(args...; kwargs...)  PFtypes.jl:38-49"""
+
+    def __init__(self, *args, **kwargs):
+        if len(args) == 1 and isinstance(args[0], AbstractParticleFilter):
+            inner = args[0]
+            adv = isinstance(inner, AdvancedParticleFilter)
+            cfg = inner._cfg
+            self.pf = inner
+            self._filter_code = FILTER_AUX_ADVANCED if adv else FILTER_AUX
+            for name in ("dynamics", "measurement", "dynamics_density", "initial_density"):
+                setattr(self, name, getattr(inner, name))
+            self._create(inner.N, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
+                         inner.seed, cfg.scan_mode, cfg.device)
+        else:
+            self.__init__(ParticleFilter(*args, **kwargs))
+
+    def __call__(self, u, y, y1, p=None, t=None):  # (pf::AuxiliaryParticleFilter)(u,y,y1,p,t) filtering.jl:239
+        return update(self, u, y, p, t, y1=y1)
+
+
+# ---------------------------------------------------------------------------------------------
+# verbs
+# ---------------------------------------------------------------------------------------------
+def reset(pf, epoch=None):
+    """reset!(pf)  filtering.jl:4-14.  Successive calls advance to a fresh RNG epoch unless one is given."""
+    if epoch is None:
+        pf._epoch += 1
+        epoch = pf._epoch
+    else:
+        pf._epoch = int(epoch)
+    check(pf._lib, pf._lib.llpf_reset(pf._h, int(epoch)))
+
+
+def correct(pf, u, y, p=None, t=None):
+    """correct!(pf,u,y,p,t) -> (ll, 0)  filtering.jl:164-174"""
+    _, up = pf._vec(u, pf.nu, "u")
+    ya, yp = pf._vec(y, pf.ny, "y")
+    ll = C.c_double()
+    check(pf._lib, pf._lib.llpf_correct(pf._h, up, yp, pf._default_t(t), C.byref(ll)))
+    return ll.value, 0
+
+
+def predict(pf, u, p=None, t=None, y1=None):
+    """predict!(pf,u,p,t) filtering.jl:140-153 ; predict!(pfa,u,y1,p,t) :195-234"""
+    _, up = pf._vec(u, pf.nu, "u")
+    if isinstance(pf, AuxiliaryParticleFilter):
+        if y1 is None:
+            raise TypeError("predict!(pfa, u, y1, p, t) needs y1")
+        _, y1p = pf._vec(y1, pf.ny, "y1")
+        check(pf._lib, pf._lib.llpf_predict_aux(pf._h, up, y1p, pf._default_t(t)))
+    else:
+        check(pf._lib, pf._lib.llpf_predict(pf._h, up, pf._default_t(t)))
+
+
+def update(pf, u, y, p=None, t=None, y1=None):
+    """update!(f,u,y,p,t) filtering.jl:181-185 ; update!(pfa,u,y,y1,p,t) :187-191.  Returns (ll, 0)."""
+    _, up = pf._vec(u, pf.nu, "u")
+    _, yp = pf._vec(y, pf.ny, "y")
+    null = C.cast(None, dp)
+    y1p = null
+    if isinstance(pf, AuxiliaryParticleFilter):
+        if y1 is None:
+            raise TypeError("update!(pfa, u, y, y1, p, t) needs y1")
+        _, y1p = pf._vec(y1, pf.ny, "y1")
+    ll = C.c_double()
+    check(pf._lib, pf._lib.llpf_update(pf._h, up, yp, y1p, pf._default_t(t), C.byref(ll)))
+    return ll.value, 0
+
+
+def _traj_inputs(pf, u, y):
+    y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1, pf.ny))
+    T = y.shape[0]
+    if pf.nu > 0:
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(-1, pf.nu))
+        if u.shape[0] != T:
+            raise ValueError("u and y must have the same number of time steps")
+        up = u.ctypes.data_as(dp)
+    else:
+        u, up = None, C.cast(None, dp)
+    return u, up, y, y.ctypes.data_as(dp), T
+
+
+def _run(pf, u, y, conv, history, epoch, want_steps=True, want_xhat=True):
+    u, up, y, yp, T = _traj_inputs(pf, u, y)
+    if epoch is None:
+        pf._epoch += 1
+        epoch = pf._epoch
+    else:
+        pf._epoch = int(epoch)
+    out = _abi.RunOutputs()
+    res = {}
+    null = C.cast(None, dp)
+    if want_steps:
+        res["ll_steps"] = np.zeros(T)
+        res["ess"] = np.zeros(T)
+        res["resampled"] = np.zeros(T, dtype=np.int32)
+        out.ll_steps = res["ll_steps"].ctypes.data_as(dp)
+        out.ess_steps = res["ess"].ctypes.data_as(dp)
+        out.resampled = res["resampled"].ctypes.data_as(_abi.c_int32_p)
+    if want_xhat:
+        res["xhat"] = np.zeros((T, pf.nx))
+        out.xhat = res["xhat"].ctypes.data_as(dp)
+    if history:
+        res["x"] = np.zeros((T, pf.N, pf.nx))
+        res["w"] = np.zeros((T, pf.N))
+        res["we"] = np.zeros((T, pf.N))
+        out.x_hist = res["x"].ctypes.data_as(dp)
+        out.w_hist = res["w"].ctypes.data_as(dp)
+        out.we_hist = res["we"].ctypes.data_as(dp)
+    else:
+        out.x_hist = out.w_hist = out.we_hist = null
+    ll = C.c_double()
+    check(pf._lib, pf._lib.llpf_run(pf._h, T, up, yp, conv, int(epoch), C.byref(ll), C.byref(out)))
+    res["ll"] = ll.value
+    res["u"], res["y"], res["T"] = u, y, T
+    return res
+
+
+def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None):
+    """forward_trajectory(pf,u,y,p) -> ParticleFilteringSolution   filtering.jl:343-384.
+    history=False skips the N x T x/w/we arrays (they are then None); the per-step ll, ESS,
+    resample flags and weighted means are always returned in `sol.extra`."""
+    r = _run(pf, u, y, TIME_FORWARD_TRAJECTORY, history, epoch)
+    t = np.arange(r["T"]) * pf.Ts  # range(0, step=Ts, length=T)  solutions.jl:345
+    extra = {k: r[k] for k in ("ll_steps", "ess", "resampled", "xhat")}
+    return ParticleFilteringSolution(pf, r["u"], r["y"], r.get("x"), r.get("w"), r.get("we"), r["ll"], t, extra)
+
+
+def loglik(pf, u, y, p=None, *, epoch=None, details=False):
+    """loglik(pf,u,y,p)  smoothing.jl:227-236"""
+    r = _run(pf, u, y, TIME_LOGLIK, False, epoch, want_steps=details, want_xhat=False)
+    return r if details else r["ll"]
+
+
+def mean_trajectory(*args, **kw):
+    """mean_trajectory(sol) / mean_trajectory(x, we)  filtering.jl:417,436-438 -> T x nx ;
+    mean_trajectory(pf,u,y) filtering.jl:393 -> (xhat, ll) through reduce_trajectory (:421-434)."""
+    if len(args) == 1 and isinstance(args[0], ParticleFilteringSolution):
+        sol = args[0]
+        if sol.x is None:
+            return sol.extra["xhat"]
+        return np.einsum("tnd,tn->td", sol.x, sol.we)
+    if len(args) == 2:
+        x, we = args
+        return np.einsum("tnd,tn->td", np.asarray(x), np.asarray(we))
+    pf, u, y = args[:3]
+    # reduce_trajectory: correct!(u[1],y[1],t=0); then pf(u[t-1], y[t], t=(t-1)Ts) for t=2..T
+    yv = np.asarray(y, dtype=np.float64).reshape(-1, pf.ny)
+    uv = np.asarray(u, dtype=np.float64).reshape(yv.shape[0], -1)
+    reset(pf, kw.get("epoch"))
+    ll = correct(pf, uv[0], yv[0], None, 0.0)[0]
+    xh = [weighted_mean(pf)]
+    for t in range(1, yv.shape[0]):
+        ll += update(pf, uv[t - 1], yv[t], None, t * pf.Ts)[0]
+        xh.append(weighted_mean(pf))
+    return np.array(xh), ll
+
+
+def mode_trajectory(sol):
+    """mode_trajectory(sol)  filtering.jl:427,434 — particle with the largest weight at each step"""
+    idx = np.argmax(sol.we, axis=1)
+    return sol.x[np.arange(sol.x.shape[0]), idx]
+
+
+# ---------------------------------------------------------------------------------------------
+# accessors (PFtypes.jl:296-334)
+# ---------------------------------------------------------------------------------------------
+def num_particles(pf):
+    n = C.c_int64()
+    check(pf._lib, pf._lib.llpf_num_particles(pf._h, C.byref(n)))
+    return n.value
+
+
+def index(pf):
+    t = C.c_int64()
+    check(pf._lib, pf._lib.llpf_index(pf._h, C.byref(t)))
+    return t.value
+
+
+def _get(pf, fn, shape, dtype=np.float64):
+    a = np.zeros(shape, dtype=dtype)
+    ptr = a.ctypes.data_as(dp if dtype == np.float64 else _abi.c_int64_p)
+    check(pf._lib, fn(pf._h, ptr))
+    return a
+
+
+def particles(pf):
+    return _get(pf, pf._lib.llpf_get_particles, (pf.N, pf.nx))
+
+
+def weights(pf):
+    return _get(pf, pf._lib.llpf_get_weights, (pf.N,))
+
+
+def expweights(pf):
+    return _get(pf, pf._lib.llpf_get_expweights, (pf.N,))
+
+
+def ancestors(pf):
+    """state(pf).j (1-based)"""
+    return _get(pf, pf._lib.llpf_get_ancestors, (pf.N,), np.int64)
+
+
+def bins(pf):
+    return _get(pf, pf._lib.llpf_get_bins, (pf.N,))
+
+
+def state(pf):
+    x = particles(pf)
+    return dict(x=x, xprev=x.copy(), w=weights(pf), we=expweights(pf), j=ancestors(pf), bins=bins(pf), t=index(pf))
+
+
+def set_state(pf, x, w, t):
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(pf.N, pf.nx))
+    w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(pf.N))
+    check(pf._lib, pf._lib.llpf_set_state(pf._h, x.ctypes.data_as(dp), w.ctypes.data_as(dp), int(t)))
+
+
+def effective_particles(pf_or_we):
+    """effective_particles(pf) / effective_particles(we) = 1/sum(abs2, we)  resample.jl:1-2"""
+    if isinstance(pf_or_we, AbstractParticleFilter):
+        v = C.c_double()
+        check(pf_or_we._lib, pf_or_we._lib.llpf_effective_particles(pf_or_we._h, C.byref(v)))
+        return v.value
+    we = np.asarray(pf_or_we, dtype=np.float64)
+    return 1.0 / float(np.sum(we * we))
+
+
+def shouldresample(pf):
+    v = C.c_int32()
+    check(pf._lib, pf._lib.llpf_shouldresample(pf._h, C.byref(v)))
+    return bool(v.value)
+
+
+def weighted_mean(pf):
+    xh = np.zeros(pf.nx)
+    check(pf._lib, pf._lib.llpf_weighted_mean(pf._h, xh.ctypes.data_as(dp)))
+    return xh
+
+
+# ---------------------------------------------------------------------------------------------
+# stand-alone numerics at the reference's function boundaries
+# ---------------------------------------------------------------------------------------------
+def resample(strategy, we, u01, M=None, j0=None, scan_mode="fast", device=0, return_bins=False):
+    """resample(T, we, j, bins, M)  resample.jl:12-61 with the rand() draws supplied by the caller:
+    systematic: u01 is the scalar rand() of :23 ; stratified: u01[M] are the rand() of :49.
+    Returns 1-based Int64 indices (entries the reference leaves untouched keep j0, default 1:M)."""
+    lib = _abi.load_library()
+    we = np.ascontiguousarray(np.asarray(we, dtype=np.float64).reshape(-1))
+    N = we.size
+    M = N if M is None else int(M)
+    j = np.arange(1, M + 1, dtype=np.int64) if j0 is None else np.array(j0, dtype=np.int64).copy()
+    b = np.zeros(N)
+    mode = SCAN_SERIAL if scan_mode in (SCAN_SERIAL, "serial") else SCAN_FAST
+    if strategy is ResampleSystematic:
+        check(lib, lib.llpf_resample_systematic(N, we.ctypes.data_as(dp), float(u01), M,
+                                                 j.ctypes.data_as(_abi.c_int64_p), b.ctypes.data_as(dp), mode, device))
+    elif strategy is ResampleStratified:
+        u = np.ascontiguousarray(np.asarray(u01, dtype=np.float64).reshape(-1))
+        if u.size != M:
+            raise ValueError("stratified resampling needs M uniforms")
+        check(lib, lib.llpf_resample_stratified(N, we.ctypes.data_as(dp), u.ctypes.data_as(dp), M,
+                                                 j.ctypes.data_as(_abi.c_int64_p), b.ctypes.data_as(dp), mode, device))
+    else:
+        raise NotImplementedError("ResampleResidual is not on the device path")
+    return (j, b) if return_bins else j
+
+
+def logsumexp(w, device=0):
+    """ll = logsumexp!(w, we)  utils.jl:18-27 -> (ll, w_normalised, we)"""
+    lib = _abi.load_library()
+    w = np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1)).copy()
+    we = np.zeros_like(w)
+    ll = C.c_double()
+    check(lib, lib.llpf_logsumexp(w.size, w.ctypes.data_as(dp), we.ctypes.data_as(dp), C.byref(ll), device))
+    return ll.value, w, we
+
+
+def launch_count(pf):
+    n = C.c_int64()
+    check(pf._lib, pf._lib.llpf_launch_count(pf._h, C.byref(n)))
+    return n.value
+
+
+def last_run_ms(pf):
+    v = C.c_float()
+    check(pf._lib, pf._lib.llpf_last_run_ms(pf._h, C.byref(v)))
+    return v.value
