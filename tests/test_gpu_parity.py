@@ -1,0 +1,472 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / Python host mirror) against the CPU oracle on
+identical inputs and identical counter-based RNG streams.
+
+Bars (BASELINE.json north_star): bit-exact particle indices for systematic resampling given the same
+u ~ U(0,1); log-likelihood within 1e-6 relative for Float64 (we assert much tighter where the
+arithmetic allows).  Full-size cases use size-independent properties (sortedness, exact dyadic
+scans, the closed-form Kalman filter).
+"""
+import numpy as np
+import pytest
+
+from models import lg_model, quadtank_model, ref_model_2state
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-6        # the north-star bar
+LL_RTOL_TIGHT = 1e-10  # what identical RNG streams + f64 actually give
+
+
+# ---------------------------------------------------------------------------------------------
+# function-boundary parity
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 10, 255, 256, 257, 5000, 100_000])
+def test_logsumexp_matches_oracle(gpu, n):
+    L = gpu
+    w0 = np.random.default_rng(n).standard_normal(n) * 4 - 3
+    ll, w, we = L.logsumexp(w0)
+    llo, wo, weo = O.logsumexp(w0)
+    assert abs(ll - llo) <= 1e-13 * max(1.0, abs(llo))
+    assert np.allclose(w, wo, rtol=0, atol=1e-12)
+    assert np.allclose(we, weo, rtol=1e-12, atol=1e-300)
+    assert abs(we.sum() - 1) < 1e-12
+
+
+def test_logsumexp_reference_invariants(gpu):   # test/runtests.jl:29-47 on the device path
+    L = gpu
+    wc = np.random.default_rng(0).standard_normal(10)
+    ll, w, we = L.logsumexp(wc)
+    assert np.isclose(we.sum(), 1) and np.isclose(np.exp(w).sum(), 1)
+    assert np.allclose(w, wc - np.log(np.sum(np.exp(wc))))
+    _, wi, _ = L.logsumexp(np.ones(10))
+    assert np.allclose(wi, np.full(10, np.log(1 / 10)))
+
+
+@pytest.mark.parametrize("N,M", [(10, 10), (500, 500), (777, 777), (4096, 4096), (100, 37), (64, 200),
+                                 (65536, 65536), (300_001, 300_001)])
+def test_systematic_indices_bit_exact_serial_scan(gpu, N, M):
+    """Bit-exact indices AND bins against the reference-order oracle (serial cumsum mode)."""
+    L = gpu
+    rng = np.random.default_rng(N * 7 + M)
+    for rep in range(2):
+        _, _, we = O.logsumexp(rng.standard_normal(N) * (1 + 2 * rep))
+        u = rng.random()
+        jo, bo = O.resample_systematic(we, u, M)
+        j, b = L.resample(L.ResampleSystematic, we, u, M, scan_mode="serial", return_bins=True)
+        assert np.array_equal(b, bo)
+        assert np.array_equal(j, jo)
+
+
+@pytest.mark.parametrize("N", [10, 512, 4096, 65536, 1 << 20])
+def test_systematic_indices_bit_exact_fast_scan_dyadic(gpu, N):
+    """Dyadic weights: every partial sum is exactly representable, so ANY correct scan must reproduce the
+    reference's serial cumsum bit for bit — the fast fixed-point scan does, at full size too."""
+    L = gpu
+    rng = np.random.default_rng(N)
+    k = rng.integers(0, 1 << 20, size=N).astype(np.float64)
+    k[rng.integers(0, N, size=max(1, N // 50))] *= 64            # a few heavy particles
+    tot = 2.0 ** np.ceil(np.log2(k.sum()))
+    we = k / tot                                                  # multiples of 2^-e, sum <= 1
+    u = rng.random()
+    jo, bo = O.resample_systematic(we, u)
+    j, b = L.resample(L.ResampleSystematic, we, u, scan_mode="fast", return_bins=True)
+    assert np.array_equal(b, bo)
+    assert np.array_equal(j, jo)
+
+
+@pytest.mark.parametrize("N", [500, 4096, 100_000, 1 << 20])
+def test_systematic_fast_scan_flips_are_rounding_ties(gpu, N):
+    """Generic weights: the parallel scan re-associates, bins differ from the serial cumsum by O(sqrt(N)) ulp.
+    Every index that differs must be a neighbour whose threshold sits inside that rounding gap."""
+    L = gpu
+    rng = np.random.default_rng(N + 1)
+    _, _, we = O.logsumexp(rng.standard_normal(N) * 2)
+    u = rng.random()
+    jo, bo = O.resample_systematic(we, u)
+    j, b = L.resample(L.ResampleSystematic, we, u, scan_mode="fast", return_bins=True)
+    assert np.max(np.abs(b - bo)) < 64 * np.sqrt(N) * 2.3e-16
+    assert np.all(np.diff(j) >= 0) and j.min() >= 1 and j.max() <= N
+    diff = np.nonzero(j != jo)[0]
+    assert diff.size <= max(2, N // 20000)
+    for i in diff:
+        assert abs(int(j[i]) - int(jo[i])) == 1
+        s = u * bo[-1] / N + i * (1.0 / N)
+        lo = min(j[i], jo[i]) - 1
+        assert abs(s - bo[lo]) < 1e-12
+
+
+def test_systematic_reference_known_answers(gpu):   # test/runtests.jl:88-106 on the device path
+    L = gpu
+    rng = np.random.default_rng(0)
+    _, _, we = L.logsumexp(np.full(10, -np.log(10)))
+    for mode in ("fast", "serial"):
+        for _ in range(5):
+            assert np.array_equal(L.resample(L.ResampleSystematic, we, rng.random(), scan_mode=mode), np.arange(1, 11))
+    _, _, we = L.logsumexp(np.array([1., 1, 1, 2, 2, 2, 3, 3, 3]))
+    j = L.resample(L.ResampleSystematic, we, rng.random())
+    assert j.sum() >= 56 and len(j) == 9
+    # stale entries keep the caller's value (resample.jl:26-34)
+    j = L.resample(L.ResampleSystematic, np.array([0.25, 0.25, 0.25, 0.2]), 0.9, j0=[9, 9, 9, 9], scan_mode="serial")
+    assert list(j) == [1, 2, 3, 9]
+
+
+@pytest.mark.parametrize("N,M", [(5, 5), (1000, 1000), (5000, 1234), (200_000, 200_000)])
+def test_stratified_matches_oracle(gpu, N, M):
+    L = gpu
+    rng = np.random.default_rng(N + 3 * M)
+    _, _, we = O.logsumexp(rng.standard_normal(N))
+    u = rng.random(M)
+    jo, bo = O.resample_stratified(we, u, M)
+    j, b = L.resample(L.ResampleStratified, we, u, M, scan_mode="serial", return_bins=True)
+    assert np.array_equal(b, bo) and np.array_equal(j, jo)
+    we5 = np.array([0.1, 0.5, 0.1, 0.15, 0.15])            # test/runtests.jl:145-154
+    for _ in range(20):
+        j = L.resample(L.ResampleStratified, we5, rng.random(5))
+        assert j[1] == 2 and j[2] == 2
+
+
+@pytest.mark.parametrize("kind", ["systematic", "stratified"])
+def test_resample_proportions_on_device(gpu, kind):     # test/runtests.jl:108-143 (fewer draws: launch cost)
+    L = gpu
+    we = np.array([0.1, 0.5, 0.1, 0.15, 0.15])
+    rng = np.random.default_rng(4)
+    counts = np.zeros(5)
+    for _ in range(600):
+        if kind == "systematic":
+            j = L.resample(L.ResampleSystematic, we, rng.random())
+        else:
+            j = L.resample(L.ResampleStratified, we, rng.random(5))
+        counts += np.bincount(j - 1, minlength=5)
+    assert np.allclose(counts / counts.sum(), we, atol=0.03)
+
+
+# ---------------------------------------------------------------------------------------------
+# step verbs
+# ---------------------------------------------------------------------------------------------
+def _assert_state_close(L, pf, of, xtol=1e-11, wtol=1e-10):
+    x, xo = L.particles(pf), of.particles
+    assert np.allclose(x, xo, rtol=0, atol=xtol), np.abs(x - xo).max()
+    assert np.allclose(L.weights(pf), of.weights, rtol=0, atol=wtol)
+    assert L.index(pf) == of.index
+
+
+@pytest.mark.parametrize("nx,nu,ny", [(2, 2, 2), (4, 2, 2), (2, 1, 1), (3, 2, 2), (6, 2, 3)])
+def test_reset_and_stepwise_verbs_match_oracle(gpu, nx, nu, ny):
+    L = gpu
+    s = lg_model(nx, nu, ny, seed=nx * 10 + ny)
+    N = 777
+    pf = s.particle_filter(N, seed=42, scan_mode="serial", resample_threshold=0.5)
+    of = s.oracle_filter(N, seed=42, resample_threshold=0.5)
+    L.reset(pf, 3); of.reset(3)
+    _assert_state_close(L, pf, of, xtol=1e-13)
+    assert np.all(L.weights(pf) == -np.log(N)) and np.all(L.expweights(pf) == 1 / N)
+    assert L.num_particles(pf) == N and not L.shouldresample(pf)
+    rng = np.random.default_rng(1)
+    n_res = 0
+    for k in range(25):
+        u, y = rng.standard_normal(nu), of.particles.mean(0) @ s.C.T + rng.standard_normal(ny) * 0.5
+        t = k * 1.0
+        ll, e = L.correct(pf, u, y, None, t)
+        llo = of.correct(u, y, t)
+        assert e == 0 and abs(ll - llo) <= 1e-11 * max(1, abs(llo))
+        assert np.allclose(L.expweights(pf), of.expweights, rtol=1e-9, atol=1e-300)
+        assert abs(L.effective_particles(pf) - O.effective_particles(of.expweights)) < 1e-7 * N
+        assert L.shouldresample(pf) == of.shouldresample()
+        assert np.allclose(L.weighted_mean(pf), of.weighted_mean(), rtol=0, atol=1e-10)
+        n_res += of.shouldresample()
+        L.predict(pf, u, None, t); of.predict(u, t)
+        _assert_state_close(L, pf, of)
+        assert np.array_equal(L.ancestors(pf), of.ancestors)
+    assert 0 < n_res <= 25
+
+
+def test_update_and_callable_filter(gpu):
+    L = gpu
+    s = lg_model(4, 2, 2, seed=1)
+    N = 600
+    pf = s.particle_filter(N, seed=9, scan_mode="serial")
+    of = s.oracle_filter(N, seed=9)
+    L.reset(pf, 1); of.reset(1)
+    rng = np.random.default_rng(2)
+    for k in range(12):
+        u, y = rng.standard_normal(2), rng.standard_normal(2)
+        # callable filter: t defaults to index(pf)*Ts  (filtering.jl:238)
+        ll, _ = pf(u, y)
+        llo = of.update(u, y, of.index * 1.0)
+        assert abs(ll - llo) <= 1e-11 * max(1, abs(llo))
+        _assert_state_close(L, pf, of)
+
+
+def test_missing_measurement_is_skipped(gpu):   # PFtypes.jl:109
+    L = gpu
+    s = lg_model()
+    pf = s.particle_filter(512, seed=1)
+    L.reset(pf, 1)
+    L.update(pf, np.zeros(2), np.array([0.3, -0.2]), None, 0.0)
+    w = L.weights(pf)
+    ll, _ = L.correct(pf, np.zeros(2), np.array([np.nan, 0.0]), None, 1.0)
+    assert abs(ll) < 1e-12 and np.allclose(L.weights(pf), w, atol=1e-12)
+
+
+def test_set_state_roundtrip(gpu):
+    L = gpu
+    s = lg_model()
+    N = 300
+    pf = s.particle_filter(N, seed=1, scan_mode="serial")
+    of = s.oracle_filter(N, seed=1)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((N, 4))
+    _, w, _ = O.logsumexp(rng.standard_normal(N) * 3)
+    L.set_state(pf, x, w, 5); of.set_state(x, w, 5)
+    assert np.array_equal(L.particles(pf), x) and np.allclose(L.weights(pf), w, atol=1e-15)
+    u = rng.standard_normal(2)
+    assert L.shouldresample(pf) == of.shouldresample()
+    L.predict(pf, u, None, 5.0); of.predict(u, 5.0)
+    _assert_state_close(L, pf, of)
+
+
+# ---------------------------------------------------------------------------------------------
+# trajectory drivers
+# ---------------------------------------------------------------------------------------------
+def _data(spec, T, seed, N=64):
+    u = np.random.default_rng(seed).standard_normal((T, spec.nu))
+    gen = spec.oracle_filter(N, seed=1)
+    _, y = gen.simulate(u, seed + 100)
+    return u, y
+
+
+def test_config1_forward_trajectory_full_history(gpu):
+    """BASELINE config 1: example_lineargaussian.jl — ParticleFilter, nx=2, N=500, T=200, full x/w/we history."""
+    L = gpu
+    s = lg_model(2, 2, 2, seed=0)
+    N, T = 500, 200
+    u, y = _data(s, T, 0)
+    pf = s.particle_filter(N, seed=5, scan_mode="serial")
+    of = s.oracle_filter(N, seed=5)
+    sol = L.forward_trajectory(pf, u, y, epoch=1)
+    ref = of.forward_trajectory(u, y, epoch=1, history=True)
+    assert sol.x.shape == (T, N, 2) and sol.w.shape == (T, N) and sol.we.shape == (T, N)
+    assert np.array_equal(sol.t, np.arange(T) * 1.0)
+    assert abs(sol.ll - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+    assert np.array_equal(sol.extra["resampled"], ref["resampled"])
+    assert 0 < ref["resampled"].sum() < T
+    assert np.allclose(sol.extra["ll_steps"], ref["ll_steps"], rtol=0, atol=1e-10)
+    assert np.allclose(sol.extra["ess"], ref["ess"], rtol=1e-9)
+    assert np.allclose(sol.x, ref["x"], rtol=0, atol=1e-10)
+    assert np.allclose(sol.w, ref["w"], rtol=0, atol=1e-9)
+    assert np.allclose(sol.we, ref["we"], rtol=1e-8, atol=1e-300)
+    assert np.allclose(sol.extra["xhat"], ref["xhat"], rtol=0, atol=1e-10)
+    assert np.allclose(L.mean_trajectory(sol), ref["xhat"], rtol=0, atol=1e-10)
+    assert np.allclose(np.sum(sol.we, axis=1), 1.0, atol=1e-12)
+    # final state == the oracle's after predict!(T)
+    _assert_state_close(L, pf, of)
+    # 4-state variant of the same recipe (BASELINE.json calls config 1 "4-state")
+    s4 = lg_model(4, 2, 2, seed=0)
+    u, y = _data(s4, T, 1)
+    pf4, of4 = s4.particle_filter(N, seed=5, scan_mode="serial"), s4.oracle_filter(N, seed=5)
+    sol4, ref4 = L.forward_trajectory(pf4, u, y, epoch=2), of4.forward_trajectory(u, y, epoch=2, history=True)
+    assert abs(sol4.ll - ref4["ll"]) <= LL_RTOL_TIGHT * abs(ref4["ll"])
+    assert np.allclose(sol4.x, ref4["x"], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("scan_mode", ["serial", "fast"])
+@pytest.mark.parametrize("N", [1000, 16384, 100_000])
+def test_loglik_matches_oracle(gpu, N, scan_mode):
+    """config-2 model at oracle-affordable sizes; loglik semantics (t = index*Ts)."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    T = 60 if N > 50_000 else 150
+    u, y = _data(s, T, 2)
+    pf = s.particle_filter(N, seed=77, scan_mode=scan_mode)
+    of = s.oracle_filter(N, seed=77)
+    got = L.loglik(pf, u, y, epoch=4, details=True)
+    ref = of.loglik(u, y, epoch=4)
+    assert abs(got["ll"] - ref["ll"]) <= (LL_RTOL_TIGHT if scan_mode == "serial" else LL_RTOL) * abs(ref["ll"])
+    assert np.array_equal(got["resampled"], ref["resampled"])
+    assert ref["resampled"].sum() > 3
+    if scan_mode == "serial":
+        _assert_state_close(L, pf, of)
+
+
+def test_loglik_equals_forward_trajectory_for_time_invariant_model(gpu):
+    L = gpu
+    s = lg_model()
+    u, y = _data(s, 50, 3)
+    pf = s.particle_filter(5000, seed=3)
+    a = L.loglik(pf, u, y, epoch=9)
+    b = L.forward_trajectory(pf, u, y, history=False, epoch=9).ll
+    assert a == b
+    assert L.loglik(pf, u, y, epoch=9) == a                      # deterministic
+    assert L.loglik(pf, u, y, epoch=10) != a                     # a new epoch is a new RNG stream
+
+
+def test_stratified_in_loop(gpu):
+    L = gpu
+    s = lg_model()
+    N, T = 2000, 80
+    u, y = _data(s, T, 5)
+    pf = s.particle_filter(N, seed=8, scan_mode="serial", resampling_strategy=L.ResampleStratified)
+    of = s.oracle_filter(N, seed=8, resampling=1)
+    got, ref = L.loglik(pf, u, y, epoch=1, details=True), of.loglik(u, y, epoch=1)
+    assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+    assert np.array_equal(got["resampled"], ref["resampled"])
+    _assert_state_close(L, pf, of)
+
+
+def test_always_resample_threshold_one(gpu):   # resample.jl:6
+    L = gpu
+    s = lg_model()
+    N, T = 1500, 40
+    u, y = _data(s, T, 6)
+    pf = s.particle_filter(N, seed=8, scan_mode="serial", resample_threshold=1.0)
+    of = s.oracle_filter(N, seed=8, resample_threshold=1.0)
+    got, ref = L.loglik(pf, u, y, epoch=1, details=True), of.loglik(u, y, epoch=1)
+    assert np.all(got["resampled"] == 1) and np.all(ref["resampled"] == 1)
+    assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+    _assert_state_close(L, pf, of)
+
+
+def test_advanced_filter_quadtank(gpu):
+    """BASELINE config 3 at oracle size: AdvancedParticleFilter, quadtank RK4 (supersample 2), threshold 0.5,
+    both time conventions (the t>t_switch leak makes them differ: SURVEY §3.2)."""
+    L = gpu
+    q = quadtank_model(t_switch=20.0, a1_factor=2.0)
+    N, T = 2048, 60
+    u = q.inputs(T)
+    of = q.oracle_filter(N, seed=4)
+    _, y = of.simulate(u, 9)
+    pf = q.advanced_filter(N, seed=4, scan_mode="serial")
+    assert pf.resample_threshold == 0.5
+    sol = L.forward_trajectory(pf, u, y, history=False, epoch=2)
+    ref = of.forward_trajectory(u, y, epoch=2)
+    assert abs(sol.ll - ref["ll"]) <= 1e-8 * abs(ref["ll"])
+    assert np.array_equal(sol.extra["resampled"], ref["resampled"]) and ref["resampled"].sum() > T // 2
+    assert np.allclose(sol.extra["xhat"], ref["xhat"], rtol=0, atol=1e-8)
+    got, refl = L.loglik(pf, u, y, epoch=2, details=True), of.loglik(u, y, epoch=2)
+    assert abs(got["ll"] - refl["ll"]) <= 1e-8 * abs(refl["ll"])
+    assert got["ll"] != sol.ll
+
+
+def test_advanced_filter_lg_equals_particle_filter(gpu):
+    L = gpu
+    s = lg_model()
+    u, y = _data(s, 40, 7)
+    a = s.advanced_filter(3000, seed=6, resample_threshold=0.1)
+    b = s.particle_filter(3000, seed=6)
+    assert L.loglik(a, u, y, epoch=1) == L.loglik(b, u, y, epoch=1)
+
+
+@pytest.mark.parametrize("N", [500, 20_000])
+def test_auxiliary_filter_matches_oracle(gpu, N):
+    """BASELINE config 4 model at oracle size: forward_trajectory(pfa) and loglik(pfa) incl. their quirks."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    T = 80
+    u, y = _data(s, T, 8)
+    pfa = s.aux_filter(N, seed=21, scan_mode="serial")
+    ofa = s.oracle_filter(N, filter=2, seed=21)
+    hist = N <= 1000
+    sol = L.forward_trajectory(pfa, u, y, history=hist, epoch=3)
+    ref = ofa.forward_trajectory(u, y, epoch=3, history=hist)
+    assert abs(sol.ll - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+    assert abs(sol.extra["ll_steps"][0]) < 1e-12
+    assert np.allclose(sol.extra["ll_steps"], ref["ll_steps"], rtol=0, atol=1e-9)
+    assert np.array_equal(sol.extra["resampled"], ref["resampled"])
+    assert np.allclose(sol.extra["xhat"], ref["xhat"], rtol=0, atol=1e-9)
+    if hist:
+        assert np.allclose(sol.x, ref["x"], rtol=0, atol=1e-10)
+        assert np.allclose(sol.w, ref["w"], rtol=0, atol=1e-9)
+        assert np.allclose(sol.we, ref["we"], rtol=1e-8, atol=1e-300)
+    got, refl = L.loglik(pfa, u, y, epoch=3, details=True), ofa.loglik(u, y, epoch=3)
+    assert abs(got["ll"] - refl["ll"]) <= LL_RTOL_TIGHT * abs(refl["ll"])
+    assert np.allclose(got["ll_steps"], refl["ll_steps"], rtol=0, atol=1e-9)
+    _assert_state_close(L, pfa, ofa)
+
+
+def test_auxiliary_stepwise_verbs(gpu):
+    L = gpu
+    s = lg_model(2, 1, 1, seed=3)
+    N = 400
+    pfa = s.aux_filter(N, seed=2, scan_mode="serial")
+    ofa = s.oracle_filter(N, filter=2, seed=2)
+    L.reset(pfa, 1); ofa.reset(1)
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal((12, 1))
+    for k in range(11):
+        u = rng.standard_normal(1)
+        ll, _ = pfa(u, y[k], y[k + 1], None, k * 1.0)       # update!(pfa,u,y,y1,p,t)
+        llo = ofa.update(u, y[k], k * 1.0, y1=y[k + 1])
+        assert abs(ll - llo) <= 1e-10 * max(1, abs(llo))
+        assert np.allclose(L.particles(pfa), ofa.particles, rtol=0, atol=1e-11)
+        assert np.array_equal(L.ancestors(pfa), ofa.ancestors)
+    # separate correct! / predict! calls
+    ll, _ = L.correct(pfa, np.zeros(1), y[11], None, 11.0)
+    assert abs(ll - ofa.correct(np.zeros(1), y[11], 11.0)) < 1e-10
+    assert np.allclose(L.weights(pfa), ofa.weights, rtol=0, atol=1e-10)
+    L.predict(pfa, np.ones(1), None, 11.0, y1=y[3]); ofa.predict_aux(np.ones(1), y[3], 11.0)
+    assert np.allclose(L.particles(pfa), ofa.particles, rtol=0, atol=1e-11)
+
+
+def test_auxiliary_over_advanced_filter(gpu):   # filtering.jl:219-234: every ll increment is ~0 (Q9)
+    L = gpu
+    s = lg_model(2, 1, 1, seed=3)
+    N, T = 600, 25
+    u, y = _data(s, T, 4)
+    pfa = L.AuxiliaryParticleFilter(s.advanced_filter(N, seed=2, scan_mode="serial"))
+    ofa = s.oracle_filter(N, filter=3, seed=2, resample_threshold=0.5)
+    sol = L.forward_trajectory(pfa, u, y, history=False, epoch=1)
+    ref = ofa.forward_trajectory(u, y, epoch=1)
+    assert np.all(np.abs(sol.extra["ll_steps"]) < 1e-10)
+    assert np.allclose(sol.extra["xhat"], ref["xhat"], rtol=0, atol=1e-9)
+    assert np.allclose(L.particles(pfa), ofa.particles, rtol=0, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference statistical test on the device path + full-size properties
+# ---------------------------------------------------------------------------------------------
+def test_pf_and_apf_loglik_vs_kalman_on_device(gpu):   # test/runtests.jl:412-449
+    L = gpu
+    A, B, C_ = ref_model_2state()
+    n, T, N = 2, 2000, 1000
+    rng = np.random.default_rng(0)
+    mu0 = rng.standard_normal(n)
+    u = rng.standard_normal((T, 1))
+
+    def omodel(sig):
+        return O.ModelArrays(2, 1, 1, C_, sig ** 2 * np.eye(n), np.eye(1), mu0, 4.0 * np.eye(n), A=A, B=B)
+
+    _, y = O.OracleFilter(omodel(0.1), 10, seed=1).simulate(u, 7)
+    svec = 10 ** np.linspace(-2, 0, 11)
+    llpf, llapf, llkf = [], [], []
+    for sg in svec:
+        args = (N, L.LinearDynamics(A, B), L.LinearMeasurement(C_), L.MvNormal(np.zeros(n), sg ** 2 * np.eye(n)),
+                L.MvNormal(np.eye(1)), L.MvNormal(mu0, 4.0 * np.eye(n)))
+        llpf.append(L.loglik(L.ParticleFilter(*args, seed=5), u, y))
+        llapf.append(L.loglik(L.AuxiliaryParticleFilter(*args, seed=5), u, y))
+        llkf.append(O.kalman_loglik(omodel(sg), u, y))
+    llpf, llapf, llkf = map(np.array, (llpf, llapf, llkf))
+    assert 4 <= np.argmax(llpf) <= 6 and 4 <= np.argmax(llapf) <= 6 and 4 <= np.argmax(llkf) <= 6
+    assert np.max(np.abs(llkf - llpf)) < 20 and np.max(np.abs(llkf - llapf)) < 20
+
+
+def test_full_size_config2_properties(gpu):
+    """N = 2^20 (BASELINE config 2 particle count), T = 100: the oracle is too slow here, so check
+    size-independent properties: the log-likelihood converges to the closed-form Kalman filter
+    (std ~ sqrt(c*T/N)), ancestors are sorted and in range, weights normalise, runs are deterministic."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    N, T = 1 << 20, 100
+    u, y = _data(s, T, 11)
+    pf = s.particle_filter(N, seed=123)
+    r = L.loglik(pf, u, y, epoch=1, details=True)
+    kf = O.kalman_loglik(s.oracle_model(), u, y)
+    assert abs(r["ll"] - kf) < 0.15, (r["ll"], kf)
+    assert 0 < r["resampled"].sum() < T
+    assert np.all(r["ess"] > 1) and np.all(r["ess"] <= N * (1 + 1e-9))
+    j = L.ancestors(pf)
+    assert j.min() >= 1 and j.max() <= N and (np.all(np.diff(j) >= 0) or r["resampled"][-1] == 0)
+    assert abs(L.expweights(pf).sum() - 1) < 1e-10
+    assert L.loglik(pf, u, y, epoch=1) == r["ll"]
+    x = L.particles(pf)
+    assert np.all(np.isfinite(x))
