@@ -68,7 +68,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("LLPF_LIB_PATH") or LIB_PATH   # LLPF_LIB_PATH: tuning variants of the same library
     if not os.path.exists(p):
         raise OSError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "

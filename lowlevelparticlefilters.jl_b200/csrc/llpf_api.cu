@@ -166,10 +166,13 @@ struct InitP {
 // reset!(pf)  filtering.jl:4-14: x = xprev ~ initial_density ; (weights handled by Scalars.uniform)
 template <int NX>
 __global__ void k_init(double* x, long long ld, long long n, long long first, RngKey key, InitP ip) {
+  __shared__ MathTab mt;
+  math_tab_load(mt);
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     double z[NX];
-    normals<NX>(key, ST_INIT, 0u, (unsigned long long)(first + i), z);
+    normals<NX>(key, ST_INIT, 0u, (unsigned long long)(first + i), z, mt);
 #pragma unroll
     for (int r = 0; r < NX; ++r) {
       double acc = 0.0;
@@ -252,50 +255,41 @@ __global__ void k_wstats(const double* we, const double* x, long long ld, long l
 // ------------------------------------------------------------------------------------------------
 // stand-alone cooperative kernels at the reference's function boundaries
 // ------------------------------------------------------------------------------------------------
-// resample(strategy, we, j, bins, M)  resample.jl:17-61 ; we -> bins (scan) -> j (search), M output slots
+// resample(strategy, we, j, bins, M)  resample.jl:17-61 ; we -> bins (scan) -> j (source-side slot ranges)
 __global__ void __launch_bounds__(BLOCK)
 k_resample(const __grid_constant__ EngineP P, const double* we, double u01, const double* u_slots,
-           long long M, long long* j_inout) {
+           int M, long long* j_inout) {
   __shared__ Shared sh;
   unsigned bar_target = 0;
-  long long beg = (long long)blockIdx.x * P.chunk, end = beg + P.chunk;
-  if (end > P.n) end = P.n;
-  if (beg > P.n) beg = P.n;
-  scan_stage1(P, sh, beg, end, [=](long long i) { return we[i]; });
-  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-  if (P.scan_mode != 0) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
-    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-    load_block_table(P, sh);
-  } else {
-    scan_stage2(P, sh, beg, end, 0ull);
-    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-  }
-  const double total = sh.offd[P.nblocks];
-  const Thresholds th = make_thresholds(P, total, u01, (double)M, u_slots);
-  for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < M; i += (long long)gridDim.x * BLOCK) {
-    const double s = threshold(th, P.key, 0u, i);
-    if (s < total) j_inout[i] = upper_bound_bins(P, sh, s) + 1;  // else: keep the caller's value (stale)
-  }
+  long long b = (long long)blockIdx.x * P.chunk, e = b + P.chunk;
+  if (e > P.n) e = P.n;
+  if (b > P.n) b = P.n;
+  double total;
+  // 1-based ids; slots >= f_total keep the caller's value (resample.jl:26-34)
+  (void)resample_indices<long long>(P, sh, (int)b, (int)e, bar_target, [=](int i) { return __ldg(we + i); },
+                                    u01, false, 0u, M, u_slots, j_inout, 1ll, total);
 }
 
 // logsumexp!(w, we)  utils.jl:18-27 on caller-provided arrays
 __global__ void __launch_bounds__(BLOCK)
 k_logsumexp(const __grid_constant__ EngineP P, double* w, double* we, double* ll_out) {
   __shared__ Shared sh;
+  math_tab_load(sh.mt);
+  __syncthreads();
   unsigned bar_target = 0;
-  long long beg = (long long)blockIdx.x * P.chunk, end = beg + P.chunk;
-  if (end > P.n) end = P.n;
-  if (beg > P.n) beg = P.n;
+  long long bl = (long long)blockIdx.x * P.chunk, el = bl + P.chunk;
+  if (el > P.n) el = P.n;
+  if (bl > P.n) bl = P.n;
+  const int beg = (int)bl, end = (int)el;
   Online<1> acc;
   acc.init();
   const double dummy[1] = {0.0};
-  for (long long i = beg + threadIdx.x; i < end; i += BLOCK) acc.add(w[i], dummy, false);
+  for (int i = beg + threadIdx.x; i < end; i += BLOCK) acc.add(w[i], dummy, false, sh.mt);
   const Stats st = reduce_stats<1>(P, sh, acc, false, bar_target);
   const double ls = log(st.s), inv = 1.0 / st.s;
-  for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
+  for (int i = beg + threadIdx.x; i < end; i += BLOCK) {
     const double wr = w[i];
-    we[i] = exp(wr - st.m) * inv;
+    we[i] = exp_nonpos(wr - st.m, sh.mt) * inv;
     w[i] = (wr - st.m) - ls;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *ll_out = st.m + ls;
@@ -321,6 +315,7 @@ struct llpf_filter {
   size_t arena_bytes = 0;
   double *x[2] = {nullptr, nullptr}, *w = nullptr, *lam = nullptr, *bins = nullptr;
   int* j = nullptr;
+  u64* loc = nullptr;
   double* partials = nullptr;
   u64* tots = nullptr;
   unsigned* bar = nullptr;
@@ -511,6 +506,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const size_t o_x0 = take((size_t)nx * f->ld * 8), o_x1 = take((size_t)nx * f->ld * 8);
   const size_t o_w = take((size_t)f->ld * 8), o_lam = take((size_t)f->ld * 8), o_bins = take((size_t)f->ld * 8);
   const size_t o_j = take((size_t)f->ld * 4);
+  const size_t o_loc = take((size_t)f->ld * 8);
   const size_t o_part = take((size_t)MAX_BLOCKS * PS * 8), o_tots = take((size_t)MAX_BLOCKS * 8);
   const size_t o_bar = take(256), o_sc = take(sizeof(Scalars));
   const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + MAX_NX) * 8);
@@ -521,6 +517,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   f->x[0] = (double*)(f->arena + o_x0); f->x[1] = (double*)(f->arena + o_x1);
   f->w = (double*)(f->arena + o_w); f->lam = (double*)(f->arena + o_lam);
   f->bins = (double*)(f->arena + o_bins); f->j = (int*)(f->arena + o_j);
+  f->loc = (u64*)(f->arena + o_loc);
   f->partials = (double*)(f->arena + o_part); f->tots = (u64*)(f->arena + o_tots);
   f->bar = (unsigned*)(f->arena + o_bar); f->sc = (Scalars*)(f->arena + o_sc);
   f->stage_u = (double*)(f->arena + o_su); f->stage_y = (double*)(f->arena + o_sy);
@@ -559,9 +556,9 @@ extern "C" int llpf_reset(llpf_handle h, uint64_t epoch) {
 static void base_params(llpf_filter* f, EngineP& P) {
   std::memset(&P, 0, sizeof(P));
   P.x[0] = f->x[0]; P.x[1] = f->x[1]; P.ld = f->ld;
-  P.w = f->w; P.lam = f->lam; P.bins = f->bins; P.j = f->j;
+  P.w = f->w; P.lam = f->lam; P.bins = f->bins; P.j = f->j; P.loc = f->loc;
   P.bar = f->bar; P.partials = f->partials; P.tots = f->tots; P.sc = f->sc;
-  P.N = f->N; P.n = f->n; P.first = f->first;
+  P.N = f->N; P.n = (int)f->n; P.first = (int)f->first;
   P.filter = f->cfg.filter;
   P.Ts = f->cfg.Ts;
   P.thr = f->cfg.resample_threshold;
@@ -571,10 +568,22 @@ static void base_params(llpf_filter* f, EngineP& P) {
   if (nb > f->max_blocks) nb = f->max_blocks;
   if (nb < 1) nb = 1;
   P.nblocks = (int)nb;
-  P.chunk = (f->n + nb - 1) / nb;
+  P.chunk = (int)((f->n + nb - 1) / nb);
   P.key = RngKey{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)f->epoch << 8};
   P.rank = 0; P.world = 1;
   P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
+}
+
+// ---- op-list construction (the kernel executes EngineP::ops in order) -------------------------------
+static void push_op(EngineP& P, int kind, int a0, int b0, int count = 1, int da = 0, int db = 0, int flags = 0) {
+  if (count < 1 || P.nops >= MAX_OPS) return;
+  P.ops[P.nops++] = OpRun{kind, a0, b0, count, da, db, flags, 0};
+}
+// correct!(pfa) = logsumexp! only (filtering.jl:170-174): reuse the stats aux_step left behind when they
+// describe the current weights, otherwise a reduce-only sweep
+static void push_aux_correct(llpf_filter* f, EngineP& P, int k) {
+  if (f->hsc.stats_ahead) push_op(P, OP_AUX_CSTATS, k, 0);
+  else push_op(P, OP_PF, 0, k, 1, 0, 0, OPF_SKIP_MEAS);
 }
 
 static int launch(llpf_filter* f, const EngineP& P, bool timed) {
@@ -619,8 +628,9 @@ extern "C" int llpf_correct(llpf_handle h, const double* u, const double* y, dou
   EngineP P;
   base_params(h, P);
   P.u = h->stage_u; P.y = h->stage_y;
-  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
-  if (is_aux(h)) { P.prog = 2; } else { P.prog = 0; P.lead_w = 1; P.trail_p = 0; }
+  P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
+  if (is_aux(h)) push_aux_correct(h, P, 1);
+  else push_op(P, OP_PF, 0, 1);
   OKR(launch(h, P, false));
   return finish_ll(h, ll);
 }
@@ -633,9 +643,9 @@ extern "C" int llpf_predict(llpf_handle h, const double* u, double t) {
   EngineP P;
   base_params(h, P);
   P.u = h->stage_u; P.y = h->stage_y;
-  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 0;
-  P.prog = 0; P.trail_p = 1;
-  if (!h->hsc.stats_valid) { P.lead_w = 1; P.lead_skip = 1; }  // refresh ESS (shouldresample, resample.jl:5-10)
+  P.use_t_override = 1; P.t_override = t; P.want_xhat = 0;
+  if (!h->hsc.stats_valid) push_op(P, OP_PF, 0, 1, 1, 0, 0, OPF_SKIP_MEAS);  // refresh ESS (resample.jl:5-10)
+  push_op(P, OP_PF, 1, 0);
   return launch(h, P, false);
 }
 
@@ -648,8 +658,8 @@ extern "C" int llpf_predict_aux(llpf_handle h, const double* u, const double* y1
   EngineP P;
   base_params(h, P);
   P.u = h->stage_u; P.y = h->stage_y;
-  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
-  P.prog = 3;
+  P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
+  push_op(P, OP_AUX_STEP, 1, 1);   // y1 staged at y[0]
   return launch(h, P, false);
 }
 
@@ -661,14 +671,16 @@ extern "C" int llpf_update(llpf_handle h, const double* u, const double* y, cons
   EngineP P;
   base_params(h, P);
   P.u = h->stage_u; P.y = h->stage_y;
-  P.T = 1; P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
+  P.use_t_override = 1; P.t_override = t; P.want_xhat = 1;
   if (is_aux(h)) {
     if (!y1) return fail(LLPF_ERR_BAD_ARG, "update!(pfa,u,y,y1): y1 is null");
     OKR(stage_inputs(h, u, y, y1));
-    P.prog = 4;
+    push_aux_correct(h, P, 1);
+    push_op(P, OP_AUX_STEP, 1, 2);   // y1 staged at y[1]
   } else {
     OKR(stage_inputs(h, u, y, nullptr));
-    P.prog = 0; P.lead_w = 1; P.trail_p = 1;
+    push_op(P, OP_PF, 0, 1);
+    push_op(P, OP_PF, 1, 0);
   }
   OKR(launch(h, P, false));
   return finish_ll(h, ll);
@@ -700,14 +712,31 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
   EngineP P;
   base_params(f, P);
   P.u = u_dev; P.y = y_dev;
-  P.T = (int)T;
+  const int Ti = (int)T;
   // APF passes t=(k-1)*Ts explicitly in both drivers (filtering.jl:376, smoothing.jl:234-235)
   P.time_conv = is_aux(f) ? 0 : (time_convention == LLPF_TIME_LOGLIK ? 1 : 0);
-  if (is_aux(f)) {
-    P.prog = 1;
-    P.aux_tail_pf = (time_convention == LLPF_TIME_LOGLIK) ? 1 : 0;
+  if (!is_aux(f)) {
+    // W(1) [P(k)+W(k+1)] k=1..T-1  P(T)
+    push_op(P, OP_PF, 0, 1);
+    push_op(P, OP_PF, 1, 2, Ti - 1, 1, 1);
+    push_op(P, OP_PF, Ti, 0);
+  } else if (time_convention != LLPF_TIME_LOGLIK) {
+    // forward_trajectory(pfa) filtering.jl:367-384: correct!(k); k<T && predict!(k, y[k+1])
+    push_aux_correct(f, P, 1);
+    push_op(P, OP_AUX_STEP, 1, 2, Ti - 1, 1, 1, OPF_POST_CSTATS);
+    push_op(P, OP_FLUSH_WHIST, Ti, 0);
   } else {
-    P.prog = 0; P.lead_w = 1; P.trail_p = 1;
+    // loglik(pfa) smoothing.jl:232-236: T-1 update!(pfa,u,y,y1) then the INNER filter's update! on the last
+    // sample: its correct! adds the likelihood of y[T] on top of the raw w = lam - log N, then predict!
+    if (Ti > 1) {
+      push_aux_correct(f, P, 1);
+      push_op(P, OP_AUX_STEP, 1, 2, Ti - 2, 1, 1, OPF_POST_CSTATS);
+      push_op(P, OP_AUX_STEP, Ti - 1, Ti);
+      push_op(P, OP_PF, 0, Ti, 1, 0, 0, OPF_RAW_WEIGHTS);
+    } else {
+      push_op(P, OP_PF, 0, 1);
+    }
+    push_op(P, OP_PF, Ti, 0);
   }
   double *xh = nullptr, *wh = nullptr, *weh = nullptr;
   const size_t NT = (size_t)f->N * (size_t)T;
@@ -938,7 +967,7 @@ static int standalone_geometry(int device, long long n, EngineP& P, const void* 
   if (nb > cap) nb = cap;
   if (nb < 1) nb = 1;
   P.nblocks = (int)nb;
-  P.chunk = (n + nb - 1) / nb;
+  P.chunk = (int)((n + nb - 1) / nb);
   return LLPF_OK;
 }
 
@@ -954,11 +983,12 @@ static int resample_standalone(int strategy, int64_t N, const double* we, double
   OKR(standalone_geometry(device, N, P, (const void*)k_resample));
   Scratchpad sp;
   double *d_we = nullptr, *d_bins = nullptr, *d_part = nullptr, *d_us = nullptr;
-  u64* d_tots = nullptr;
+  u64 *d_tots = nullptr, *d_loc = nullptr;
   unsigned* d_bar = nullptr;
   long long* d_j = nullptr;
   CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_bins, (size_t)N)); CU(sp.alloc(&d_part, (size_t)MAX_BLOCKS * PS));
   CU(sp.alloc(&d_tots, (size_t)MAX_BLOCKS)); CU(sp.alloc(&d_bar, 64)); CU(sp.alloc(&d_j, (size_t)M));
+  CU(sp.alloc(&d_loc, (size_t)N));
   CU(cudaMemcpy(d_we, we, sizeof(double) * N, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d_j, j_inout, sizeof(long long) * M, cudaMemcpyHostToDevice));
   CU(cudaMemset(d_bar, 0, 64 * sizeof(unsigned)));
@@ -974,12 +1004,12 @@ static int resample_standalone(int strategy, int64_t N, const double* we, double
   if (e < 0) e = 0;
   P.fix_scale = std::ldexp(1.0, 62 - e);
   P.fix_inv = std::ldexp(1.0, e - 62);
-  P.bins = d_bins; P.partials = d_part; P.tots = d_tots; P.bar = d_bar;
-  P.N = N; P.n = N; P.first = 0; P.strategy = strategy; P.scan_mode = scan_mode;
+  P.bins = d_bins; P.partials = d_part; P.tots = d_tots; P.bar = d_bar; P.loc = d_loc;
+  P.N = N; P.n = (int)N; P.first = 0; P.strategy = strategy; P.scan_mode = scan_mode;
   P.world = 1;
   const double* d_us_c = d_us;
-  long long Mll = M;
-  void* args[] = {(void*)&P, (void*)&d_we, (void*)&u01, (void*)&d_us_c, (void*)&Mll, (void*)&d_j};
+  int Mi = (int)M;
+  void* args[] = {(void*)&P, (void*)&d_we, (void*)&u01, (void*)&d_us_c, (void*)&Mi, (void*)&d_j};
   CU(cudaLaunchCooperativeKernel((const void*)k_resample, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(j_inout, d_j, sizeof(long long) * M, cudaMemcpyDeviceToHost));
@@ -1012,7 +1042,7 @@ extern "C" int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int3
   CU(sp.alloc(&d_ll, 1)); CU(sp.alloc(&d_bar, 64));
   CU(cudaMemcpy(d_w, w, sizeof(double) * N, cudaMemcpyHostToDevice));
   CU(cudaMemset(d_bar, 0, 64 * sizeof(unsigned)));
-  P.partials = d_part; P.bar = d_bar; P.N = N; P.n = N; P.world = 1;
+  P.partials = d_part; P.bar = d_bar; P.N = N; P.n = (int)N; P.world = 1;
   void* args[] = {(void*)&P, (void*)&d_w, (void*)&d_we, (void*)&d_ll};
   CU(cudaLaunchCooperativeKernel((const void*)k_logsumexp, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));
   CU(cudaDeviceSynchronize());

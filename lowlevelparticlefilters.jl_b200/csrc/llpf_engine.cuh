@@ -1,9 +1,11 @@
-// llpf_engine.cuh — the persistent, cooperative particle-filter engine for sm_100a.
+// llpf_engine.cuh — the persistent, cooperative particle-filter engine for sm_100a (v2).
 //
 // One launch runs a whole trajectory (or one step verb): the sequential time loop of
 // forward_trajectory / loglik (reference src/filtering.jl:343-384, src/smoothing.jl:227-236) never
 // returns to the host.  The grid is co-resident (cooperative launch); blocks own contiguous particle
-// chunks and meet at a hand-rolled grid barrier (one red.release + ld.acquire spin per block).
+// chunks and meet at a hand-rolled grid barrier (one red.release + spin per block).
+// The host compiles the call into a tiny run-length op list (EngineP::ops); the kernel has exactly one
+// inlined call site per pass kind, so the filter scalars and all per-particle state live in registers.
 //
 // Pass structure for ParticleFilter / AdvancedParticleFilter (filtering.jl:140-168):
 //     W(1)  [P(1)+W(2)] [P(2)+W(3)] ... [P(T-1)+W(T)]  P(T)
@@ -14,7 +16,7 @@
 //   per particle-step instead of the 3*nx*8+16 B of the un-fused formulation; the copyto!(xprev,x)
 //   of filtering.jl:151 disappears (in-place update, ping-pong only on resample steps).
 //
-// Pass structure for AuxiliaryParticleFilter (filtering.jl:195-217): A(k) -> scan -> B(k), see aux_A/aux_B.
+// AuxiliaryParticleFilter (filtering.jl:195-217): aux_step = sweep A -> scan -> sweep B.
 //
 // Weight normalisation is lazy: w[] keeps the un-normalised log-weights and the pair (max, log sum)
 // found by the grid reduction is applied when w is next read (same two subtractions as utils.jl:20,25).
@@ -22,8 +24,11 @@
 //
 // Resampling (resample.jl:17-61): bins = device-wide inclusive scan of we.  FAST mode scans in 2^-62
 // fixed point (u64): exact, associative, monotone, independent of block/GPU partitioning.  SERIAL mode
-// is one thread doing the reference's left-to-right f64 adds (bit-exact verification mode).  Offspring
-// indices come from a two-level upper-bound search (block table in smem, then the block's chunk).
+// is one thread doing the reference's left-to-right f64 adds (bit-exact verification mode).  Indices
+// come from the *source side*: particle b owns the output slots {i : bins[b-1] <= s_i < bins[b]}, whose
+// first element is found in O(1) by inverting the threshold sequence (with an exact fix-up that
+// evaluates s_i in the reference's arithmetic) — the same partition as the reference's two-pointer
+// walk (resample.jl:26-34), with no dependent memory chain.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
@@ -34,15 +39,19 @@
 namespace llpf {
 
 #ifndef LLPF_MIN_BLOCKS
-#define LLPF_MIN_BLOCKS 3
+#define LLPF_MIN_BLOCKS 2
 #endif
-constexpr int BLOCK = 256;
+#ifndef LLPF_BLOCK
+#define LLPF_BLOCK 256
+#endif
+constexpr int BLOCK = LLPF_BLOCK;
 constexpr int NWARP = BLOCK / 32;
 constexpr int MAX_BLOCKS = 1024;
 constexpr int MAX_NU = 8;
 constexpr int MAX_NX = 8;
 constexpr int MAX_WORLD = 8;
 constexpr int PS = 12;  // doubles per block partial: m, s, q, sx[8], pad
+constexpr int MAX_OPS = 8;
 constexpr double FIX_SCALE = 4611686018427387904.0;        // 2^62
 constexpr double FIX_INV = 2.168404344971008868e-19;       // 2^-62
 
@@ -70,10 +79,11 @@ struct Scalars {
   double xhat[MAX_NX];
 };
 
-struct PeerTable {        // multi-GPU: peer views of each rank's arrays (IPC-mapped), index = rank
-  double* x[MAX_WORLD][2];
-  double* bins[MAX_WORLD];
-  double* mailbox[MAX_WORLD];
+// run-length op list: for c in [0,count): run kind with (a0 + c*da, b0 + c*db)
+enum { OP_PF = 0, OP_AUX_STEP = 1, OP_AUX_CSTATS = 2, OP_FLUSH_WHIST = 3 };
+enum { OPF_SKIP_MEAS = 1, OPF_RAW_WEIGHTS = 2, OPF_POST_CSTATS = 4 };
+struct OpRun {
+  int kind, a0, b0, count, da, db, flags, pad;
 };
 
 struct EngineP {
@@ -82,6 +92,7 @@ struct EngineP {
   double* w;              // [n] log-weights (lazy-normalised)
   double* lam;            // [n] APF lambda (the reference aliases state.we, filtering.jl:200)
   double* bins;           // [n] cumulative weights of the last resample (state.bins)
+  u64* loc;               // [n] scratch: block-local fixed-point prefix of the running scan
   int* j;                 // [n] 0-based global ancestor indices of the last resample (state.j)
   unsigned int* bar;      // grid barrier counter (zeroed by the host before every launch)
   double* partials;       // [MAX_BLOCKS*PS]
@@ -97,15 +108,11 @@ struct EngineP {
   double* w_hist;         // [T][N]
   double* we_hist;        // [T][N]
   long long N;            // global particle count
-  long long n;            // local particle count
-  long long first;        // global index of local particle 0
-  int T;                  // steps in this launch
-  int prog;               // 0: PF program; 1: APF trajectory; 2: APF correct!; 3: APF predict!; 4: APF update!
-  int lead_w;             // PF program starts with W(1)
-  int lead_skip;          // ... which is reduce-only (no measurement update): refreshes ESS for predict!
-  int trail_p;            // PF program ends with P(T)
+  int n;                  // local particle count
+  int first;              // global index of local particle 0
+  int nops;
   int filter;             // LLPF_FILTER_*
-  int aux_tail_pf;        // APF loglik: last step is the inner filter's update! (smoothing.jl:235)
+  OpRun ops[MAX_OPS];
   int time_conv;          // 0: t=(k-1)*Ts (filtering.jl:352) ; 1: t=k*Ts (filtering.jl:181 with index from 1)
   int use_t_override;
   double t_override;
@@ -115,9 +122,9 @@ struct EngineP {
   int scan_mode;          // LLPF_SCAN_*
   int want_xhat;
   int nblocks;            // == gridDim.x
-  long long chunk;        // particles per block
-  RngKey key;
+  int chunk;              // particles per block
   int rank, world;
+  RngKey key;
   double fix_scale, fix_inv;  // fixed-point scan scale: 2^62 / 2^-62 for normalised weights
 };
 
@@ -144,44 +151,71 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// All blocks are co-resident (cooperative launch).  One arrive + spin per block.
+// All blocks are co-resident (cooperative launch).  One arrive + spin per block; the spin polls with
+// relaxed loads and issues a single acquire once the count is reached (one L1 invalidation per barrier).
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     target += nblocks;
-    __threadfence();
     red_release_add_u32(bar, 1u);
-    while ((int)(ld_acquire_u32(bar) - target) < 0) {
+    while ((int)(ld_relaxed_u32(bar) - target) < 0) {
     }
-    __threadfence();
+    (void)ld_acquire_u32(bar);
   }
   __syncthreads();
 }
 
+__host__ __device__ constexpr int mdl_stride(int nx) { return (nx + 1) & ~1; }   // even row stride: rows are 16-byte aligned
+
 struct Shared {
-  double red[NWARP * (3 + MAX_NX)];
+  // model matrices, read with volatile 16-byte shared loads inside the particle loop (see llpf_math.cuh:
+  // the compiler would otherwise hoist ~35 loop-invariant constant loads into registers and spill them)
+  alignas(16) double mA[MAX_NX * MAX_NX];   // row r at mA + r*stride
+  alignas(16) double mL[MAX_NX * MAX_NX];   // lower Cholesky factor of R1
+  alignas(16) double mG[8 * MAX_NX];        // whitened measurement matrix
+  double red_a[NWARP];
+  double red_b[NWARP * (2 + MAX_NX)];
   u64 wtot[NWARP];
   double bu[MAX_NX];
   double yt[8];
   int skip;
   u64 offs[MAX_BLOCKS + 1];     // exclusive block offsets of the fixed-point scan
-  double offd[MAX_BLOCKS + 1];  // the same as doubles == bins at chunk ends
+  alignas(16) MathTab mt;       // log / exp tables + polynomial coefficients of llpf_math.cuh
 };
 
-// max over the block, result in every thread (deterministic)
+template <int K>
+__device__ __forceinline__ void lds_row(const double* row, double (&out)[K]) {   // row is 16-byte aligned, padded
+#pragma unroll
+  for (int c = 0; c < K; c += 2) {
+    const double2 v = lds2v(reinterpret_cast<const double2*>(row + c));
+    out[c] = v.x;
+    if (c + 1 < K) out[c + 1] = v.y;
+  }
+}
+template <int NX, int NY>
+struct ModelP;
+template <int NX, int NY>
+__device__ __forceinline__ void model_to_shared(const ModelP<NX, NY>& M, Shared& sh);
+
+// max over the block, result in every thread (deterministic).  One barrier: red_a and red_b are
+// used alternately (max -> sum -> max -> sum), which orders every reuse behind a barrier.
 __device__ __forceinline__ double block_max(double v, Shared& sh) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh.red_a[threadIdx.x >> 5] = v;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh.red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = sh.red[0];
+  double r = sh.red_a[0];
 #pragma unroll
-  for (int i = 1; i < NWARP; ++i) r = fmax(r, sh.red[i]);
+  for (int i = 1; i < NWARP; ++i) r = fmax(r, sh.red_a[i]);
   return r;
 }
 
@@ -193,17 +227,16 @@ __device__ __forceinline__ void block_sum(double (&v)[M], Shared& sh) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
   }
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int k = 0; k < M; ++k) sh.red[(threadIdx.x >> 5) * M + k] = v[k];
+    for (int k = 0; k < M; ++k) sh.red_b[(threadIdx.x >> 5) * M + k] = v[k];
   }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < M; ++k) {
-    double r = sh.red[k];
+    double r = sh.red_b[k];
 #pragma unroll
-    for (int i = 1; i < NWARP; ++i) r += sh.red[i * M + k];
+    for (int i = 1; i < NWARP; ++i) r += sh.red_b[i * M + k];
     v[k] = r;
   }
 }
@@ -218,9 +251,9 @@ struct Online {
 #pragma unroll
     for (int d = 0; d < NX; ++d) sx[d] = 0.0;
   }
-  __device__ __forceinline__ void add(double wv, const double (&x)[NX], bool with_x) {
+  __device__ __forceinline__ void add(double wv, const double (&x)[NX], bool with_x, const MathTab& T) {
     const double d = wv - m;
-    const double e = exp(-fabs(d));
+    const double e = exp_nonpos(-fabs(d), T);
     if (d > 0.0) {   // new running maximum: rescale what we have
       s = fma(s, e, 1.0);
       q = fma(q, e * e, 1.0);
@@ -251,7 +284,7 @@ template <int NX>
 __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Online<NX>& acc,
                                               bool with_x, unsigned& bar_target) {
   const double mb = block_max(acc.m, sh);
-  const double sc = exp(acc.m - mb);  // 0 for empty threads
+  const double sc = exp_nonpos(acc.m - mb, sh.mt);  // 0 for empty threads
   double v[2 + NX];
   v[0] = acc.s * sc;
   v[1] = acc.q * (sc * sc);
@@ -276,7 +309,7 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
   for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
   for (int b = threadIdx.x; b < P.nblocks; b += BLOCK) {
     const double* p = P.partials + (size_t)b * PS;
-    const double e = exp(__ldcg(p) - m);
+    const double e = exp_nonpos(__ldcg(p) - m, sh.mt);
     t[0] = fma(__ldcg(p + 1), e, t[0]);
     t[1] = fma(__ldcg(p + 2), e * e, t[1]);
     if (with_x) {
@@ -293,7 +326,7 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
 }
 
 // ------------------------------------------------------------------------------------------------
-// scan + search (shared by the engine and the stand-alone resample entry points)
+// scan + source-side index construction (shared by the engine and the stand-alone resample entry)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ u64 to_fixed(double we, double scale) {
   // we*scale in [0,2^62] (normalised weights: scale = 2^62); NaN/negative -> 0
@@ -302,20 +335,18 @@ __device__ __forceinline__ u64 to_fixed(double we, double scale) {
 }
 
 // Stage 1: block-local inclusive scan of the block's chunk [beg,end).
-// FAST  : bins[i] (as u64) = local inclusive fixed-point prefix; tots[b] = block total.
+// FAST  : loc[i] = local inclusive fixed-point prefix; tots[b] = block total.
 // SERIAL: bins[i] = we_i (double); the single-thread pass runs after the barrier.
 template <class WeFn>
-__device__ __forceinline__ void scan_stage1(const EngineP& P, Shared& sh, long long beg, long long end,
-                                            WeFn wefn) {
+__device__ __forceinline__ void scan_stage1(const EngineP& P, Shared& sh, int beg, int end, WeFn wefn) {
   if (P.scan_mode != 0) {
-    for (long long i = beg + threadIdx.x; i < end; i += BLOCK) __stcg(P.bins + i, wefn(i));
+    for (int i = beg + threadIdx.x; i < end; i += BLOCK) __stcg(P.bins + i, wefn(i));
     return;
   }
-  u64* lbins = reinterpret_cast<u64*>(P.bins);
   u64 carry = 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = beg; base < end; base += BLOCK) {
-    const long long i = base + threadIdx.x;
+  for (int base = beg; base < end; base += BLOCK) {
+    const int i = base + threadIdx.x;
     u64 v = (i < end) ? to_fixed(wefn(i), P.fix_scale) : 0ull;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -332,24 +363,22 @@ __device__ __forceinline__ void scan_stage1(const EngineP& P, Shared& sh, long l
       if (k < warp) woff += t;
       rtot += t;
     }
-    if (i < end) __stcg(lbins + i, carry + woff + v);
+    if (i < end) __stcg(P.loc + i, carry + woff + v);
     carry += rtot;
   }
   if (threadIdx.x == 0) __stcg(P.tots + blockIdx.x, carry);
 }
 
-// Stage 2 (after a grid barrier): exclusive block offsets, then finalise bins for the own chunk.
-// Leaves sh.offs / sh.offd filled for FAST mode.  `base_fixed` is this GPU's global CDF offset.
-__device__ __forceinline__ void scan_stage2(const EngineP& P, Shared& sh, long long beg, long long end,
-                                            u64 base_fixed) {
+// After the grid barrier that follows stage 1 (FAST): exclusive block offsets into sh.offs[0..nb]
+// (exact integer arithmetic: any summation order gives the same bits).
+__device__ __forceinline__ void scan_block_offsets(const EngineP& P, Shared& sh, u64 base_fixed) {
   const int nb = P.nblocks;
-  // every block scans all block totals (exact integer arithmetic: any order gives the same bits)
-  __syncthreads();
-  u64 t4[4];
+  constexpr int PER = (MAX_BLOCKS + BLOCK - 1) / BLOCK;
+  u64 t4[PER];
   u64 mine = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int b = threadIdx.x * 4 + k;
+  for (int k = 0; k < PER; ++k) {
+    const int b = threadIdx.x * PER + k;
     t4[k] = (b < nb) ? __ldcg(P.tots + b) : 0ull;
     mine += t4[k];
   }
@@ -360,6 +389,7 @@ __device__ __forceinline__ void scan_stage2(const EngineP& P, Shared& sh, long l
     const u64 t = __shfl_up_sync(0xffffffffu, v, o);
     if (lane >= o) v += t;
   }
+  __syncthreads();
   if (lane == 31) sh.wtot[warp] = v;
   __syncthreads();
   u64 woff = 0;
@@ -368,27 +398,18 @@ __device__ __forceinline__ void scan_stage2(const EngineP& P, Shared& sh, long l
     if (k < warp) woff += sh.wtot[k];
   u64 excl = base_fixed + woff + v - mine;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int b = threadIdx.x * 4 + k;
-    if (b <= nb) {
-      sh.offs[b] = excl;
-      sh.offd[b] = (double)excl * P.fix_inv;
-    }
+  for (int k = 0; k < PER; ++k) {
+    const int b = threadIdx.x * PER + k;
+    if (b <= nb) sh.offs[b] = excl;
     excl += t4[k];
   }
   __syncthreads();
-  const u64 off = sh.offs[blockIdx.x];
-  u64* lbins = reinterpret_cast<u64*>(P.bins);
-  for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
-    const u64 loc = __ldcg(lbins + i);
-    __stcg(P.bins + i, (double)(off + loc) * P.fix_inv);
-  }
 }
 
 // SERIAL mode: the reference's cumsum (resample.jl:19-22), one thread, strict left-to-right f64 adds.
-__device__ __noinline__ void scan_serial(double* bins, long long n) {
+__device__ __noinline__ void scan_serial(double* bins, int n) {
   double acc = __ldcg(bins);
-  long long i = 1;
+  int i = 1;
   for (; i + 8 <= n; i += 8) {
     double v[8];
 #pragma unroll
@@ -405,56 +426,23 @@ __device__ __noinline__ void scan_serial(double* bins, long long n) {
   }
 }
 
-// After the bins barrier in SERIAL mode: block table = bins at chunk ends.
-__device__ __forceinline__ void load_block_table(const EngineP& P, Shared& sh) {
-  __syncthreads();
-  for (int b = threadIdx.x; b <= P.nblocks; b += BLOCK) {
-    if (b == 0) {
-      sh.offd[0] = 0.0;
-    } else {
-      long long e = (long long)b * P.chunk;
-      if (e > P.n) e = P.n;
-      sh.offd[b] = __ldcg(P.bins + e - 1);
-    }
-  }
-  __syncthreads();
-}
-
-// smallest local index a with bins[a] > s  (== the reference's two-pointer search, resample.jl:26-34,
-// expressed as an upper bound).  Requires s < offd[nb].  Two levels: block table, then the chunk.
-__device__ __forceinline__ long long upper_bound_bins(const EngineP& P, const Shared& sh, double s) {
-  int lo = 0, hi = P.nblocks - 1;  // find smallest b with offd[b+1] > s
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (sh.offd[mid + 1] > s) hi = mid; else lo = mid + 1;
-  }
-  long long a = (long long)lo * P.chunk;
-  long long e = a + P.chunk;
-  if (e > P.n) e = P.n;
-  long long b = e - 1;  // bins[b] == offd[lo+1] > s
-  while (a < b) {
-    const long long mid = (a + b) >> 1;
-    if (__ldcg(P.bins + mid) > s) b = mid; else a = mid + 1;
-  }
-  return a;
-}
-
 struct Thresholds {
   double r, step, total, M;
+  int Mi;
   int strategy;
+  uint32_t step_idx;
   const double* u_slots;   // stratified: caller-supplied rand() per slot (stand-alone entry), else RNG
 };
 
 // s[i] = fl(r + fl(i * fl(1/M)))   (Julia StepRangeLen getindex; resample.jl:24) — the
 // product and the sum are rounded separately (no FMA).  Stratified: ((i + rand_i)/M)*bins[N] (resample.jl:49).
-__device__ __forceinline__ double threshold(const Thresholds& th, const RngKey& key, uint32_t step_idx,
-                                            long long gi) {
+__device__ __forceinline__ double threshold(const Thresholds& th, const RngKey& key, int gi) {
   if (th.strategy == 1) {
     double u;
     if (th.u_slots) {
-      u = th.u_slots[gi];
+      u = __ldcg(th.u_slots + gi);
     } else {
-      const uint4 r = rng_block(key, ST_STRAT, step_idx, (unsigned long long)gi, 0);
+      const uint4 r = rng_block(key, ST_STRAT, th.step_idx, (unsigned long long)(unsigned)gi, 0);
       u = uniform53(r.x, r.y);
     }
     return __dmul_rn(__ddiv_rn(__dadd_rn((double)gi, u), th.M), th.total);
@@ -462,14 +450,16 @@ __device__ __forceinline__ double threshold(const Thresholds& th, const RngKey& 
   return __dadd_rn(th.r, __dmul_rn((double)gi, th.step));
 }
 
-__device__ __forceinline__ Thresholds make_thresholds(const EngineP& P, double total, double u01,
-                                                      double Mslots, const double* u_slots) {
+__device__ __forceinline__ Thresholds make_thresholds(const EngineP& P, double total, double u01, int Mslots,
+                                                      uint32_t step_idx, const double* u_slots) {
   Thresholds th;
   th.total = total;
-  th.M = Mslots;
+  th.M = (double)Mslots;
+  th.Mi = Mslots;
   th.strategy = P.strategy;
+  th.step_idx = step_idx;
   th.u_slots = u_slots;
-  th.step = __ddiv_rn(1.0, Mslots);
+  th.step = __ddiv_rn(1.0, th.M);
   // r = rand()*bins[end]/N   (resample.jl:23; note /N, N = length(we))
   th.r = __ddiv_rn(__dmul_rn(u01, total), (double)P.N);
   return th;
@@ -479,12 +469,93 @@ __device__ __forceinline__ double resample_u01(const RngKey& key, uint32_t step_
   return uniform53(r.x, r.y);
 }
 
+// F(v) = min{ i in [0,M] : s_i >= v }  (M if none).  The thresholds are nondecreasing in i, so an
+// estimate from the real-valued inverse plus an exact fix-up (evaluating s_i exactly as the reference
+// does) gives the same partition of the slots as the reference's comparison `s[i] < bins[b]`.
+__device__ __forceinline__ int first_slot_ge(const Thresholds& th, const RngKey& key, double v) {
+  const double t = (th.strategy == 1) ? (v / th.total) * th.M - 1.0 : (v - th.r) * th.M;
+  int i0;
+  if (!(t > 0.0)) i0 = 0;
+  else if (t >= th.M) i0 = th.Mi;
+  else i0 = (int)ceil(t);
+  while (i0 > 0 && threshold(th, key, i0 - 1) >= v) --i0;
+  while (i0 < th.Mi && threshold(th, key, i0) < v) ++i0;
+  return i0;
+}
+
+// write `id` into slots [lo, lo+cnt) of j: short runs by the owning lane, long runs by the whole warp.
+// Must be called by all 32 lanes (cnt = 0 for idle lanes).
+template <class T>
+__device__ __forceinline__ void scatter_runs(T* j, int lo, int cnt, T id) {
+  const int lane = threadIdx.x & 31;
+  if (cnt > 0 && cnt <= 4) {
+    for (int s = 0; s < cnt; ++s) __stcg(j + lo + s, id);
+  }
+  unsigned heavy = __ballot_sync(0xffffffffu, cnt > 4);
+  while (heavy) {
+    const int src = __ffs(heavy) - 1;
+    heavy &= heavy - 1;
+    const int lo_s = __shfl_sync(0xffffffffu, lo, src);
+    const int c = __shfl_sync(0xffffffffu, cnt, src);
+    const T id_s = __shfl_sync(0xffffffffu, id, src);
+    for (int s = lane; s < c; s += 32) __stcg(j + lo_s + s, id_s);
+  }
+}
+
+// The whole resample: scan(we) -> bins (global) -> per-source slot ranges -> j (global, id = jbase + i).
+// Ends with a grid barrier: afterwards j[s] is valid for every slot s < f_total (returned); the
+// remaining slots are the reference's "untouched" entries (resample.jl:26-34).
+template <class JT, class WeFn>
+__device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, int beg, int end, unsigned& bar_target,
+                                                WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
+                                                int Mslots, const double* u_slots, JT* jout, JT jbase,
+                                                double& total_out) {
+  scan_stage1(P, sh, beg, end, wefn);
+  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  double total;
+  u64 off = 0;
+  if (P.scan_mode != 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
+    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+    total = __ldcg(P.bins + P.n - 1);
+  } else {
+    scan_block_offsets(P, sh, 0ull);
+    total = (double)sh.offs[P.nblocks] * P.fix_inv;
+    off = sh.offs[blockIdx.x];
+  }
+  total_out = total;
+  if (gen_u01) u01 = resample_u01(P.key, step_idx);
+  const Thresholds th = make_thresholds(P, total, u01, Mslots, step_idx, u_slots);
+  for (int base = beg; base < end; base += BLOCK) {   // uniform trip count: warp collectives inside
+    const int i = base + threadIdx.x;
+    int f_lo = 0, cnt = 0;
+    if (i < end) {
+      double lo, hi;
+      if (P.scan_mode != 0) {
+        hi = __ldcg(P.bins + i);
+        lo = (i > 0) ? __ldcg(P.bins + i - 1) : 0.0;
+      } else {
+        hi = (double)(off + __ldcg(P.loc + i)) * P.fix_inv;
+        lo = (i > beg) ? (double)(off + __ldcg(P.loc + i - 1)) * P.fix_inv : (double)off * P.fix_inv;
+        __stcg(P.bins + i, hi);
+      }
+      f_lo = first_slot_ge(th, P.key, lo);
+      const int f_hi = (hi > lo) ? first_slot_ge(th, P.key, hi) : f_lo;
+      cnt = f_hi - f_lo;
+    }
+    scatter_runs<JT>(jout, f_lo, cnt, jbase + (JT)i);
+  }
+  const int f_total = first_slot_ge(th, P.key, total);
+  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  return f_total;
+}
+
 // ------------------------------------------------------------------------------------------------
 // models
 // ------------------------------------------------------------------------------------------------
 // quadtank right-hand side, example_quadtank.jl:91-106 (+ the t>500 leak switch of :15-17)
 template <int NX, int NY>
-__device__ __forceinline__ void quadtank_rhs(const ModelP<NX, NY>& M, const double* bu, double t,
+__device__ __forceinline__ void quadtank_rhs(const ModelP<NX, NY>& M, const double (&bu)[NX], double t,
                                              const double (&h)[NX], double (&xd)[NX]) {
   const double c1 = (t > M.t_switch) ? M.qt[1] : M.qt[0];
   const double co = M.qt[0], ci = M.qt[2], tg = M.qt[3];
@@ -500,15 +571,17 @@ __device__ __forceinline__ void quadtank_rhs(const ModelP<NX, NY>& M, const doub
 
 // dynamics(x,u,p,t) without noise, in place.  DYN==0: A*x .+ B*u ; DYN==1: rk4(quadtank) utils.jl:220-237
 template <int NX, int NY, int DYN>
-__device__ __forceinline__ void dynamics_mean(const ModelP<NX, NY>& M, const double* bu, double t,
+__device__ __forceinline__ void dynamics_mean(const ModelP<NX, NY>& M, const Shared& sh, const double (&bu)[NX], double t,
                                               double (&x)[NX]) {
   if (DYN == 0) {
     double xn[NX];
 #pragma unroll
     for (int r = 0; r < NX; ++r) {
-      double acc = M.A[r * NX] * x[0];
+      double a[NX];
+      lds_row<NX>(sh.mA + r * mdl_stride(NX), a);
+      double acc = a[0] * x[0];
 #pragma unroll
-      for (int c = 1; c < NX; ++c) acc = fma(M.A[r * NX + c], x[c], acc);
+      for (int c = 1; c < NX; ++c) acc = fma(a[c], x[c], acc);
       xn[r] = acc + bu[r];
     }
 #pragma unroll
@@ -537,426 +610,438 @@ __device__ __forceinline__ void dynamics_mean(const ModelP<NX, NY>& M, const dou
 // x += L1*z, z ~ N(0,I) from the (ST_DYN, step, particle) counter  (PFtypes.jl:135,153; utils.jl:260-268)
 template <int NX, int NY>
 __device__ __forceinline__ void add_dynamics_noise(const ModelP<NX, NY>& M, const RngKey& key,
-                                                   uint32_t step_idx, long long gi, double (&x)[NX]) {
+                                                   uint32_t step_idx, int gi, double (&x)[NX], const Shared& sh) {
   double z[NX];
-  normals<NX>(key, ST_DYN, step_idx, (unsigned long long)gi, z);
+  normals<NX>(key, ST_DYN, step_idx, (unsigned long long)(unsigned)gi, z, sh.mt);
 #pragma unroll
   for (int r = 0; r < NX; ++r) {
-    double acc = 0.0;
+    double l[NX];
+    lds_row<NX>(sh.mL + r * mdl_stride(NX), l);
+    double acc = x[r];
 #pragma unroll
-    for (int c = 0; c <= r; ++c) acc = fma(M.L1[r * NX + c], z[c], acc);
-    x[r] += acc;
+    for (int c = 0; c <= r; ++c) acc = fma(l[c], z[c], acc);
+    x[r] = acc;
   }
 }
 
 // logpdf(N(0,R2), y - C x) = c0 - |W(y - Cx)|^2/2 = c0 - |yt - G x|^2/2   (utils.jl:252-257)
 template <int NX, int NY>
-__device__ __forceinline__ double meas_loglik(const ModelP<NX, NY>& M, const double* yt,
+__device__ __forceinline__ double meas_loglik(const ModelP<NX, NY>& M, const Shared& sh, const double (&yt)[NY],
                                               const double (&x)[NX]) {
   double q = 0.0;
 #pragma unroll
   for (int a = 0; a < NY; ++a) {
+    double g[NX];
+    lds_row<NX>(sh.mG + a * mdl_stride(NX), g);
     double v = yt[a];
 #pragma unroll
-    for (int c = 0; c < NX; ++c) v = fma(-M.G[a * NX + c], x[c], v);
+    for (int c = 0; c < NX; ++c) v = fma(-g[c], x[c], v);
     q = fma(v, v, q);
   }
   return fma(-0.5, q, M.c0);
 }
 
+template <int NX, int NY>
+__device__ __forceinline__ void model_to_shared(const ModelP<NX, NY>& M, Shared& sh) {
+  constexpr int S = mdl_stride(NX);
+  for (int k = threadIdx.x; k < NX * S; k += BLOCK) {
+    const int r = k / S, c = k % S;
+    sh.mA[k] = (c < NX) ? M.A[r * NX + c] : 0.0;
+    sh.mL[k] = (c < NX) ? M.L1[r * NX + c] : 0.0;
+  }
+  for (int k = threadIdx.x; k < NY * S; k += BLOCK) {
+    const int r = k / S, c = k % S;
+    sh.mG[k] = (c < NX) ? M.G[r * NX + c] : 0.0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// the engine
+// per-pass helpers
 // ------------------------------------------------------------------------------------------------
-template <int NX, int NY, int DYN>
-struct Engine {
-  const EngineP& P;
-  const ModelP<NX, NY>& M;
-  Shared& sh;
-  Scalars sc;          // every block carries an identical copy, block 0 writes it back at the end
-  unsigned bar_target;
-  long long beg, end;  // own chunk (local indices)
+struct Ctx {
+  int beg, end;        // own chunk (local indices)
   double lwN;          // -log(N)  (filtering.jl:11)
   double lw1N;         // log(1/N) (utils.jl:75)
+  unsigned bar_target;
+};
 
-  __device__ Engine(const EngineP& p, const ModelP<NX, NY>& m, Shared& s) : P(p), M(m), sh(s) {
-    sc = *P.sc;
-    bar_target = 0;
-    beg = (long long)blockIdx.x * P.chunk;
-    end = beg + P.chunk;
-    if (end > P.n) end = P.n;
-    if (beg > P.n) beg = P.n;
-    lwN = -log((double)P.N);
-    lw1N = log(1.0 / (double)P.N);
+// by-value snapshot of the lazy weight state
+struct WState {
+  int uniform, pend;
+  double pm, pls, inv_s, wu, weu;
+  const double* w;
+  const MathTab* T;
+  // logical (normalised) log-weight of local particle i: (w - offset) - log1p(s)  utils.jl:20,25
+  __device__ __forceinline__ double weight_norm(int i) const {
+    if (uniform) return wu;
+    const double wr = __ldcg(w + i);
+    return pend ? (wr - pm) - pls : wr;
   }
+  // we = exp(w - offset) * 1/(s+1)   utils.jl:21-24
+  __device__ __forceinline__ double expweight(int i) const {
+    if (uniform) return weu;
+    const double wr = __ldcg(w + i);
+    return pend ? exp_nonpos(wr - pm, *T) * inv_s : exp(wr);
+  }
+};
+__device__ __forceinline__ WState make_wstate(const EngineP& P, const Scalars& sc, const Ctx& cx, const MathTab& T) {
+  WState ws;
+  ws.uniform = sc.uniform; ws.pend = sc.pend;
+  ws.pm = sc.pend_m; ws.pls = sc.pend_ls;
+  ws.inv_s = sc.pend ? 1.0 / sc.pend_s : 1.0;
+  ws.wu = (sc.uniform == 1) ? cx.lwN : cx.lw1N;
+  ws.weu = 1.0 / (double)P.N;
+  ws.w = P.w;
+  ws.T = &T;
+  return ws;
+}
 
-  __device__ __forceinline__ double step_time(int k) const {  // k is 1-based
-    if (P.use_t_override) return P.t_override;
-    return (double)(k - 1 + P.time_conv) * P.Ts;
-  }
+__device__ __forceinline__ double step_time(const EngineP& P, int k) {  // k is 1-based
+  if (P.use_t_override) return P.t_override;
+  return (double)(k - 1 + P.time_conv) * P.Ts;
+}
 
-  // per-pass uniform data: bu = B*u_k (or the quadtank input terms), yt = W*y_k, skip = any(isnan(y))
-  __device__ __forceinline__ void stage_step(int k_u, int k_y) {
-    __syncthreads();
-    if (k_u > 0 && threadIdx.x < NX) {
-      const double* u = P.u + (size_t)(k_u - 1) * M.nu;
-      double acc = 0.0;
-      if (DYN == 0) {
-        for (int c = 0; c < M.nu; ++c) acc = fma(M.B[threadIdx.x * MAX_NU + c], u[c], acc);
-      } else {
-        // {g1k1/A*u1, g2k2/A*u2, (1-g2)k2/A*u2, (1-g1)k1/A*u1}
-        const int ui = (threadIdx.x == 0 || threadIdx.x == 3) ? 0 : 1;
-        acc = M.qt[4 + threadIdx.x] * u[ui];
-      }
-      sh.bu[threadIdx.x] = acc;
-    }
-    if (k_y > 0 && threadIdx.x == 32) {
-      const double* y = P.y + (size_t)(k_y - 1) * NY;
-      int skip = 0;
-#pragma unroll
-      for (int a = 0; a < NY; ++a) {
-        if (isnan(y[a])) skip = 1;
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c <= a; ++c) acc = fma(M.W[a * NY + c], y[c], acc);
-        sh.yt[a] = acc;
-      }
-      sh.skip = skip;
-    }
-    __syncthreads();
-  }
-
-  __device__ __forceinline__ void load_x(const double* buf, long long i, double (&x)[NX]) const {
-#pragma unroll
-    for (int d = 0; d < NX; ++d) x[d] = buf[(size_t)d * P.ld + i];
-  }
-  __device__ __forceinline__ void load_x_cg(const double* buf, long long i, double (&x)[NX]) const {
-#pragma unroll
-    for (int d = 0; d < NX; ++d) x[d] = __ldcg(buf + (size_t)d * P.ld + i);
-  }
-  __device__ __forceinline__ void store_x(double* buf, long long i, const double (&x)[NX]) const {
-#pragma unroll
-    for (int d = 0; d < NX; ++d) buf[(size_t)d * P.ld + i] = x[d];
-  }
-  __device__ __forceinline__ void store_hist_x(int k, long long gi, const double (&x)[NX]) const {
-    double* p = P.x_hist + ((size_t)(k - 1) * P.N + gi) * NX;
-#pragma unroll
-    for (int d = 0; d < NX; ++d) __stcs(p + d, x[d]);
-  }
-
-  // by-value snapshot of the lazy weight state (keeps the particle loops free of this->sc reloads)
-  struct WState {
-    int uniform, pend;
-    double pm, pls, inv_s, wu, weu;
-    const double* w;
-    // logical (normalised) log-weight of local particle i: (w - offset) - log1p(s)  utils.jl:20,25
-    __device__ __forceinline__ double weight_norm(long long i) const {
-      if (uniform) return wu;
-      const double wr = w[i];
-      return pend ? (wr - pm) - pls : wr;
-    }
-    // we = exp(w - offset) * 1/(s+1)   utils.jl:21-24
-    __device__ __forceinline__ double expweight(long long i) const {
-      if (uniform) return weu;
-      const double wr = w[i];
-      return pend ? exp(wr - pm) * inv_s : exp(wr);
-    }
-  };
-  __device__ __forceinline__ WState wstate() const {
-    WState ws;
-    ws.uniform = sc.uniform; ws.pend = sc.pend;
-    ws.pm = sc.pend_m; ws.pls = sc.pend_ls;
-    ws.inv_s = sc.pend ? 1.0 / sc.pend_s : 1.0;
-    ws.wu = (sc.uniform == 1) ? lwN : lw1N;
-    ws.weu = 1.0 / (double)P.N;
-    ws.w = P.w;
-    return ws;
-  }
-
-  // ---- resampling: bins <- scan(we); returns the thresholds --------------------------------------
-  template <class WeFn>
-  __device__ __forceinline__ Thresholds build_bins(WeFn wefn) {
-    scan_stage1(P, sh, beg, end, wefn);
-    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-    if (P.scan_mode != 0) {
-      if (blockIdx.x == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
-      grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-      load_block_table(P, sh);
+// per-pass uniform data: bu = B*u_k (or the quadtank input terms), yt = W*y_k, skip = any(isnan(y))
+template <int NX, int NY, int DYN>
+__device__ __forceinline__ void stage_step(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh, int k_u, int k_y,
+                                           double (&bu)[NX], double (&yt)[NY], bool& skip) {
+  __syncthreads();
+  if (k_u > 0 && threadIdx.x < NX) {
+    const double* u = P.u + (size_t)(k_u - 1) * M.nu;
+    double acc = 0.0;
+    if (DYN == 0) {
+      for (int c = 0; c < M.nu; ++c) acc = fma(M.B[threadIdx.x * MAX_NU + c], __ldg(u + c), acc);
     } else {
-      scan_stage2(P, sh, beg, end, 0ull);
-      grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+      // {g1k1/A*u1, g2k2/A*u2, (1-g2)k2/A*u2, (1-g1)k1/A*u1}
+      const int ui = (threadIdx.x == 0 || threadIdx.x == 3) ? 0 : 1;
+      acc = M.qt[4 + threadIdx.x] * __ldg(u + ui);
     }
-    const double total = sh.offd[P.nblocks];
-    sc.bins_total = total;
-    return make_thresholds(P, total, resample_u01(P.key, (uint32_t)sc.t_index), (double)P.N, nullptr);
+    sh.bu[threadIdx.x] = acc;
   }
-
-  // ancestor (local==global index, world==1) of output slot i; stale slots keep state.j (resample.jl:26-34)
-  __device__ __forceinline__ long long ancestor(const Thresholds& th, long long i) const {
-    const double s = threshold(th, P.key, (uint32_t)sc.t_index, P.first + i);
-    if (s < th.total) return upper_bound_bins(P, sh, s);
-    return sc.j_identity ? i : (long long)P.j[i];
+  if (k_y > 0 && threadIdx.x == 32) {
+    const double* y = P.y + (size_t)(k_y - 1) * NY;
+    int sk = 0;
+    double yv[NY];
+#pragma unroll
+    for (int a = 0; a < NY; ++a) {
+      yv[a] = __ldg(y + a);
+      if (isnan(yv[a])) sk = 1;
+    }
+#pragma unroll
+    for (int a = 0; a < NY; ++a) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c <= a; ++c) acc = fma(M.W[a * NY + c], yv[c], acc);
+      sh.yt[a] = acc;
+    }
+    sh.skip = sk;
   }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < NX; ++r) bu[r] = (k_u > 0) ? sh.bu[r] : 0.0;
+#pragma unroll
+  for (int a = 0; a < NY; ++a) yt[a] = (k_y > 0) ? sh.yt[a] : 0.0;
+  skip = (k_y > 0) ? (sh.skip != 0) : false;
+}
 
-  __device__ __forceinline__ void publish_step(int k, const Stats& st) {
-    const double ls = log(st.s);
-    const double ll = st.m + ls;  // log1p(s)+offset of utils.jl:26 (s there excludes the arg-max term)
-    sc.pend = 1; sc.uniform = 0; sc.stats_ahead = 0; sc.stats_valid = 1;
-    sc.pend_m = st.m; sc.pend_ls = ls; sc.pend_s = st.s;
-    sc.ess = st.s * st.s / st.q;   // effective_particles = 1/sum(abs2, we)  resample.jl:1-2
-    sc.ll_last = ll;
-    sc.ll_total += ll;
-    if (!(fabs(ll) <= DBL_MAX)) sc.nonfinite = 1;
+template <int NX>
+__device__ __forceinline__ void load_x(const double* buf, long long ld, int i, double (&x)[NX]) {
 #pragma unroll
-    for (int d = 0; d < NX; ++d) sc.xhat[d] = st.sx[d] / st.s;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && k > 0) {
-      if (P.ll_steps) P.ll_steps[k - 1] = ll;
-      if (P.ess_steps) P.ess_steps[k - 1] = sc.ess;
-      if (P.xhat) {
+  for (int d = 0; d < NX; ++d) x[d] = __ldcg(buf + (size_t)d * ld + i);
+}
+template <int NX>
+__device__ __forceinline__ void store_x(double* buf, long long ld, int i, const double (&x)[NX]) {
 #pragma unroll
-        for (int d = 0; d < NX; ++d) P.xhat[(size_t)(k - 1) * NX + d] = sc.xhat[d];
-      }
+  for (int d = 0; d < NX; ++d) __stcg(buf + (size_t)d * ld + i, x[d]);
+}
+template <int NX>
+__device__ __forceinline__ void store_hist_x(const EngineP& P, int k, int gi, const double (&x)[NX]) {
+  double* p = P.x_hist + ((size_t)(k - 1) * P.N + gi) * NX;
+#pragma unroll
+  for (int d = 0; d < NX; ++d) __stcs(p + d, x[d]);
+}
+
+template <int NX>
+__device__ __forceinline__ void publish_step(const EngineP& P, Scalars& sc, int k, const Stats& st) {
+  const double ls = log(st.s);
+  const double ll = st.m + ls;  // log1p(s)+offset of utils.jl:26 (s there excludes the arg-max term)
+  sc.pend = 1; sc.uniform = 0; sc.stats_ahead = 0; sc.stats_valid = 1;
+  sc.pend_m = st.m; sc.pend_ls = ls; sc.pend_s = st.s;
+  sc.ess = st.s * st.s / st.q;   // effective_particles = 1/sum(abs2, we)  resample.jl:1-2
+  sc.ll_last = ll;
+  sc.ll_total += ll;
+  if (!(fabs(ll) <= DBL_MAX)) sc.nonfinite = 1;
+#pragma unroll
+  for (int d = 0; d < NX; ++d) sc.xhat[d] = st.sx[d] / st.s;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && k > 0) {
+    if (P.ll_steps) P.ll_steps[k - 1] = ll;
+    if (P.ess_steps) P.ess_steps[k - 1] = sc.ess;
+    if (P.xhat) {
+#pragma unroll
+      for (int d = 0; d < NX; ++d) P.xhat[(size_t)(k - 1) * NX + d] = sc.xhat[d];
     }
   }
+}
 
+// ---- PF / AdvancedPF pass: [predict!(k_prop)] fused with [correct!(k_weigh)] -----------------------
+// k_prop / k_weigh are 1-based step numbers, 0 = phase absent.
+template <int NX, int NY, int DYN>
+__device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh, Scalars& sc,
+                                        Ctx& cx, int k_prop, int k_weigh, int flags) {
+  if (flags & OPF_RAW_WEIGHTS) { sc.pend = 0; sc.stats_ahead = 0; }
+  const bool skip_meas = (flags & OPF_SKIP_MEAS) != 0;
+  double bu[NX], yt[NY];
+  bool nan_y;
+  stage_step<NX, NY, DYN>(P, M, sh, k_prop, skip_meas ? 0 : k_weigh, bu, yt, nan_y);
+  const bool skip = skip_meas || nan_y;
   // shouldresample(pf)  resample.jl:5-10
-  __device__ __forceinline__ bool should_resample() const {
-    if (P.thr == 1.0) return true;
-    return sc.ess < (double)P.N * P.thr;
+  const bool res = (k_prop > 0) && ((P.thr == 1.0) || (sc.ess < (double)P.N * P.thr));
+  const bool hist_w = (P.w_hist != nullptr) && (k_prop > 0);   // weights of step k_prop, just corrected
+  const WState ws = make_wstate(P, sc, cx, sh.mt);
+  const uint32_t step_idx = (uint32_t)sc.t_index;
+  const size_t hbase = hist_w ? (size_t)(k_prop - 1) * P.N + P.first : 0;
+  double* const wh = P.w_hist;
+  double* const weh = P.we_hist;
+  int f_total = 0;
+  if (res) {
+    double total;
+    f_total = resample_indices<int>(
+        P, sh, cx.beg, cx.end, cx.bar_target,
+        [=](int i) {
+          const double we = ws.expweight(i);
+          if (hist_w) {
+            __stcs(wh + hbase + i, ws.weight_norm(i));
+            __stcs(weh + hbase + i, we);
+          }
+          return we;
+        },
+        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total);
+    sc.bins_total = total;
   }
-
-  // ---- PF / AdvancedPF pass: [predict!(k_prop)] fused with [correct!(k_weigh)] ---------------------
-  // k_prop / k_weigh are 1-based step numbers, 0 = phase absent.  skip_meas: reduce-only correct!.
-  __device__ __noinline__ void pf_pass(int k_prop, int k_weigh, bool skip_meas) {
-    stage_step(k_prop, skip_meas ? 0 : k_weigh);
-    const bool skip = skip_meas || (k_weigh > 0 && sh.skip);
-    const bool res = (k_prop > 0) && should_resample();
-    const bool hist_w = (P.w_hist != nullptr) && (k_prop > 0);   // weights of step k_prop, just corrected
-    const WState ws = wstate();
-    const EngineP& Pr = P;
-    Thresholds th;
+  const double* src = P.x[sc.cur];
+  double* dst = res ? P.x[sc.cur ^ 1] : P.x[sc.cur];
+  const double tprop = step_time(P, k_prop);
+  const bool with_x = (P.want_xhat != 0);
+  const int jid = sc.j_identity;
+  Online<NX> acc;
+  acc.init();
+  for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
+    const int gi = P.first + i;
+    double x[NX];
+    double wv;
     if (res) {
-      th = build_bins([=, &Pr](long long i) {
-        const double we = ws.expweight(i);
-        if (hist_w) {
-          const size_t o = (size_t)(k_prop - 1) * Pr.N + Pr.first + i;
-          __stcs(Pr.w_hist + o, ws.weight_norm(i));
-          __stcs(Pr.we_hist + o, we);
-        }
-        return we;
-      });
-    }
-    const double* src = P.x[sc.cur];
-    double* dst = res ? P.x[sc.cur ^ 1] : P.x[sc.cur];
-    const double tprop = step_time(k_prop);
-    const bool with_x = (P.want_xhat != 0);
-    Online<NX> acc;
-    acc.init();
-    for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
-      const long long gi = P.first + i;
-      double x[NX];
-      double wv;
-      if (res) {
-        const long long a = ancestor(th, i);
-        load_x_cg(src, a, x);
-        P.j[i] = (int)a;
-        wv = lw1N;  // reset_weights!  utils.jl:75
-      } else {
-        load_x(src, i, x);
-        wv = ws.weight_norm(i);
-        if (hist_w) {
-          const size_t o = (size_t)(k_prop - 1) * P.N + gi;
-          __stcs(P.w_hist + o, wv);
-          __stcs(P.we_hist + o, ws.expweight(i));
-        }
+      int a;
+      if (gi < f_total) {
+        a = __ldcg(P.j + i);
+      } else {                       // untouched entry (resample.jl:26-34): keep state.j
+        a = jid ? gi : __ldcg(P.j + i);
+        __stcg(P.j + i, a);
       }
-      if (k_prop > 0) {
-        dynamics_mean<NX, NY, DYN>(M, sh.bu, tprop, x);
-        add_dynamics_noise<NX, NY>(M, P.key, (uint32_t)sc.t_index, gi, x);
-        store_x(dst, i, x);
-      }
-      if (k_weigh > 0) {
-        if (P.x_hist) store_hist_x(k_weigh, gi, x);
-        if (!skip) wv += meas_loglik<NX, NY>(M, sh.yt, x);
-        P.w[i] = wv;
-        acc.add(wv, x, with_x);
+      load_x<NX>(src, P.ld, a - P.first, x);
+      wv = cx.lw1N;                  // reset_weights!  utils.jl:75
+    } else {
+      load_x<NX>(src, P.ld, i, x);
+      wv = ws.weight_norm(i);
+      if (hist_w) {
+        __stcs(wh + hbase + i, wv);
+        __stcs(weh + hbase + i, ws.expweight(i));
       }
     }
     if (k_prop > 0) {
-      if (res) {
-        sc.cur ^= 1;
-        sc.uniform = 2; sc.pend = 0; sc.stats_ahead = 0;
-        sc.ess = (double)P.N; sc.stats_valid = 1;
-        sc.j_identity = 0;
-        sc.resample_count += 1;
-      } else {
-        sc.j_identity = 1;   // s.j .= 1:N  filtering.jl:148
-      }
-      sc.last_resampled = res ? 1 : 0;
-      if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k_prop - 1] = res ? 1 : 0;
-      sc.t_index += 1;       // filtering.jl:152
+      dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
+      add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);
+      store_x<NX>(dst, P.ld, i, x);
     }
     if (k_weigh > 0) {
-      const Stats st = reduce_stats<NX>(P, sh, acc, with_x, bar_target);
-      publish_step(k_weigh, st);
+      if (P.x_hist) store_hist_x<NX>(P, k_weigh, gi, x);
+      if (!skip) wv += meas_loglik<NX, NY>(M, sh, yt, x);
+      __stcg(P.w + i, wv);
+      acc.add(wv, x, with_x, sh.mt);
     }
   }
+  if (k_prop > 0) {
+    if (res) {
+      sc.cur ^= 1;
+      sc.uniform = 2; sc.pend = 0; sc.stats_ahead = 0;
+      sc.ess = (double)P.N; sc.stats_valid = 1;
+      sc.j_identity = 0;
+      sc.resample_count += 1;
+    } else {
+      sc.j_identity = 1;   // s.j .= 1:N  filtering.jl:148
+    }
+    sc.last_resampled = res ? 1 : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k_prop - 1] = res ? 1 : 0;
+    sc.t_index += 1;       // filtering.jl:152
+  }
+  if (k_weigh > 0) {
+    const Stats st = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target);
+    publish_step<NX>(P, sc, k_weigh, st);
+  }
+}
 
-  // ---- AuxiliaryParticleFilter predict!(pfa,u,y1,p,t)  filtering.jl:195-217 (and :219-234) ----------
-  // A: x̄ = f(x) (no noise) ; λ = logpdf(y1 - C x̄) ; v = w + λ ; expnormalize!(v)  -> W
-  // scan(W) -> bins -> j
-  // B: x = x̄[j] + L z ; w = λ - log N (UNresampled λ, :210-213) ; stats of the new w == next correct!
-  __device__ __noinline__ void aux_step(int k, int k_y1) {
-    stage_step(k, k_y1);
-    const bool skip = sh.skip;
-    const bool adv = (P.filter == 3);
-    const double tprop = step_time(k);
-    const double* cur = P.x[sc.cur];
-    double* oth = P.x[sc.cur ^ 1];
-    const bool hist_w = (P.w_hist != nullptr);
-    const WState ws = wstate();
-    Online<NX> acc;
-    acc.init();
-    for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
-      double x[NX];
-      load_x(cur, i, x);
-      const double wn = ws.weight_norm(i);
-      if (hist_w) {
-        const size_t o = (size_t)(k - 1) * P.N + P.first + i;
-        __stcs(P.w_hist + o, wn);
-        __stcs(P.we_hist + o, ws.expweight(i));
-      }
-      dynamics_mean<NX, NY, DYN>(M, sh.bu, tprop, x);           // :199 no noise
-      if (!adv) store_x(oth, i, x);
-      const double lam = skip ? 0.0 : meas_loglik<NX, NY>(M, sh.yt, x);  // :200-202
-      P.lam[i] = lam;
-      const double v = wn + lam;                                 // :203
-      P.w[i] = v;
-      acc.add(v, x, false);
+// ---- AuxiliaryParticleFilter predict!(pfa,u,y1,p,t)  filtering.jl:195-217 (and :219-234) -------------
+// A: xbar = f(x) (no noise) ; lam = logpdf(y1 - C xbar) ; v = w + lam ; expnormalize!(v)  -> W
+// scan(W) -> bins -> j
+// B: x = xbar[j] + L z ; w = lam - log N (UNresampled lam, :210-213) ; stats of the new w == next correct!
+template <int NX, int NY, int DYN>
+__device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh, Scalars& sc,
+                                         Ctx& cx, int k, int k_y1) {
+  double bu[NX], yt[NY];
+  bool skip;
+  stage_step<NX, NY, DYN>(P, M, sh, k, k_y1, bu, yt, skip);
+  const bool adv = (P.filter == 3);
+  const double tprop = step_time(P, k);
+  const double* cur = P.x[sc.cur];
+  double* oth = P.x[sc.cur ^ 1];
+  const bool hist_w = (P.w_hist != nullptr);
+  const WState ws = make_wstate(P, sc, cx, sh.mt);
+  const uint32_t step_idx = (uint32_t)sc.t_index;
+  const size_t hbase = hist_w ? (size_t)(k - 1) * P.N + P.first : 0;
+  Online<NX> acc;
+  acc.init();
+  for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
+    double x[NX];
+    load_x<NX>(cur, P.ld, i, x);
+    const double wn = ws.weight_norm(i);
+    if (hist_w) {
+      __stcs(P.w_hist + hbase + i, wn);
+      __stcs(P.we_hist + hbase + i, ws.expweight(i));
     }
-    const Stats s1 = reduce_stats<NX>(P, sh, acc, false, bar_target);
-    const double inv1 = 1.0 / s1.s;
-    // expnormalize!(w): exp(w-offset)*1/(s+1)   utils.jl:57-63 ; then resample (always)  :205
-    const double m1 = s1.m;
-    const double* wraw = P.w;
-    const Thresholds th = build_bins([=](long long i) { return exp(wraw[i] - m1) * inv1; });
-    const bool with_x = (P.want_xhat != 0);
-    const double lN = log((double)P.N);
-    acc.init();
-    for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
-      const long long gi = P.first + i;
-      const long long a = ancestor(th, i);
-      P.j[i] = (int)a;
-      double x[NX];
-      double wnew;
-      if (adv) {
-        load_x_cg(cur, a, x);                                    // :230 propagate again from xprev[j]
-        dynamics_mean<NX, NY, DYN>(M, sh.bu, tprop, x);
-        add_dynamics_noise<NX, NY>(M, P.key, (uint32_t)sc.t_index, gi, x);
-        store_x(oth, i, x);
-        wnew = lw1N;                                             // :228 reset_weights!
-      } else {
-        load_x_cg(oth, a, x);                                    // :207 permute_with_buffer!
-        add_dynamics_noise<NX, NY>(M, P.key, (uint32_t)sc.t_index, gi, x);  // :208 add_noise!
-        store_x(P.x[sc.cur], i, x);
-        wnew = P.lam[i] - lN;                                    // :210-213
-      }
-      if (P.x_hist) store_hist_x(k + 1, gi, x);
-      P.w[i] = wnew;
-      acc.add(wnew, x, with_x);
+    dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);                 // :199 no noise
+    if (!adv) store_x<NX>(oth, P.ld, i, x);
+    const double lam = skip ? 0.0 : meas_loglik<NX, NY>(M, sh, yt, x);  // :200-202
+    __stcg(P.lam + i, lam);
+    const double v = wn + lam;                                    // :203
+    __stcg(P.w + i, v);
+    acc.add(v, x, false, sh.mt);
+  }
+  const Stats s1 = reduce_stats<NX>(P, sh, acc, false, cx.bar_target);
+  const double inv1 = 1.0 / s1.s;
+  const double m1 = s1.m;
+  const double* wraw = P.w;
+  const MathTab* mtp = &sh.mt;
+  // expnormalize!(w): exp(w-offset)*1/(s+1)   utils.jl:57-63 ; then resample (always)  :205
+  double total;
+  const int f_total = resample_indices<int>(
+      P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return exp_nonpos(__ldcg(wraw + i) - m1, *mtp) * inv1; }, 0.0, true,
+      step_idx, (int)P.N, nullptr, P.j, P.first, total);
+  sc.bins_total = total;
+  const bool with_x = (P.want_xhat != 0);
+  const double lN = log((double)P.N);
+  const int jid = sc.j_identity;
+  acc.init();
+  for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
+    const int gi = P.first + i;
+    int a;
+    if (gi < f_total) {
+      a = __ldcg(P.j + i);
+    } else {
+      a = jid ? gi : __ldcg(P.j + i);
+      __stcg(P.j + i, a);
     }
-    if (adv) sc.cur ^= 1;
-    sc.j_identity = 0;
-    sc.resample_count += 1;
-    sc.last_resampled = 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k - 1] = 1;
-    sc.t_index += 1;                                             // :215
-    const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, bar_target);
-    // stats of the raw w[] are ready; correct! (filtering.jl:170-174) has not been *called* yet
-    sc.pend = 0; sc.uniform = 0;
-    sc.stats_ahead = 1; sc.stats_valid = 0;
-    sc.pend_m = s2.m; sc.pend_ls = log(s2.s); sc.pend_s = s2.s;
-    sc.ess = s2.s * s2.s / s2.q;
+    double x[NX];
+    double wnew;
+    if (adv) {
+      load_x<NX>(cur, P.ld, a - P.first, x);                     // :230 propagate again from xprev[j]
+      dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
+      add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);
+      store_x<NX>(oth, P.ld, i, x);
+      wnew = cx.lw1N;                                            // :228 reset_weights!
+    } else {
+      load_x<NX>(oth, P.ld, a - P.first, x);                     // :207 permute_with_buffer!
+      add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);     // :208 add_noise!
+      store_x<NX>(P.x[sc.cur], P.ld, i, x);
+      wnew = __ldcg(P.lam + i) - lN;                             // :210-213
+    }
+    if (P.x_hist) store_hist_x<NX>(P, k + 1, gi, x);
+    __stcg(P.w + i, wnew);
+    acc.add(wnew, x, with_x, sh.mt);
+  }
+  if (adv) sc.cur ^= 1;
+  sc.j_identity = 0;
+  sc.resample_count += 1;
+  sc.last_resampled = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k - 1] = 1;
+  sc.t_index += 1;                                               // :215
+  const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target);
+  // stats of the raw w[] are ready; correct! (filtering.jl:170-174) has not been *called* yet
+  sc.pend = 0; sc.uniform = 0;
+  sc.stats_ahead = 1; sc.stats_valid = 0;
+  sc.pend_m = s2.m; sc.pend_ls = log(s2.s); sc.pend_s = s2.s;
+  sc.ess = s2.s * s2.s / s2.q;
 #pragma unroll
-    for (int d = 0; d < NX; ++d) sc.xhat[d] = s2.sx[d] / s2.s;
-  }
+  for (int d = 0; d < NX; ++d) sc.xhat[d] = s2.sx[d] / s2.s;
+}
 
-  // correct!(pfa,...) = logsumexp!(state) only  filtering.jl:170-174, using the stats found by aux_step
-  __device__ __forceinline__ void aux_correct_from_stats(int k) {
-    const double ll = sc.pend_m + sc.pend_ls;
-    sc.pend = 1; sc.stats_ahead = 0; sc.stats_valid = 1;
-    sc.ll_last = ll;
-    sc.ll_total += ll;
-    if (!(fabs(ll) <= DBL_MAX)) sc.nonfinite = 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && k > 0) {
-      if (P.ll_steps) P.ll_steps[k - 1] = ll;
-      if (P.ess_steps) P.ess_steps[k - 1] = sc.ess;
-      if (P.xhat) {
+// correct!(pfa,...) = logsumexp!(state) only  filtering.jl:170-174, using the stats found by aux_step
+template <int NX>
+__device__ __forceinline__ void aux_correct_from_stats(const EngineP& P, Scalars& sc, int k) {
+  const double ll = sc.pend_m + sc.pend_ls;
+  sc.pend = 1; sc.stats_ahead = 0; sc.stats_valid = 1;
+  sc.ll_last = ll;
+  sc.ll_total += ll;
+  if (!(fabs(ll) <= DBL_MAX)) sc.nonfinite = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && k > 0) {
+    if (P.ll_steps) P.ll_steps[k - 1] = ll;
+    if (P.ess_steps) P.ess_steps[k - 1] = sc.ess;
+    if (P.xhat) {
 #pragma unroll
-        for (int d = 0; d < NX; ++d) P.xhat[(size_t)(k - 1) * NX + d] = sc.xhat[d];
-      }
+      for (int d = 0; d < NX; ++d) P.xhat[(size_t)(k - 1) * NX + d] = sc.xhat[d];
     }
   }
+}
 
-  // write the weight history of step k for filters whose last step has no following pass
-  __device__ void flush_weight_history(int k) {
-    if (!P.w_hist) return;
-    const WState ws = wstate();
-    for (long long i = beg + threadIdx.x; i < end; i += BLOCK) {
-      const size_t o = (size_t)(k - 1) * P.N + P.first + i;
-      __stcs(P.w_hist + o, ws.weight_norm(i));
-      __stcs(P.we_hist + o, ws.expweight(i));
-    }
+// write the weight history of step k for filters whose last step has no following pass
+__device__ __forceinline__ void flush_weight_history(const EngineP& P, Shared& sh, const Scalars& sc, const Ctx& cx, int k) {
+  if (!P.w_hist) return;
+  const WState ws = make_wstate(P, sc, cx, sh.mt);
+  const size_t hbase = (size_t)(k - 1) * P.N + P.first;
+  for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
+    __stcs(P.w_hist + hbase + i, ws.weight_norm(i));
+    __stcs(P.we_hist + hbase + i, ws.expweight(i));
   }
-
-  // correct!(pfa): reuse the stats found by aux_step when they describe the current weights,
-  // otherwise a reduce-only sweep (logsumexp! of whatever the weights are)
-  __device__ __forceinline__ void aux_correct(int k) {
-    if (sc.stats_ahead) aux_correct_from_stats(k);
-    else pf_pass(0, k, true);
-  }
-
-  __device__ void run() {
-    const int T = P.T;
-    switch (P.prog) {
-      case 0: {  // ParticleFilter / AdvancedParticleFilter:  W(1) [P(k)+W(k+1)]... P(T)
-        if (P.lead_w) pf_pass(0, 1, P.lead_skip != 0);
-        for (int k = 1; k < T; ++k) pf_pass(k, k + 1, false);
-        if (P.trail_p) pf_pass(T, 0, false);
-      } break;
-      case 1: {  // forward_trajectory(pfa) filtering.jl:367-384 / loglik(pfa) smoothing.jl:232-236
-        const bool tail = (P.aux_tail_pf != 0);
-        if (!(tail && T == 1)) aux_correct(1);
-        for (int k = 1; k < T; ++k) {
-          aux_step(k, k + 1);
-          if (k + 1 < T || !tail) aux_correct_from_stats(k + 1);
-        }
-        if (tail) {
-          // pf.pf(u[end], y[end], p, (T-1)*Ts): the INNER filter's update! — its correct! adds the
-          // likelihood of y[T] on top of the raw (un-normalised) w = λ - log N, then predict!.
-          if (sc.stats_ahead) { sc.pend = 0; sc.stats_ahead = 0; }
-          pf_pass(0, T, false);
-          pf_pass(T, 0, false);
-        } else {
-          flush_weight_history(T);
-        }
-      } break;
-      case 2: aux_correct(1); break;                       // correct!(pfa)
-      case 3: aux_step(1, 1); break;                       // predict!(pfa,u,y1): y1 staged at y[0]
-      case 4: aux_correct(1); aux_step(1, 2); break;       // update!(pfa,u,y,y1): y1 staged at y[1]
-      default: break;
-    }
-    // every block must have read the incoming scalars before block 0 overwrites them
-    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *P.sc = sc;
-  }
-};
+}
 
 template <int NX, int NY, int DYN>
 __global__ void __launch_bounds__(BLOCK, LLPF_MIN_BLOCKS)
 k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, NY> M) {
   __shared__ Shared sh;
-  Engine<NX, NY, DYN> e(P, M, sh);
-  e.run();
+  math_tab_load(sh.mt);
+  model_to_shared<NX, NY>(M, sh);
+  __syncthreads();
+  Scalars sc = *P.sc;   // every block carries an identical copy in registers; block 0 writes it back
+  Ctx cx;
+  cx.bar_target = 0;
+  {
+    long long b = (long long)blockIdx.x * P.chunk;
+    long long e = b + P.chunk;
+    if (b > P.n) b = P.n;
+    if (e > P.n) e = P.n;
+    cx.beg = (int)b; cx.end = (int)e;
+  }
+  cx.lwN = -log((double)P.N);
+  cx.lw1N = log(1.0 / (double)P.N);
+  for (int r = 0; r < P.nops; ++r) {
+    const int kind = P.ops[r].kind, a0 = P.ops[r].a0, b0 = P.ops[r].b0, count = P.ops[r].count;
+    const int da = P.ops[r].da, db = P.ops[r].db, flags = P.ops[r].flags;
+    for (int c = 0; c < count; ++c) {
+      int a = a0 + c * da, b = b0 + c * db, fl = flags;
+      asm volatile("" : "+r"(a), "+r"(b), "+r"(fl));   // keep the decoded op in registers (no re-decode per particle)
+      if (kind == OP_PF) {
+        pf_pass<NX, NY, DYN>(P, M, sh, sc, cx, a, b, fl);
+      } else if (kind == OP_AUX_STEP) {
+        aux_step<NX, NY, DYN>(P, M, sh, sc, cx, a, b);
+        if (fl & OPF_POST_CSTATS) aux_correct_from_stats<NX>(P, sc, a + 1);
+      } else if (kind == OP_AUX_CSTATS) {
+        aux_correct_from_stats<NX>(P, sc, a);
+      } else {
+        flush_weight_history(P, sh, sc, cx, a);
+      }
+    }
+  }
+  // every block must have read the incoming scalars before block 0 overwrites them
+  grid_barrier(P.bar, (unsigned)P.nblocks, cx.bar_target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *P.sc = sc;
 }
 
 }  // namespace llpf

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "llpf_math.cuh"
+
 namespace llpf {
 
 enum : uint32_t { ST_INIT = 0, ST_DYN = 1, ST_RESAMPLE = 2, ST_STRAT = 3, ST_RESID = 4 };
@@ -56,32 +58,43 @@ __device__ __forceinline__ double uniform32_open(uint32_t r) {
   return fma((double)r, 2.3283064365386963e-10, 1.1641532182693481e-10);
 }
 
-__device__ __forceinline__ void normal_pair(uint32_t ra, uint32_t rb, double& z0, double& z1) {
-  const double u1 = uniform32_open(ra);
-  // 2*u2 = (rb + 0.5) * 2^-31, exact
-  const double a2 = fma((double)rb, 4.6566128730773926e-10, 2.3283064365386963e-10);
-  const double rad = sqrt(-2.0 * log(u1));
-  double s, c;
-  sincospi(a2, &s, &c);
-  z0 = rad * c;
-  z1 = rad * s;
+// Box-Muller on V pairs of 32-bit words at once (constants of llpf_math.cuh fetched once per call):
+// z0 = rad cos(2 pi u2), z1 = rad sin(2 pi u2), rad = sqrt(-2 ln u1), u1 = (ra+0.5) 2^-32, 2 u2 = (rb+0.5) 2^-31
+template <int V>
+__device__ __forceinline__ void normal_pairs(const uint32_t (&ra)[V], const uint32_t (&rb)[V], double (&z0)[V],
+                                             double (&z1)[V], const MathTab& T) {
+  double L[V], s[V], c[V];
+  log_u32_v<V>(ra, L, T);
+  sincospi_u32_v<V>(rb, s, c, T);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const double rad = sqrt_pos(-2.0 * L[v]);
+    z0[v] = rad * c[v];
+    z1[v] = rad * s[v];
+  }
 }
 
 // N standard normals for (stream, step, particle i), blocks of 4 per Philox call
 template <int N>
 __device__ __forceinline__ void normals(const RngKey& key, uint32_t stream, uint32_t step,
-                                        unsigned long long i, double (&z)[N]) {
+                                        unsigned long long i, double (&z)[N], const MathTab& T) {
 #pragma unroll
   for (int b = 0; 4 * b < N; ++b) {
     const uint4 r = rng_block(key, stream, step, i, (uint32_t)b);
-    double a0, a1, a2, a3;
-    normal_pair(r.x, r.y, a0, a1);
-    z[4 * b] = a0;
-    if (4 * b + 1 < N) z[4 * b + 1] = a1;
     if (4 * b + 2 < N) {
-      normal_pair(r.z, r.w, a2, a3);
-      z[4 * b + 2] = a2;
-      if (4 * b + 3 < N) z[4 * b + 3] = a3;
+      const uint32_t ra[2] = {r.x, r.z}, rb[2] = {r.y, r.w};
+      double a0[2], a1[2];
+      normal_pairs<2>(ra, rb, a0, a1, T);
+      z[4 * b] = a0[0];
+      z[4 * b + 1] = a1[0];
+      z[4 * b + 2] = a0[1];
+      if (4 * b + 3 < N) z[4 * b + 3] = a1[1];
+    } else {
+      const uint32_t ra[1] = {r.x}, rb[1] = {r.y};
+      double a0[1], a1[1];
+      normal_pairs<1>(ra, rb, a0, a1, T);
+      z[4 * b] = a0[0];
+      if (4 * b + 1 < N) z[4 * b + 1] = a1[0];
     }
   }
 }

@@ -1,5 +1,5 @@
-"""Timing experiments on the GPU box: per-time-step cost of the engine under different regimes."""
-import ctypes as C
+"""Timing experiments on the GPU box: per-time-step cost of the engine under different regimes.
+LLPF_LIB_PATH selects a tuning variant of the library."""
 import os
 import sys
 import numpy as np
@@ -21,14 +21,21 @@ def run(log2n, T, thr, reps=3, filt="pf", **kw):
         best = min(best, L.last_run_ms(pf))
     rho = d["resampled"].mean()
     print(f"{filt} N=2^{log2n} T={T} thr={thr} {kw}: {best:8.3f} ms  {best / T * 1e3:7.2f} us/step  "
-          f"{N * T / best / 1e6:9.1f} Mps/s  rho={rho:.3f} ll={d['ll']:.4f}", flush=True)
+          f"{N * T / best / 1e6:9.1f} Gps/s  rho={rho:.3f} ll={d['ll']:.4f}", flush=True)
 
 
 if __name__ == "__main__":
-    for thr in (0.0, 0.1, 1.0):
-        run(20, 300, thr)
-    for n in (10, 14, 16, 18, 22):
-        run(n, 300, 0.0)
-        run(n, 300, 1.0)
-    run(20, 300, 0.1, filt="aux")
-    run(20, 100, 1.0, scan_mode="serial", reps=1)
+    mode = sys.argv[1] if len(sys.argv) > 1 else "full"
+    print("lib:", os.environ.get("LLPF_LIB_PATH", "default"), flush=True)
+    if mode == "quick":
+        for thr in (0.0, 0.1, 1.0):
+            run(20, 300, thr)
+        run(10, 300, 0.0)
+    else:
+        for thr in (0.0, 0.1, 1.0):
+            run(20, 300, thr)
+        for n in (10, 14, 16, 18, 22):
+            run(n, 300, 0.0)
+            run(n, 300, 1.0)
+        run(20, 300, 0.1, filt="aux")
+        run(18, 50, 1.0, scan_mode="serial", reps=1)

@@ -141,6 +141,24 @@ def test_resample_proportions_on_device(gpu, kind):     # test/runtests.jl:108-1
     assert np.allclose(counts / counts.sum(), we, atol=0.03)
 
 
+def test_device_normals_match_oracle_libm(gpu):
+    """The device's specialised log/sqrt/sincospi (llpf_math.cuh) against the oracle's libm Box-Muller on the
+    same Philox words: reset!(pf) with initial_density = N(0, I) exposes the raw N(0,1) variates."""
+    L = gpu
+    N = 1 << 18
+    for nx in (4, 6):
+        pf = L.ParticleFilter(N, L.LinearDynamics(np.eye(nx), np.zeros((nx, 1))), L.LinearMeasurement(np.eye(nx)[:2]),
+                              L.MvNormal(np.eye(nx)), L.MvNormal(np.eye(2)), L.MvNormal(np.zeros(nx), np.eye(nx)), seed=99)
+        L.reset(pf, 7)
+        z = L.particles(pf)
+        idx = np.concatenate([np.arange(0, 3000), np.random.default_rng(0).integers(0, N, 3000)])
+        zo = np.array([O.normals(99, 7, 0, 0, int(i), nx) for i in idx])
+        err = np.abs(z[idx] - zo)
+        assert err.max() < 4e-15 * max(1.0, np.abs(zo).max()), err.max()
+        assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3 and abs(np.mean(z ** 4) - 3) < 0.05
+        assert np.abs(z).max() < 6.8                       # 32-bit uniforms: |z| <= sqrt(-2 ln 2^-33) = 6.76
+
+
 # ---------------------------------------------------------------------------------------------
 # step verbs
 # ---------------------------------------------------------------------------------------------
