@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -267,7 +268,7 @@ k_resample(const __grid_constant__ EngineP P, const double* we, double u01, cons
   double total;
   // 1-based ids; slots >= f_total keep the caller's value (resample.jl:26-34)
   (void)resample_indices<long long>(P, sh, (int)b, (int)e, bar_target, [=](int i) { return __ldg(we + i); },
-                                    u01, false, 0u, M, u_slots, j_inout, 1ll, total);
+                                    [](int, double v) { return v; }, u01, false, 0u, M, u_slots, j_inout, 1ll, total);
 }
 
 // logsumexp!(w, we)  utils.jl:18-27 on caller-provided arrays
@@ -569,6 +570,7 @@ static void base_params(llpf_filter* f, EngineP& P) {
   if (nb < 1) nb = 1;
   P.nblocks = (int)nb;
   P.chunk = (int)((f->n + nb - 1) / nb);
+  P.chunk = (P.chunk + 1) & ~1;   // even chunk starts: 16-byte aligned particle pairs in the scan
   P.key = RngKey{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)f->epoch << 8};
   P.rank = 0; P.world = 1;
   P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
@@ -754,7 +756,25 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
     }
     if (P.resampled) CU(cudaMemsetAsync(f->d_res, 0, sizeof(int) * T, f->stream));
   }
+#ifdef LLPF_PHASE_TIMING
+  long long* d_dbg = nullptr;
+  const char* dump = std::getenv("LLPF_PHASE_DUMP");
+  if (dump) {
+    CU(cudaMalloc(&d_dbg, sizeof(long long) * 16 * (T + 2)));
+    CU(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * (T + 2), f->stream));
+    P.dbg = d_dbg;
+  }
+#endif
   int rc = launch(f, P, true);
+#ifdef LLPF_PHASE_TIMING
+  if (dump && rc == LLPF_OK) {
+    std::vector<long long> hb((size_t)16 * (T + 2));
+    cudaMemcpy(hb.data(), d_dbg, sizeof(long long) * hb.size(), cudaMemcpyDeviceToHost);
+    FILE* fp = std::fopen(dump, "wb");
+    if (fp) { std::fwrite(hb.data(), sizeof(long long), hb.size(), fp); std::fclose(fp); }
+  }
+  cudaFree(d_dbg);
+#endif
   if (rc == LLPF_OK && out) {
     cudaError_t e = cudaSuccess;
     if (out->ll_steps) e = cudaMemcpyAsync(out->ll_steps, f->d_ll, 8 * T, cudaMemcpyDeviceToHost, f->stream);
@@ -968,6 +988,7 @@ static int standalone_geometry(int device, long long n, EngineP& P, const void* 
   if (nb < 1) nb = 1;
   P.nblocks = (int)nb;
   P.chunk = (int)((n + nb - 1) / nb);
+  P.chunk = (P.chunk + 1) & ~1;
   return LLPF_OK;
 }
 

@@ -52,6 +52,7 @@ constexpr int MAX_NX = 8;
 constexpr int MAX_WORLD = 8;
 constexpr int PS = 12;  // doubles per block partial: m, s, q, sx[8], pad
 constexpr int MAX_OPS = 8;
+constexpr int MAX_ROWS = 128;   // rows (of BLOCK particles) per block handled by the 2-barrier scan
 constexpr double FIX_SCALE = 4611686018427387904.0;        // 2^62
 constexpr double FIX_INV = 2.168404344971008868e-19;       // 2^-62
 
@@ -126,7 +127,17 @@ struct EngineP {
   int rank, world;
   RngKey key;
   double fix_scale, fix_inv;  // fixed-point scan scale: 2^62 / 2^-62 for normalised weights
+  long long* dbg;             // optional phase timestamps [pass][16] (block 0, thread 0; -DLLPF_PHASE_TIMING)
 };
+
+#ifdef LLPF_PHASE_TIMING
+#define LLPF_TS(P, sh, k)                                                              \
+  do {                                                                                 \
+    if ((P).dbg && blockIdx.x == 0 && threadIdx.x == 0) (P).dbg[(size_t)(sh).pass_id * 16 + (k)] = clock64(); \
+  } while (0)
+#else
+#define LLPF_TS(P, sh, k) do { } while (0)
+#endif
 
 template <int NX, int NY>
 struct ModelP {
@@ -185,9 +196,12 @@ struct Shared {
   double red_a[NWARP];
   double red_b[NWARP * (2 + MAX_NX)];
   u64 wtot[NWARP];
+  u64 wt[MAX_ROWS * NWARP];     // per (row, warp) totals -> exclusive offsets of the block-local scan
+  int wtf[MAX_ROWS * NWARP];    // F(bins) at the segment starts (first output slot of each segment)
   double bu[MAX_NX];
   double yt[8];
   int skip;
+  int pass_id;
   u64 offs[MAX_BLOCKS + 1];     // exclusive block offsets of the fixed-point scan
   alignas(16) MathTab mt;       // log / exp tables + polynomial coefficients of llpf_math.cuh
 };
@@ -291,33 +305,46 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
 #pragma unroll
   for (int d = 0; d < NX; ++d) v[2 + d] = with_x ? acc.sx[d] * sc : 0.0;
   block_sum<2 + NX>(v, sh);
-  if (threadIdx.x == 0) {
-    double* p = P.partials + (size_t)blockIdx.x * PS;
-    __stcg(p + 0, mb);
-    __stcg(p + 1, v[0]);
-    __stcg(p + 2, v[1]);
+  LLPF_TS(P, sh, 6);
+  if (threadIdx.x == 0) {   // partial = {m, s, q, sx[NX]} as 16-byte pairs
+    double2* p = reinterpret_cast<double2*>(P.partials + (size_t)blockIdx.x * PS);
+    double pk[2 * ((3 + NX + 1) / 2)];
+    pk[0] = mb; pk[1] = v[0]; pk[2] = v[1];
 #pragma unroll
-    for (int d = 0; d < NX; ++d) __stcg(p + 3 + d, v[2 + d]);
+    for (int d = 0; d < NX; ++d) pk[3 + d] = v[2 + d];
+    if ((3 + NX) & 1) pk[3 + NX] = 0.0;
+#pragma unroll
+    for (int k = 0; k < (3 + NX + 1) / 2; ++k) __stcg(p + k, make_double2(pk[2 * k], pk[2 * k + 1]));
   }
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-  // combine
+  LLPF_TS(P, sh, 7);
+  // combine: the barrier's acquire invalidated L1, so these (L1-allocating) loads are fresh and the
+  // second sweep over the same lines hits L1
   double m = -DBL_MAX;
-  for (int b = threadIdx.x; b < P.nblocks; b += BLOCK) m = fmax(m, __ldcg(P.partials + (size_t)b * PS));
+  for (int b = threadIdx.x; b < P.nblocks; b += BLOCK)
+    m = fmax(m, __ldca(reinterpret_cast<const double2*>(P.partials + (size_t)b * PS)).x);
   m = block_max(m, sh);
   double t[2 + NX];
 #pragma unroll
   for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
   for (int b = threadIdx.x; b < P.nblocks; b += BLOCK) {
-    const double* p = P.partials + (size_t)b * PS;
-    const double e = exp_nonpos(__ldcg(p) - m, sh.mt);
-    t[0] = fma(__ldcg(p + 1), e, t[0]);
-    t[1] = fma(__ldcg(p + 2), e * e, t[1]);
+    const double2* p = reinterpret_cast<const double2*>(P.partials + (size_t)b * PS);
+    double pk[2 * ((3 + NX + 1) / 2)];
+#pragma unroll
+    for (int k = 0; k < (3 + NX + 1) / 2; ++k) {
+      const double2 q2 = (with_x || k < 2) ? __ldca(p + k) : make_double2(0.0, 0.0);
+      pk[2 * k] = q2.x; pk[2 * k + 1] = q2.y;
+    }
+    const double e = exp_nonpos(pk[0] - m, sh.mt);
+    t[0] = fma(pk[1], e, t[0]);
+    t[1] = fma(pk[2], e * e, t[1]);
     if (with_x) {
 #pragma unroll
-      for (int d = 0; d < NX; ++d) t[2 + d] = fma(__ldcg(p + 3 + d), e, t[2 + d]);
+      for (int d = 0; d < NX; ++d) t[2 + d] = fma(pk[3 + d], e, t[2 + d]);
     }
   }
   block_sum<2 + NX>(t, sh);
+  LLPF_TS(P, sh, 8);
   Stats st;
   st.m = m; st.s = t[0]; st.q = t[1];
 #pragma unroll
@@ -334,20 +361,64 @@ __device__ __forceinline__ u64 to_fixed(double we, double scale) {
   return (v > 0.0) ? __double2ull_rn(fmin(v, FIX_SCALE)) : 0ull;
 }
 
-// Stage 1: block-local inclusive scan of the block's chunk [beg,end).
-// FAST  : loc[i] = local inclusive fixed-point prefix; tots[b] = block total.
-// SERIAL: bins[i] = we_i (double); the single-thread pass runs after the barrier.
-template <class WeFn>
-__device__ __forceinline__ void scan_stage1(const EngineP& P, Shared& sh, int beg, int end, WeFn wefn) {
+// Stage 1: block-local scan of the block's chunk [beg,end).
+// FAST  : loc[i] = inclusive fixed-point prefix within its (row, warp) segment; sh.wt[row*NWARP+warp] = exclusive
+//         offset of that segment inside the block (two block barriers in total); tots[b] = block total.
+//         (Chunks of more than MAX_ROWS rows fall back to a per-row barrier and keep the full prefix in loc[].)
+// SERIAL: bins[i] = we_i (double); the single-thread pass runs after the grid barrier.
+// Returns true when the (row, warp) table is in use.
+template <class LoadFn, class WeFn>
+__device__ __forceinline__ bool scan_stage1(const EngineP& P, Shared& sh, int beg, int end, LoadFn loadfn, WeFn wefn) {
   if (P.scan_mode != 0) {
-    for (int i = beg + threadIdx.x; i < end; i += BLOCK) __stcg(P.bins + i, wefn(i));
-    return;
+    for (int i = beg + threadIdx.x; i < end; i += BLOCK) __stcg(P.bins + i, wefn(i, loadfn(i)));
+    return false;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows = (end - beg + BLOCK - 1) / BLOCK;
+  if (rows <= MAX_ROWS) {
+    // software pipeline: the raw weight of the next row is in flight while this row is scanned
+    double raw_next = (beg + (int)threadIdx.x < end) ? loadfn(beg + threadIdx.x) : 0.0;
+    for (int k = 0; k < rows; ++k) {
+      const int i = beg + k * BLOCK + threadIdx.x;
+      const double raw = raw_next;
+      if (i + BLOCK < end) raw_next = loadfn(i + BLOCK);
+      u64 v = (i < end) ? to_fixed(wefn(i, raw), P.fix_scale) : 0ull;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      if (i < end) __stcg(P.loc + i, v);
+      if (lane == 31) sh.wt[k * NWARP + warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the rows*NWARP segment totals, in (row, warp) order
+      const int n = rows * NWARP;
+      const int per = (n + 31) >> 5;
+      const int s0 = lane * per, s1 = (s0 + per < n) ? s0 + per : n;
+      u64 sum = 0;
+      for (int q = s0; q < s1; ++q) sum += sh.wt[q];
+      u64 incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      u64 run = incl - sum;
+      for (int q = s0; q < s1; ++q) {
+        const u64 t = sh.wt[q];
+        sh.wt[q] = run;
+        run += t;
+      }
+      if (lane == 31) __stcg(P.tots + blockIdx.x, incl);
+    }
+    __syncthreads();
+    return true;
   }
   u64 carry = 0;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = beg; base < end; base += BLOCK) {
     const int i = base + threadIdx.x;
-    u64 v = (i < end) ? to_fixed(wefn(i), P.fix_scale) : 0ull;
+    u64 v = (i < end) ? to_fixed(wefn(i, loadfn(i)), P.fix_scale) : 0ull;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const u64 t = __shfl_up_sync(0xffffffffu, v, o);
@@ -367,6 +438,7 @@ __device__ __forceinline__ void scan_stage1(const EngineP& P, Shared& sh, int be
     carry += rtot;
   }
   if (threadIdx.x == 0) __stcg(P.tots + blockIdx.x, carry);
+  return false;
 }
 
 // After the grid barrier that follows stage 1 (FAST): exclusive block offsets into sh.offs[0..nb]
@@ -473,7 +545,26 @@ __device__ __forceinline__ double resample_u01(const RngKey& key, uint32_t step_
 // estimate from the real-valued inverse plus an exact fix-up (evaluating s_i exactly as the reference
 // does) gives the same partition of the slots as the reference's comparison `s[i] < bins[b]`.
 __device__ __forceinline__ int first_slot_ge(const Thresholds& th, const RngKey& key, double v) {
-  const double t = (th.strategy == 1) ? (v / th.total) * th.M - 1.0 : (v - th.r) * th.M;
+  if (th.strategy != 1) {
+    // systematic: s_i = fl(r + fl(i*step)); estimate ceil((v - r) M), then check the two neighbours once
+    int i0 = __double2int_ru((v - th.r) * th.M);
+    i0 = max(0, min(i0, th.Mi));
+    const double f0 = (double)i0;
+    const double s_m = __dadd_rn(th.r, __dmul_rn(f0 - 1.0, th.step));   // s[i0-1]
+    const double s_0 = __dadd_rn(th.r, __dmul_rn(f0, th.step));         // s[i0]
+    const bool down = (i0 > 0) && (s_m >= v);
+    const bool up = (i0 < th.Mi) && (s_0 < v);
+    if (!(down || up)) return i0;          // the estimate is exact (always, up to rounding ties)
+    if (down) {
+      --i0;
+      while (i0 > 0 && threshold(th, key, i0 - 1) >= v) --i0;
+    } else {
+      ++i0;
+      while (i0 < th.Mi && threshold(th, key, i0) < v) ++i0;
+    }
+    return i0;
+  }
+  const double t = (v / th.total) * th.M - 1.0;
   int i0;
   if (!(t > 0.0)) i0 = 0;
   else if (t >= th.M) i0 = th.Mi;
@@ -483,13 +574,16 @@ __device__ __forceinline__ int first_slot_ge(const Thresholds& th, const RngKey&
   return i0;
 }
 
-// write `id` into slots [lo, lo+cnt) of j: short runs by the owning lane, long runs by the whole warp.
-// Must be called by all 32 lanes (cnt = 0 for idle lanes).
+// write `id` into slots [lo, lo+cnt) of j: runs of up to 4 by predicated stores of the owning lane, longer
+// runs by the whole warp.  Must be called by all 32 lanes (cnt = 0 for idle lanes).
 template <class T>
 __device__ __forceinline__ void scatter_runs(T* j, int lo, int cnt, T id) {
   const int lane = threadIdx.x & 31;
-  if (cnt > 0 && cnt <= 4) {
-    for (int s = 0; s < cnt; ++s) __stcg(j + lo + s, id);
+  if (cnt <= 4) {
+    if (cnt > 0) __stcg(j + lo, id);
+    if (cnt > 1) __stcg(j + lo + 1, id);
+    if (cnt > 2) __stcg(j + lo + 2, id);
+    if (cnt > 3) __stcg(j + lo + 3, id);
   }
   unsigned heavy = __ballot_sync(0xffffffffu, cnt > 4);
   while (heavy) {
@@ -502,16 +596,129 @@ __device__ __forceinline__ void scatter_runs(T* j, int lo, int cnt, T id) {
   }
 }
 
+// ---- FAST path, two adjacent particles per lane (16-byte loads/stores, half the shuffles per particle) ----
+// Needs an even chunk start (the host rounds chunks to even sizes).  Row r covers 2*BLOCK particles.
+template <class LoadFn, class WeFn>
+__device__ __forceinline__ void scan_stage1_pairs(const EngineP& P, Shared& sh, int beg, int end, LoadFn loadfn, WeFn wefn) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
+  double r0n = 0.0, r1n = 0.0;
+  {
+    const int i = beg + 2 * threadIdx.x;
+    if (i < end) r0n = loadfn(i);
+    if (i + 1 < end) r1n = loadfn(i + 1);
+  }
+  for (int k = 0; k < rows; ++k) {
+    const int i = beg + k * 2 * BLOCK + 2 * threadIdx.x;
+    const double r0 = r0n, r1 = r1n;
+    {
+      const int in = i + 2 * BLOCK;
+      if (in < end) r0n = loadfn(in);
+      if (in + 1 < end) r1n = loadfn(in + 1);
+    }
+    const u64 f0 = (i < end) ? to_fixed(wefn(i, r0), P.fix_scale) : 0ull;
+    const u64 f1 = (i + 1 < end) ? to_fixed(wefn(i + 1, r1), P.fix_scale) : 0ull;
+    const u64 pr = f0 + f1;
+    u64 v = pr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (i + 1 < end) {
+      __stcg(reinterpret_cast<ulonglong2*>(P.loc + i), make_ulonglong2(v - f1, v));
+    } else if (i < end) {
+      __stcg(P.loc + i, v - f1);
+    }
+    if (lane == 31) sh.wt[k * NWARP + warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {   // exclusive scan of the rows*NWARP segment totals, in (row, warp) order
+    const int n = rows * NWARP;
+    const int per = (n + 31) >> 5;
+    const int s0 = lane * per, s1 = (s0 + per < n) ? s0 + per : n;
+    u64 sum = 0;
+    for (int q = s0; q < s1; ++q) sum += sh.wt[q];
+    u64 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    u64 run = incl - sum;
+    for (int q = s0; q < s1; ++q) {
+      const u64 t = sh.wt[q];
+      sh.wt[q] = run;
+      run += t;
+    }
+    if (lane == 31) __stcg(P.tots + blockIdx.x, incl);
+  }
+  __syncthreads();
+}
+
+template <class JT>
+__device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int beg, int end, u64 off,
+                                              const Thresholds& th, JT* jout, JT jbase) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
+  // F at every (row, warp) segment start: lane 0 of a segment needs it for its first particle
+  __syncthreads();
+  for (int q = threadIdx.x; q < rows * NWARP; q += BLOCK)
+    sh.wtf[q] = first_slot_ge(th, P.key, (double)(off + sh.wt[q]) * P.fix_inv);
+  __syncthreads();
+  ulonglong2 mn = make_ulonglong2(0ull, 0ull);
+  {
+    const int i = beg + 2 * threadIdx.x;
+    if (i + 1 < end) mn = __ldcg(reinterpret_cast<const ulonglong2*>(P.loc + i));
+    else if (i < end) mn.x = __ldcg(P.loc + i);
+  }
+  for (int k = 0; k < rows; ++k) {
+    const int i = beg + k * 2 * BLOCK + 2 * threadIdx.x;
+    const ulonglong2 m = mn;
+    {
+      const int in = i + 2 * BLOCK;
+      mn = make_ulonglong2(0ull, 0ull);
+      if (in + 1 < end) mn = __ldcg(reinterpret_cast<const ulonglong2*>(P.loc + in));
+      else if (in < end) mn.x = __ldcg(P.loc + in);
+    }
+    const u64 seg = off + sh.wt[k * NWARP + warp];
+    int fB = 0, fC = 0;
+    if (i < end) {
+      const double hi0 = (double)(seg + m.x) * P.fix_inv;
+      fB = first_slot_ge(th, P.key, hi0);
+      fC = fB;
+      if (i + 1 < end) {
+        const double hi1 = (double)(seg + m.y) * P.fix_inv;
+        fC = (m.y > m.x) ? first_slot_ge(th, P.key, hi1) : fB;
+        __stcg(reinterpret_cast<double2*>(P.bins + i), make_double2(hi0, hi1));
+      } else {
+        __stcg(P.bins + i, hi0);
+      }
+    }
+    int fA = __shfl_up_sync(0xffffffffu, fC, 1);       // F(lo) of my first particle = F(hi) of the previous lane's second
+    if (lane == 0) fA = sh.wtf[k * NWARP + warp];
+    if (i >= end) { fA = 0; fB = 0; fC = 0; }
+    scatter_runs<JT>(jout, fA, fB - fA, jbase + (JT)i);
+    scatter_runs<JT>(jout, fB, fC - fB, jbase + (JT)(i + 1));
+  }
+}
+
 // The whole resample: scan(we) -> bins (global) -> per-source slot ranges -> j (global, id = jbase + i).
 // Ends with a grid barrier: afterwards j[s] is valid for every slot s < f_total (returned); the
 // remaining slots are the reference's "untouched" entries (resample.jl:26-34).
-template <class JT, class WeFn>
+template <class JT, class LoadFn, class WeFn>
 __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, int beg, int end, unsigned& bar_target,
-                                                WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
+                                                LoadFn loadfn, WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
                                                 int Mslots, const double* u_slots, JT* jout, JT jbase,
                                                 double& total_out) {
-  scan_stage1(P, sh, beg, end, wefn);
+  const int rows2 = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
+  const bool pairs = (P.scan_mode == 0) && (rows2 <= MAX_ROWS) && ((beg & 1) == 0);
+  bool tabled = false;
+  if (pairs) scan_stage1_pairs(P, sh, beg, end, loadfn, wefn);
+  else tabled = scan_stage1(P, sh, beg, end, loadfn, wefn);
+  LLPF_TS(P, sh, 1);
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  LLPF_TS(P, sh, 2);
   double total;
   u64 off = 0;
   if (P.scan_mode != 0) {
@@ -526,17 +733,51 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   total_out = total;
   if (gen_u01) u01 = resample_u01(P.key, step_idx);
   const Thresholds th = make_thresholds(P, total, u01, Mslots, step_idx, u_slots);
-  for (int base = beg; base < end; base += BLOCK) {   // uniform trip count: warp collectives inside
+  if (pairs) {
+    scatter_pairs<JT>(P, sh, beg, end, off, th, jout, jbase);
+    const int f_tot = first_slot_ge(th, P.key, total);
+    LLPF_TS(P, sh, 3);
+    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+    LLPF_TS(P, sh, 4);
+    return f_tot;
+  }
+  int row = 0;
+  // software pipeline: the next row's prefix (FAST) / bins pair (SERIAL) is in flight while this row is processed
+  u64 mine_next = 0;
+  double hi_next = 0.0, lo_next = 0.0;
+  {
+    const int i0 = beg + threadIdx.x;
+    if (i0 < end) {
+      if (P.scan_mode == 0) mine_next = __ldcg(P.loc + i0);
+      else { hi_next = __ldcg(P.bins + i0); lo_next = (i0 > 0) ? __ldcg(P.bins + i0 - 1) : 0.0; }
+    }
+  }
+  for (int base = beg; base < end; base += BLOCK, ++row) {   // uniform trip count: warp collectives inside
     const int i = base + threadIdx.x;
     int f_lo = 0, cnt = 0;
+    u64 mine = mine_next, seg = 0;
+    const double hi_s = hi_next, lo_s = lo_next;
+    {
+      const int in = i + BLOCK;
+      mine_next = 0;
+      if (in < end) {
+        if (P.scan_mode == 0) mine_next = __ldcg(P.loc + in);
+        else { hi_next = __ldcg(P.bins + in); lo_next = __ldcg(P.bins + in - 1); }
+      }
+    }
+    if (P.scan_mode == 0 && tabled) seg = sh.wt[row * NWARP + (threadIdx.x >> 5)];
+    const u64 prev = __shfl_up_sync(0xffffffffu, mine, 1);   // inclusive prefix of the previous lane's particle
     if (i < end) {
       double lo, hi;
       if (P.scan_mode != 0) {
-        hi = __ldcg(P.bins + i);
-        lo = (i > 0) ? __ldcg(P.bins + i - 1) : 0.0;
+        hi = hi_s;
+        lo = lo_s;
       } else {
-        hi = (double)(off + __ldcg(P.loc + i)) * P.fix_inv;
-        lo = (i > beg) ? (double)(off + __ldcg(P.loc + i - 1)) * P.fix_inv : (double)off * P.fix_inv;
+        u64 plo;
+        if (tabled) plo = ((threadIdx.x & 31) == 0) ? 0ull : prev;         // segment-relative
+        else plo = (i > beg) ? (((threadIdx.x & 31) == 0) ? __ldcg(P.loc + i - 1) : prev) : 0ull;
+        hi = (double)(off + seg + mine) * P.fix_inv;
+        lo = (double)(off + seg + plo) * P.fix_inv;
         __stcg(P.bins + i, hi);
       }
       f_lo = first_slot_ge(th, P.key, lo);
@@ -546,7 +787,9 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     scatter_runs<JT>(jout, f_lo, cnt, jbase + (JT)i);
   }
   const int f_total = first_slot_ge(th, P.key, total);
+  LLPF_TS(P, sh, 3);
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  LLPF_TS(P, sh, 4);
   return f_total;
 }
 
@@ -624,6 +867,22 @@ __device__ __forceinline__ void add_dynamics_noise(const ModelP<NX, NY>& M, cons
   }
 }
 
+// nz = L1*z (the additive dynamics noise), independent of the particle value
+template <int NX, int NY>
+__device__ __forceinline__ void noise_vector(const RngKey& key, uint32_t step_idx, int gi, double (&nz)[NX], const Shared& sh) {
+  double z[NX];
+  normals<NX>(key, ST_DYN, step_idx, (unsigned long long)(unsigned)gi, z, sh.mt);
+#pragma unroll
+  for (int r = 0; r < NX; ++r) {
+    double l[NX];
+    lds_row<NX>(sh.mL + r * mdl_stride(NX), l);
+    double acc = l[0] * z[0];
+#pragma unroll
+    for (int c = 1; c <= r; ++c) acc = fma(l[c], z[c], acc);
+    nz[r] = acc;
+  }
+}
+
 // logpdf(N(0,R2), y - C x) = c0 - |W(y - Cx)|^2/2 = c0 - |yt - G x|^2/2   (utils.jl:252-257)
 template <int NX, int NY>
 __device__ __forceinline__ double meas_loglik(const ModelP<NX, NY>& M, const Shared& sh, const double (&yt)[NY],
@@ -671,6 +930,14 @@ struct WState {
   double pm, pls, inv_s, wu, weu;
   const double* w;
   const MathTab* T;
+  __device__ __forceinline__ double weight_norm_raw(double wr) const {
+    if (uniform) return wu;
+    return pend ? (wr - pm) - pls : wr;
+  }
+  __device__ __forceinline__ double expweight_raw(double wr) const {
+    if (uniform) return weu;
+    return pend ? exp_nonpos(wr - pm, *T) * inv_s : exp(wr);
+  }
   // logical (normalised) log-weight of local particle i: (w - offset) - log1p(s)  utils.jl:20,25
   __device__ __forceinline__ double weight_norm(int i) const {
     if (uniform) return wu;
@@ -792,7 +1059,11 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   const bool skip_meas = (flags & OPF_SKIP_MEAS) != 0;
   double bu[NX], yt[NY];
   bool nan_y;
+#ifdef LLPF_PHASE_TIMING
+  if (threadIdx.x == 0) sh.pass_id = (k_prop > 0) ? k_prop : 0;
+#endif
   stage_step<NX, NY, DYN>(P, M, sh, k_prop, skip_meas ? 0 : k_weigh, bu, yt, nan_y);
+  LLPF_TS(P, sh, 0);
   const bool skip = skip_meas || nan_y;
   // shouldresample(pf)  resample.jl:5-10
   const bool res = (k_prop > 0) && ((P.thr == 1.0) || (sc.ess < (double)P.N * P.thr));
@@ -807,10 +1078,11 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
     double total;
     f_total = resample_indices<int>(
         P, sh, cx.beg, cx.end, cx.bar_target,
-        [=](int i) {
-          const double we = ws.expweight(i);
+        [=](int i) { return ws.uniform ? 0.0 : __ldcg(ws.w + i); },
+        [=](int i, double wr) {
+          const double we = ws.expweight_raw(wr);
           if (hist_w) {
-            __stcs(wh + hbase + i, ws.weight_norm(i));
+            __stcs(wh + hbase + i, ws.weight_norm_raw(wr));
             __stcs(weh + hbase + i, we);
           }
           return we;
@@ -825,23 +1097,34 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   const int jid = sc.j_identity;
   Online<NX> acc;
   acc.init();
+  // software pipeline: the ancestor index of the NEXT iteration is fetched one iteration ahead; within an
+  // iteration the particle/weight loads are issued first, the (data-independent) noise is computed while
+  // they are in flight, and only then are they consumed.
+  int a_next = 0;
+  if (res && cx.beg + (int)threadIdx.x < cx.end) a_next = __ldcg(P.j + cx.beg + threadIdx.x);
   for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
     const int gi = P.first + i;
     double x[NX];
-    double wv;
+    double wraw = 0.0;
     if (res) {
-      int a;
-      if (gi < f_total) {
-        a = __ldcg(P.j + i);
-      } else {                       // untouched entry (resample.jl:26-34): keep state.j
-        a = jid ? gi : __ldcg(P.j + i);
+      int a = a_next;
+      if (i + BLOCK < cx.end) a_next = __ldcg(P.j + i + BLOCK);
+      if (gi >= f_total) {             // untouched entry (resample.jl:26-34): keep state.j
+        if (jid) a = gi;
         __stcg(P.j + i, a);
       }
       load_x<NX>(src, P.ld, a - P.first, x);
-      wv = cx.lw1N;                  // reset_weights!  utils.jl:75
     } else {
       load_x<NX>(src, P.ld, i, x);
-      wv = ws.weight_norm(i);
+      if (!ws.uniform) wraw = __ldcg(P.w + i);
+    }
+    double z[NX];
+    if (k_prop > 0) noise_vector<NX, NY>(P.key, step_idx, gi, z, sh);
+    double wv;
+    if (res) {
+      wv = cx.lw1N;                    // reset_weights!  utils.jl:75
+    } else {
+      wv = ws.uniform ? ws.wu : (ws.pend ? (wraw - ws.pm) - ws.pls : wraw);
       if (hist_w) {
         __stcs(wh + hbase + i, wv);
         __stcs(weh + hbase + i, ws.expweight(i));
@@ -849,7 +1132,8 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
     }
     if (k_prop > 0) {
       dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
-      add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] += z[d];
       store_x<NX>(dst, P.ld, i, x);
     }
     if (k_weigh > 0) {
@@ -859,6 +1143,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
       acc.add(wv, x, with_x, sh.mt);
     }
   }
+  LLPF_TS(P, sh, 5);
   if (k_prop > 0) {
     if (res) {
       sc.cur ^= 1;
@@ -923,7 +1208,8 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   // expnormalize!(w): exp(w-offset)*1/(s+1)   utils.jl:57-63 ; then resample (always)  :205
   double total;
   const int f_total = resample_indices<int>(
-      P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return exp_nonpos(__ldcg(wraw + i) - m1, *mtp) * inv1; }, 0.0, true,
+      P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return __ldcg(wraw + i); },
+      [=](int, double wr) { return exp_nonpos(wr - m1, *mtp) * inv1; }, 0.0, true,
       step_idx, (int)P.N, nullptr, P.j, P.first, total);
   sc.bins_total = total;
   const bool with_x = (P.want_xhat != 0);
@@ -1018,6 +1304,7 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
     if (b > P.n) b = P.n;
     if (e > P.n) e = P.n;
     cx.beg = (int)b; cx.end = (int)e;
+    asm volatile("" : "+r"(cx.beg), "+r"(cx.end));   // keep the bounds in registers (no per-iteration re-derivation)
   }
   cx.lwN = -log((double)P.N);
   cx.lw1N = log(1.0 / (double)P.N);

@@ -112,6 +112,10 @@ __device__ __forceinline__ void sincospi_u32_v(const uint32_t (&r)[V], double (&
     t[v] = fma((double)ti, 4.6566128730773926e-10, 2.3283064365386963e-10);  // (ti + 0.5) 2^-31, exact
     t2[v] = t[v] * t[v];
   }
+#ifndef LLPF_SC_BATCH
+#define LLPF_SC_BATCH 3
+#endif
+  // coefficients are fetched LLPF_SC_BATCH at a time so that their LDS.128 latencies overlap
   {
     const double2 c8 = lds2v(&T.sc[8]), c7 = lds2v(&T.sc[7]);
 #pragma unroll
@@ -121,12 +125,20 @@ __device__ __forceinline__ void sincospi_u32_v(const uint32_t (&r)[V], double (&
     }
   }
 #pragma unroll
-  for (int i = 6; i >= 0; --i) {
-    const double2 ci = lds2v(&T.sc[i]);
+  for (int i0 = 6; i0 >= 0; i0 -= LLPF_SC_BATCH) {
+    double2 co[LLPF_SC_BATCH];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      sp[v] = fma(t2[v], sp[v], ci.x);
-      cp[v] = fma(t2[v], cp[v], ci.y);
+    for (int b = 0; b < LLPF_SC_BATCH; ++b)
+      if (i0 - b >= 0) co[b] = lds2v(&T.sc[i0 - b]);
+#pragma unroll
+    for (int b = 0; b < LLPF_SC_BATCH; ++b) {
+      if (i0 - b >= 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          sp[v] = fma(t2[v], sp[v], co[b].x);
+          cp[v] = fma(t2[v], cp[v], co[b].y);
+        }
+      }
     }
   }
 #pragma unroll
