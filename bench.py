@@ -167,13 +167,14 @@ def main():
     N_global = (1 << args.log2n) * world      # weak scaling: 2^20 particles per GPU
     T = args.T
     spec, u, y = workload(T)
-    sharded = world > 1 and hasattr(L, "ShardedParticleFilter")
-    if sharded:
-        pf = L.ShardedParticleFilter(spec, N_global, seed=1, resample_threshold=THRESHOLD, device=local_rank)
-        par = f"particles sharded over {world} GPUs (peer-memory exchange)"
-    else:
-        pf = spec.particle_filter(1 << args.log2n, seed=1 + rank, resample_threshold=THRESHOLD, device=local_rank)
-        par = "single GPU" if world == 1 else f"{world} independent replicas (one filter per GPU)"
+    # ONE global filter; with N > 1 its particles are block-partitioned over the ranks and the kernels exchange
+    # (max, sum exp, sum exp^2) partials, CDF offsets, offspring indices and resampled particles over NVLink
+    # peer memory (torch.distributed only carries the 200-byte IPC descriptors at set-up)
+    pf = spec.particle_filter(N_global, seed=1, resample_threshold=THRESHOLD, device=local_rank, rank=rank, world=world)
+    if world > 1:
+        L.connect_shards(pf)
+    par = "single GPU" if world == 1 else (f"particles sharded over {world} GPUs (dp{world}); in-kernel exchange over "
+                                           "NVLink peer memory: 1 all-gather of 7 doubles per step, +2 on resample steps")
     n_local = 1 << args.log2n
 
     # device-resident inputs for `value`
@@ -200,7 +201,11 @@ def main():
             torch.cuda.synchronize()
 
     for w in range(args.warmup):
+        if world > 1:
+            dist.barrier()
         run_dev(100 + w)
+    if world > 1:
+        dist.barrier()
     rho_probe = L.loglik(pf, u, y, epoch=99, details=True)
     rho = float(rho_probe["resampled"].mean())
 
@@ -213,6 +218,8 @@ def main():
     for k in range(args.steps):
         flush.zero_()                      # L2 flush between timed trajectories (untimed)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                 # ranks enter the launch together (a late peer would be waited for in-kernel)
         kernel_ms.append(run_dev(200 + k))
     sync_all()
     t_wall = time.perf_counter() - t_wall0
@@ -226,6 +233,8 @@ def main():
     sync_all()
     e2e_t0 = time.perf_counter()
     for k in range(args.steps):
+        if world > 1:
+            dist.barrier()
         L.loglik(pf, u_pin, y_pin, epoch=300 + k)
     torch.cuda.synchronize()
     e2e_ms_local = (time.perf_counter() - e2e_t0) * 1e3 / args.steps

@@ -9,7 +9,7 @@ from ._abi import LLPFError, load_library  # noqa: F401
 from .filters import (  # noqa: F401
     AbstractParticleFilter, AdvancedParticleFilter, AuxiliaryParticleFilter, GaussianLikelihood,
     LinearDynamics, LinearMeasurement, MvNormal, ParticleFilter, ParticleFilteringSolution, QuadtankRK4,
-    ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, correct,
+    ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, connect_shards, correct,
     effective_particles, expweights, forward_trajectory, index, last_run_ms, launch_count, loglik, logsumexp,
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
-    shouldresample, state, update, weighted_mean, weights)
+    shard_blob, shouldresample, state, update, weighted_mean, weights)

@@ -266,9 +266,10 @@ k_resample(const __grid_constant__ EngineP P, const double* we, double u01, cons
   if (e > P.n) e = P.n;
   if (b > P.n) b = P.n;
   double total;
+  u64 xs = 0;
   // 1-based ids; slots >= f_total keep the caller's value (resample.jl:26-34)
   (void)resample_indices<long long>(P, sh, (int)b, (int)e, bar_target, [=](int i) { return __ldg(we + i); },
-                                    [](int, double v) { return v; }, u01, false, 0u, M, u_slots, j_inout, 1ll, total);
+                                    [](int, double v) { return v; }, u01, false, 0u, M, u_slots, j_inout, 1ll, total, xs);
 }
 
 // logsumexp!(w, we)  utils.jl:18-27 on caller-provided arrays
@@ -286,7 +287,8 @@ k_logsumexp(const __grid_constant__ EngineP P, double* w, double* we, double* ll
   acc.init();
   const double dummy[1] = {0.0};
   for (int i = beg + threadIdx.x; i < end; i += BLOCK) acc.add(w[i], dummy, false, sh.mt);
-  const Stats st = reduce_stats<1>(P, sh, acc, false, bar_target);
+  u64 xs = 0;
+  const Stats st = reduce_stats<1>(P, sh, acc, false, bar_target, xs);
   const double ls = log(st.s), inv = 1.0 / st.s;
   for (int i = beg + threadIdx.x; i < end; i += BLOCK) {
     const double wr = w[i];
@@ -322,6 +324,14 @@ struct llpf_filter {
   unsigned* bar = nullptr;
   Scalars* sc = nullptr;
   double *stage_u = nullptr, *stage_y = nullptr, *wstat = nullptr, *scratch = nullptr;
+  double* mbox = nullptr;
+  double* bcast = nullptr;
+  u64* bcast_flag = nullptr;
+  // sharding (one process per GPU): IPC-mapped peer arenas
+  int rank = 0, world = 1;
+  bool connected = false;
+  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0;
+  char* peer_base[MAX_WORLD] = {nullptr};
   // per-run buffers (grow-only)
   double *d_u = nullptr, *d_y = nullptr, *d_ll = nullptr, *d_ess = nullptr, *d_xhat = nullptr;
   int* d_res = nullptr;
@@ -418,6 +428,8 @@ extern "C" int llpf_destroy(llpf_handle h) {
   if (!h) return LLPF_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int r = 0; r < MAX_WORLD; ++r)
+    if (r != h->rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
   cudaFree(h->arena);
   cudaFree(h->d_u); cudaFree(h->d_y); cudaFree(h->d_ll); cudaFree(h->d_ess); cudaFree(h->d_xhat);
   cudaFree(h->d_res);
@@ -449,7 +461,12 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED)
     return fail(LLPF_ERR_UNSUPPORTED, "in-loop resampling: systematic or stratified");
   const int world = cfg->world < 1 ? 1 : cfg->world;
-  if (world > 1) return fail(LLPF_ERR_UNSUPPORTED, "sharded filters: see llpf_shard_* (not in this build)");
+  if (world > MAX_WORLD) return fail(LLPF_ERR_UNSUPPORTED, "at most 8 ranks (one box)");
+  if (world > 1) {
+    if (cfg->rank < 0 || cfg->rank >= world) return fail(LLPF_ERR_BAD_ARG, "bad rank");
+    if (cfg->N % world) return fail(LLPF_ERR_BAD_ARG, "N must be divisible by the number of ranks");
+    if (cfg->scan_mode != LLPF_SCAN_FAST) return fail(LLPF_ERR_UNSUPPORTED, "sharded filters use the fixed-point scan (serial cumsum is single-GPU)");
+  }
   int ndev = 0;
   OKR(llpf_device_count(&ndev));
   if (ndev < 1) return fail(LLPF_ERR_NO_DEVICE, "no CUDA device; the product path has no CPU fallback");
@@ -498,8 +515,10 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   CUF(cudaMallocHost(&f->pin_sc, sizeof(Scalars)));
 
   f->N = cfg->N;
-  f->n = cfg->N;
-  f->first = 0;
+  f->world = world;
+  f->rank = world > 1 ? cfg->rank : 0;
+  f->n = cfg->N / world;
+  f->first = (long long)f->rank * f->n;
   f->ld = (long long)align_up((size_t)f->n, 32);
   const int nx = f->hm.nx;
   size_t off = 0;
@@ -512,6 +531,9 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const size_t o_bar = take(256), o_sc = take(sizeof(Scalars));
   const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + MAX_NX) * 8);
   const size_t o_scr = take((size_t)(nx + 2) * f->ld * 8);
+  const size_t o_mbox = take((size_t)2 * MAX_WORLD * MBOX_WORDS * 8);
+  const size_t o_bcast = take((size_t)2 * MAX_WORLD * MBOX_DOUBLES * 8), o_bflag = take(64);
+  f->o_x0 = o_x0; f->o_x1 = o_x1; f->o_j = o_j; f->o_mbox = o_mbox;
   f->arena_bytes = off;
   CUF(cudaMalloc(&f->arena, f->arena_bytes));
   CUF(cudaMemsetAsync(f->arena, 0, f->arena_bytes, f->stream));
@@ -523,6 +545,9 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   f->bar = (unsigned*)(f->arena + o_bar); f->sc = (Scalars*)(f->arena + o_sc);
   f->stage_u = (double*)(f->arena + o_su); f->stage_y = (double*)(f->arena + o_sy);
   f->wstat = (double*)(f->arena + o_ws); f->scratch = (double*)(f->arena + o_scr);
+  f->mbox = (double*)(f->arena + o_mbox);
+  f->bcast = (double*)(f->arena + o_bcast); f->bcast_flag = (u64*)(f->arena + o_bflag);
+  f->peer_base[f->rank] = f->arena;
 #undef CUF
   rc = llpf_reset(f, 0);
   if (rc) { llpf_destroy(f); return rc; }
@@ -547,6 +572,7 @@ extern "C" int llpf_reset(llpf_handle h, uint64_t epoch) {
   s.stats_valid = 1;
   s.ess = (double)h->N;
   s.j_identity = 1;
+  s.xseq = h->hsc.xseq;   // the peer-exchange counter runs on across resets (mailboxes are never re-zeroed)
   h->hsc = s;
   return push_scalars(h);
 }
@@ -572,8 +598,16 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.chunk = (int)((f->n + nb - 1) / nb);
   P.chunk = (P.chunk + 1) & ~1;   // even chunk starts: 16-byte aligned particle pairs in the scan
   P.key = RngKey{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)f->epoch << 8};
-  P.rank = 0; P.world = 1;
+  P.rank = f->rank; P.world = f->world;
   P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
+  P.bcast = f->bcast; P.bcast_flag = f->bcast_flag;
+  for (int r = 0; r < f->world; ++r) {
+    char* base = f->peer_base[r];
+    P.peer_x[r][0] = base ? (double*)(base + f->o_x0) : nullptr;
+    P.peer_x[r][1] = base ? (double*)(base + f->o_x1) : nullptr;
+    P.peer_j[r] = base ? (int*)(base + f->o_j) : nullptr;
+    P.peer_mbox[r] = base ? (double*)(base + f->o_mbox) : nullptr;
+  }
 }
 
 // ---- op-list construction (the kernel executes EngineP::ops in order) -------------------------------
@@ -589,6 +623,8 @@ static void push_aux_correct(llpf_filter* f, EngineP& P, int k) {
 }
 
 static int launch(llpf_filter* f, const EngineP& P, bool timed) {
+  if (f->world > 1 && !f->connected)
+    return fail(LLPF_ERR_BAD_ARG, "sharded filter: call llpf_shard_connect with every rank's blob first");
   CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned), f->stream));
   if (timed) CU(cudaEventRecord(f->ev0, f->stream));
   CU(f->launch(f, P));
@@ -1074,22 +1110,55 @@ extern "C" int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int3
 }
 
 // ------------------------------------------------------------------------------------------------
-// multi-GPU (peer-memory exchange) — filled in by llpf_shard.cu once enabled
+// multi-GPU: particles sharded over the GPUs of one box, exchange through IPC-mapped peer memory
 // ------------------------------------------------------------------------------------------------
+struct ShardBlob {
+  unsigned long long magic;
+  int rank, world, nx, pad;
+  long long n, ld;
+  unsigned long long arena_bytes, o_x0, o_x1, o_j, o_mbox;
+  cudaIpcMemHandle_t mem;
+};
+static const unsigned long long kBlobMagic = 0x4c4c504642323030ull;  // "LLPFB200"
+
 extern "C" int llpf_shard_blob_size(size_t* bytes) {
   if (!bytes) return fail(LLPF_ERR_BAD_ARG, "null");
-  *bytes = 256;
+  *bytes = sizeof(ShardBlob);
   return LLPF_OK;
 }
 extern "C" int llpf_shard_export(llpf_handle h, void* blob) {
   OKR(check_handle(h));
-  (void)blob;
-  return fail(LLPF_ERR_UNSUPPORTED, "sharded filters are not available in this build");
+  if (!blob) return fail(LLPF_ERR_BAD_ARG, "null");
+  CU(cudaSetDevice(h->device));
+  ShardBlob b;
+  std::memset(&b, 0, sizeof(b));
+  b.magic = kBlobMagic; b.rank = h->rank; b.world = h->world; b.nx = h->hm.nx;
+  b.n = h->n; b.ld = h->ld; b.arena_bytes = h->arena_bytes;
+  b.o_x0 = h->o_x0; b.o_x1 = h->o_x1; b.o_j = h->o_j; b.o_mbox = h->o_mbox;
+  CU(cudaIpcGetMemHandle(&b.mem, h->arena));
+  std::memcpy(blob, &b, sizeof(b));
+  return LLPF_OK;
 }
 extern "C" int llpf_shard_connect(llpf_handle h, const void* blobs) {
   OKR(check_handle(h));
-  (void)blobs;
-  return fail(LLPF_ERR_UNSUPPORTED, "sharded filters are not available in this build");
+  if (!blobs) return fail(LLPF_ERR_BAD_ARG, "null");
+  if (h->world <= 1) { h->connected = true; return LLPF_OK; }
+  CU(cudaSetDevice(h->device));
+  const ShardBlob* B = reinterpret_cast<const ShardBlob*>(blobs);
+  for (int r = 0; r < h->world; ++r) {
+    const ShardBlob& b = B[r];
+    if (b.magic != kBlobMagic || b.rank != r || b.world != h->world || b.nx != h->hm.nx || b.n != h->n ||
+        b.ld != h->ld || b.arena_bytes != h->arena_bytes || b.o_x0 != h->o_x0 || b.o_j != h->o_j || b.o_mbox != h->o_mbox)
+      return fail(LLPF_ERR_BAD_ARG, "shard blob mismatch (all ranks must create identical filters, blobs ordered by rank)");
+  }
+  for (int r = 0; r < h->world; ++r) {
+    if (r == h->rank || h->peer_base[r]) continue;
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, B[r].mem, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_base[r] = (char*)base;
+  }
+  h->connected = true;
+  return LLPF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

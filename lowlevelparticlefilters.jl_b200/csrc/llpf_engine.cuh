@@ -78,6 +78,7 @@ struct Scalars {
   double ll_total;
   double bins_total;
   double xhat[MAX_NX];
+  unsigned long long xseq;   // multi-GPU: number of peer exchanges done so far (identical on every rank)
 };
 
 // run-length op list: for c in [0,count): run kind with (a0 + c*da, b0 + c*db)
@@ -128,7 +129,15 @@ struct EngineP {
   RngKey key;
   double fix_scale, fix_inv;  // fixed-point scan scale: 2^62 / 2^-62 for normalised weights
   long long* dbg;             // optional phase timestamps [pass][16] (block 0, thread 0; -DLLPF_PHASE_TIMING)
+  // ---- sharded filters (world > 1): IPC-mapped views of every rank's arrays, index = rank ----
+  double* peer_x[MAX_WORLD][2];   // particle buffers (gather source on resample steps)
+  int* peer_j[MAX_WORLD];         // ancestor arrays (offspring indices are scattered to the slot's owner)
+  double* peer_mbox[MAX_WORLD];   // mailboxes: [2 parities][MAX_WORLD senders][MBOX_WORDS] tagged words
+  double* bcast;                  // local re-broadcast of a finished exchange: [2][MAX_WORLD][MBOX_DOUBLES]
+  u64* bcast_flag;                // [2]
 };
+constexpr int MBOX_DOUBLES = 16;  // broadcast-buffer stride per rank ([1..] payload)
+constexpr int MBOX_WORDS = 32;    // mailbox slot: 2 tagged 8-byte words per payload double
 
 #ifdef LLPF_PHASE_TIMING
 #define LLPF_TS(P, sh, k)                                                              \
@@ -186,6 +195,118 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks, un
 }
 
 __host__ __device__ constexpr int mdl_stride(int nx) { return (nx + 1) & ~1; }   // even row stride: rows are 16-byte aligned
+
+// ------------------------------------------------------------------------------------------------
+// cross-GPU exchange over NVLink peer memory (one process per GPU, arrays mapped with CUDA IPC)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 ld_acquire_sys_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(u64* p, u64 v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(u64* p, u64 v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ u64 ld_relaxed_sys_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 ld_relaxed_gpu_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ u64 ld_acquire_gpu_u64(const u64* p) {
+  u64 v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(u64* p, u64 v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// All-gather of NV doubles per rank.  Every block of every rank calls it with identical `mine` (the
+// values every block derived from the same local data after a local grid barrier).
+//   block 0, thread r (r != rank): writes the rank's values into peer r's mailbox (plain stores over
+//     NVLink, then a release flag), waits for peer r's flag in the LOCAL mailbox (relaxed polling, one
+//     system-scope acquire), copies peer r's payload into a local broadcast buffer;
+//   block 0, thread 0: publishes the broadcast buffer with a gpu-scope release flag;
+//   every other block: waits for that flag (gpu scope only — no system-scope traffic outside block 0).
+// Slots are double-buffered by the parity of the sequence number; a rank can never be more than one
+// exchange ahead of a peer (it needs that peer's post to get past the current one), and a post is only
+// made after a local grid barrier, i.e. after all of the rank's blocks finished reading the previous
+// exchange of the same parity.
+template <int NV>
+__device__ __forceinline__ void peer_allgather(const EngineP& P, u64& xseq, const double (&mine)[NV],
+                                               double (&all)[MAX_WORLD][NV]) {
+  static_assert(NV < MBOX_DOUBLES, "payload too large");
+  xseq += 1;
+  const int par = (int)(xseq & 1ull);
+  double* bc = P.bcast + (size_t)par * MAX_WORLD * MBOX_DOUBLES;
+  u64* bflag = P.bcast_flag + par;
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+      // "LL" protocol (as in NCCL's low-latency path): every 8-byte word carries 4 bytes of payload and the
+      // 4-byte sequence number, 8-byte stores are single NVLink transactions, so no fence is needed: a word
+      // is valid exactly when its flag half equals the expected sequence number.
+      const int r = threadIdx.x;
+      const u64 tag = (xseq & 0xffffffffull) << 32;
+      u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const u64 bits = (u64)__double_as_longlong(mine[k]);
+        st_relaxed_sys_u64(out + 2 * k, tag | (bits & 0xffffffffull));
+        st_relaxed_sys_u64(out + 2 * k + 1, tag | (bits >> 32));
+      }
+      const u64* in = reinterpret_cast<const u64*>(P.peer_mbox[P.rank]) + ((size_t)par * MAX_WORLD + r) * MBOX_WORDS;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        u64 lo, hi;
+        do { lo = ld_relaxed_sys_u64(in + 2 * k); } while ((lo & 0xffffffff00000000ull) != tag);
+        do { hi = ld_relaxed_sys_u64(in + 2 * k + 1); } while ((hi & 0xffffffff00000000ull) != tag);
+        __stcg(bc + r * MBOX_DOUBLES + 1 + k, __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull))));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_release_gpu_u64(bflag, xseq);
+    }
+  } else {
+    if (threadIdx.x == 0) {
+      while (ld_relaxed_gpu_u64(bflag) != xseq) {
+      }
+      (void)ld_acquire_gpu_u64(bflag);
+    }
+    __syncthreads();
+  }
+  for (int r = 0; r < P.world; ++r) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) all[r][k] = (r == P.rank) ? mine[k] : __ldcg(bc + r * MBOX_DOUBLES + 1 + k);
+  }
+}
+
+// cross-GPU barrier.  Call right after a local grid barrier; every thread that stored into peer memory
+// must have executed __threadfence_system() before arriving at that barrier, so all of this rank's peer
+// stores are performed before block 0 posts.
+__device__ __forceinline__ void peer_barrier(const EngineP& P, u64& xseq) {
+  const double none[1] = {0.0};
+  double all[MAX_WORLD][1];
+  peer_allgather<1>(P, xseq, none, all);
+}
 
 struct Shared {
   // model matrices, read with volatile 16-byte shared loads inside the particle loop (see llpf_math.cuh:
@@ -296,7 +417,7 @@ struct Stats {
 // combine all block partials in a fixed order (every block computes bitwise-identical Stats).
 template <int NX>
 __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Online<NX>& acc,
-                                              bool with_x, unsigned& bar_target) {
+                                              bool with_x, unsigned& bar_target, u64& xseq) {
   const double mb = block_max(acc.m, sh);
   const double sc = exp_nonpos(acc.m - mb, sh.mt);  // 0 for empty threads
   double v[2 + NX];
@@ -344,6 +465,27 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
     }
   }
   block_sum<2 + NX>(t, sh);
+  LLPF_TS(P, sh, 9);
+  if (P.world > 1) {
+    // one all-gather of (m, s, q, sx) per rank over NVLink; combined in rank order on every rank
+    double mine[3 + NX], all[MAX_WORLD][3 + NX];
+    mine[0] = m;
+#pragma unroll
+    for (int k = 0; k < 2 + NX; ++k) mine[1 + k] = t[k];
+    peer_allgather<3 + NX>(P, xseq, mine, all);
+    double gm = all[0][0];
+    for (int r = 1; r < P.world; ++r) gm = fmax(gm, all[r][0]);
+#pragma unroll
+    for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
+    for (int r = 0; r < P.world; ++r) {
+      const double e = exp_nonpos(all[r][0] - gm, sh.mt);
+      t[0] = fma(all[r][1], e, t[0]);
+      t[1] = fma(all[r][2], e * e, t[1]);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) t[2 + d] = fma(all[r][3 + d], e, t[2 + d]);
+    }
+    m = gm;
+  }
   LLPF_TS(P, sh, 8);
   Stats st;
   st.m = m; st.s = t[0]; st.q = t[1];
@@ -574,16 +716,33 @@ __device__ __forceinline__ int first_slot_ge(const Thresholds& th, const RngKey&
   return i0;
 }
 
-// write `id` into slots [lo, lo+cnt) of j: runs of up to 4 by predicated stores of the owning lane, longer
+// Destination of a global output slot: single GPU -> j + slot ; sharded -> the owner rank's j array.
+template <class T>
+struct SlotRouter {
+  T* j;                 // world == 1 (or stand-alone): flat array
+  T* const* peer;       // world > 1: per-rank arrays
+  int n;                // slots per rank
+  int world;
+  int rank;
+  mutable int remote;   // set once this thread has stored into another rank's array
+  __device__ __forceinline__ T* at(int slot) const {
+    if (world <= 1) return j + slot;
+    const int r = slot / n;
+    if (r != rank) remote = 1;
+    return peer[r] + (slot - r * n);
+  }
+};
+
+// write `id` into slots [lo, lo+cnt): runs of up to 4 by predicated stores of the owning lane, longer
 // runs by the whole warp.  Must be called by all 32 lanes (cnt = 0 for idle lanes).
 template <class T>
-__device__ __forceinline__ void scatter_runs(T* j, int lo, int cnt, T id) {
+__device__ __forceinline__ void scatter_runs(const SlotRouter<T>& R, int lo, int cnt, T id) {
   const int lane = threadIdx.x & 31;
   if (cnt <= 4) {
-    if (cnt > 0) __stcg(j + lo, id);
-    if (cnt > 1) __stcg(j + lo + 1, id);
-    if (cnt > 2) __stcg(j + lo + 2, id);
-    if (cnt > 3) __stcg(j + lo + 3, id);
+    if (cnt > 0) __stcg(R.at(lo), id);
+    if (cnt > 1) __stcg(R.at(lo + 1), id);
+    if (cnt > 2) __stcg(R.at(lo + 2), id);
+    if (cnt > 3) __stcg(R.at(lo + 3), id);
   }
   unsigned heavy = __ballot_sync(0xffffffffu, cnt > 4);
   while (heavy) {
@@ -592,7 +751,7 @@ __device__ __forceinline__ void scatter_runs(T* j, int lo, int cnt, T id) {
     const int lo_s = __shfl_sync(0xffffffffu, lo, src);
     const int c = __shfl_sync(0xffffffffu, cnt, src);
     const T id_s = __shfl_sync(0xffffffffu, id, src);
-    for (int s = lane; s < c; s += 32) __stcg(j + lo_s + s, id_s);
+    for (int s = lane; s < c; s += 32) __stcg(R.at(lo_s + s), id_s);
   }
 }
 
@@ -658,7 +817,7 @@ __device__ __forceinline__ void scan_stage1_pairs(const EngineP& P, Shared& sh, 
 
 template <class JT>
 __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int beg, int end, u64 off,
-                                              const Thresholds& th, JT* jout, JT jbase) {
+                                              const Thresholds& th, const SlotRouter<JT>& jout, JT jbase) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
   // F at every (row, warp) segment start: lane 0 of a segment needs it for its first particle
@@ -709,8 +868,15 @@ __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int 
 template <class JT, class LoadFn, class WeFn>
 __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, int beg, int end, unsigned& bar_target,
                                                 LoadFn loadfn, WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
-                                                int Mslots, const double* u_slots, JT* jout, JT jbase,
-                                                double& total_out) {
+                                                int Mslots, const double* u_slots, JT* jout_flat, JT jbase,
+                                                double& total_out, u64& xseq) {
+  SlotRouter<JT> jout;
+  jout.j = jout_flat;
+  jout.peer = reinterpret_cast<JT* const*>(P.peer_j);   // only dereferenced when world > 1 (JT == int there)
+  jout.n = P.n;
+  jout.world = P.world;
+  jout.rank = P.rank;
+  jout.remote = 0;
   const int rows2 = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
   const bool pairs = (P.scan_mode == 0) && (rows2 <= MAX_ROWS) && ((beg & 1) == 0);
   bool tabled = false;
@@ -727,8 +893,21 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     total = __ldcg(P.bins + P.n - 1);
   } else {
     scan_block_offsets(P, sh, 0ull);
-    total = (double)sh.offs[P.nblocks] * P.fix_inv;
-    off = sh.offs[blockIdx.x];
+    u64 gbase = 0, gtot = sh.offs[P.nblocks];
+    if (P.world > 1) {
+      // global CDF offset of this rank: all-gather of the ranks' fixed-point totals (exact integers, so the
+      // global bins are bit-identical to a single-GPU scan of the same weights)
+      double mine[1] = {__longlong_as_double((long long)gtot)}, all[MAX_WORLD][1];
+      peer_allgather<1>(P, xseq, mine, all);
+      gtot = 0;
+      for (int r = 0; r < P.world; ++r) {
+        const u64 tr = (u64)__double_as_longlong(all[r][0]);
+        if (r < P.rank) gbase += tr;
+        gtot += tr;
+      }
+    }
+    total = (double)gtot * P.fix_inv;
+    off = gbase + sh.offs[blockIdx.x];
   }
   total_out = total;
   if (gen_u01) u01 = resample_u01(P.key, step_idx);
@@ -737,7 +916,9 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     scatter_pairs<JT>(P, sh, beg, end, off, th, jout, jbase);
     const int f_tot = first_slot_ge(th, P.key, total);
     LLPF_TS(P, sh, 3);
+    if (jout.remote) __threadfence_system();   // my peer stores are performed system-wide before I arrive
     grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+    if (P.world > 1) peer_barrier(P, xseq);    // every rank's offspring indices have landed in my j
     LLPF_TS(P, sh, 4);
     return f_tot;
   }
@@ -788,7 +969,9 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   }
   const int f_total = first_slot_ge(th, P.key, total);
   LLPF_TS(P, sh, 3);
+  if (jout.remote) __threadfence_system();
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  if (P.world > 1) peer_barrier(P, xseq);
   LLPF_TS(P, sh, 4);
   return f_total;
 }
@@ -1011,6 +1194,22 @@ __device__ __forceinline__ void stage_step(const EngineP& P, const ModelP<NX, NY
   skip = (k_y > 0) ? (sh.skip != 0) : false;
 }
 
+// particle `a` (GLOBAL index) from buffer `buf_id` of whichever rank owns it
+template <int NX>
+__device__ __forceinline__ void gather_x(const EngineP& P, int buf_id, int a, double (&x)[NX]) {
+  const double* buf;
+  int li;
+  if (P.world > 1) {
+    const int r = a / P.n;
+    li = a - r * P.n;
+    buf = P.peer_x[r][buf_id];
+  } else {
+    li = a - P.first;
+    buf = P.x[buf_id];
+  }
+#pragma unroll
+  for (int d = 0; d < NX; ++d) x[d] = __ldcg(buf + (size_t)d * P.ld + li);
+}
 template <int NX>
 __device__ __forceinline__ void load_x(const double* buf, long long ld, int i, double (&x)[NX]) {
 #pragma unroll
@@ -1087,7 +1286,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
           }
           return we;
         },
-        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total);
+        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq);
     sc.bins_total = total;
   }
   const double* src = P.x[sc.cur];
@@ -1100,20 +1299,41 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   // software pipeline: the ancestor index of the NEXT iteration is fetched one iteration ahead; within an
   // iteration the particle/weight loads are issued first, the (data-independent) noise is computed while
   // they are in flight, and only then are they consumed.
-  int a_next = 0;
-  if (res && cx.beg + (int)threadIdx.x < cx.end) a_next = __ldcg(P.j + cx.beg + threadIdx.x);
+  // resample path: ancestor index fetched TWO iterations ahead, the gathered particle ONE iteration ahead
+  // (it may live in a peer GPU's memory: ~2 us over NVLink)
+  int a_n1 = 0, a_n2 = 0;
+  double xn[NX];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) xn[d] = 0.0;
+  if (res) {
+    const int i0 = cx.beg + threadIdx.x;
+    if (i0 < cx.end) {
+      a_n1 = __ldcg(P.j + i0);
+      if (P.first + i0 >= f_total) {
+        if (jid) a_n1 = P.first + i0;
+        __stcg(P.j + i0, a_n1);
+      }
+      gather_x<NX>(P, sc.cur, a_n1, xn);
+    }
+    if (i0 + BLOCK < cx.end) a_n2 = __ldcg(P.j + i0 + BLOCK);
+  }
   for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
     const int gi = P.first + i;
     double x[NX];
     double wraw = 0.0;
     if (res) {
-      int a = a_next;
-      if (i + BLOCK < cx.end) a_next = __ldcg(P.j + i + BLOCK);
-      if (gi >= f_total) {             // untouched entry (resample.jl:26-34): keep state.j
-        if (jid) a = gi;
-        __stcg(P.j + i, a);
+#pragma unroll
+      for (int d = 0; d < NX; ++d) x[d] = xn[d];
+      const int in = i + BLOCK;
+      if (in < cx.end) {
+        int a = a_n2;
+        if (P.first + in >= f_total) {     // untouched entry (resample.jl:26-34): keep state.j
+          if (jid) a = P.first + in;
+          __stcg(P.j + in, a);
+        }
+        gather_x<NX>(P, sc.cur, a, xn);
+        if (in + BLOCK < cx.end) a_n2 = __ldcg(P.j + in + BLOCK);
       }
-      load_x<NX>(src, P.ld, a - P.first, x);
     } else {
       load_x<NX>(src, P.ld, i, x);
       if (!ws.uniform) wraw = __ldcg(P.w + i);
@@ -1159,7 +1379,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
     sc.t_index += 1;       // filtering.jl:152
   }
   if (k_weigh > 0) {
-    const Stats st = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target);
+    const Stats st = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target, sc.xseq);
     publish_step<NX>(P, sc, k_weigh, st);
   }
 }
@@ -1200,7 +1420,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
     __stcg(P.w + i, v);
     acc.add(v, x, false, sh.mt);
   }
-  const Stats s1 = reduce_stats<NX>(P, sh, acc, false, cx.bar_target);
+  const Stats s1 = reduce_stats<NX>(P, sh, acc, false, cx.bar_target, sc.xseq);
   const double inv1 = 1.0 / s1.s;
   const double m1 = s1.m;
   const double* wraw = P.w;
@@ -1210,7 +1430,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   const int f_total = resample_indices<int>(
       P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return __ldcg(wraw + i); },
       [=](int, double wr) { return exp_nonpos(wr - m1, *mtp) * inv1; }, 0.0, true,
-      step_idx, (int)P.N, nullptr, P.j, P.first, total);
+      step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq);
   sc.bins_total = total;
   const bool with_x = (P.want_xhat != 0);
   const double lN = log((double)P.N);
@@ -1228,13 +1448,13 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
     double x[NX];
     double wnew;
     if (adv) {
-      load_x<NX>(cur, P.ld, a - P.first, x);                     // :230 propagate again from xprev[j]
+      gather_x<NX>(P, sc.cur, a, x);                             // :230 propagate again from xprev[j]
       dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
       add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);
       store_x<NX>(oth, P.ld, i, x);
       wnew = cx.lw1N;                                            // :228 reset_weights!
     } else {
-      load_x<NX>(oth, P.ld, a - P.first, x);                     // :207 permute_with_buffer!
+      gather_x<NX>(P, sc.cur ^ 1, a, x);                         // :207 permute_with_buffer!
       add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);     // :208 add_noise!
       store_x<NX>(P.x[sc.cur], P.ld, i, x);
       wnew = __ldcg(P.lam + i) - lN;                             // :210-213
@@ -1249,7 +1469,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   sc.last_resampled = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k - 1] = 1;
   sc.t_index += 1;                                               // :215
-  const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target);
+  const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target, sc.xseq);
   // stats of the raw w[] are ready; correct! (filtering.jl:170-174) has not been *called* yet
   sc.pend = 0; sc.uniform = 0;
   sc.stats_ahead = 1; sc.stats_valid = 0;

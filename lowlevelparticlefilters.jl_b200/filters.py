@@ -169,6 +169,8 @@ class AbstractParticleFilter:
 
     def _create(self, N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device,
                 rank=0, world=1):
+        """N is the GLOBAL particle count; with world > 1 this process owns the contiguous slice
+        [rank*N/world, (rank+1)*N/world) and must call connect_shards() before the first step."""
         self._lib = _abi.load_library()
         self._model = model
         cfg = _abi.Config()
@@ -183,7 +185,10 @@ class AbstractParticleFilter:
         self._cfg = cfg
         self._h = C.c_void_p()
         check(self._lib, self._lib.llpf_create(C.byref(cfg), C.byref(model.struct), C.byref(self._h)))
-        self.N = int(N)
+        self.N_global = int(N)
+        self.rank, self.world = int(rank), max(1, int(world))
+        self.N = int(N) // self.world          # local particle count: accessor arrays have this length
+        self.first = self.rank * self.N
         self.nx, self.nu, self.ny = model.nx, model.nu, model.ny
         self.Ts = float(Ts)
         self.resample_threshold = float(resample_threshold)
@@ -220,7 +225,7 @@ class ParticleFilter(AbstractParticleFilter):
 
     def __init__(self, N, dynamics, measurement, dynamics_density, measurement_density, initial_density, *,
                  resample_threshold=0.1, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
-                 scan_mode="fast", device=0, p=None, **_ignored):
+                 scan_mode="fast", device=0, p=None, rank=0, world=1, **_ignored):
         if not isinstance(measurement, LinearMeasurement):
             raise TypeError("measurement must be a LinearMeasurement descriptor")
         self.dynamics, self.measurement = dynamics, measurement
@@ -228,7 +233,7 @@ class ParticleFilter(AbstractParticleFilter):
         self.initial_density = initial_density
         model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
                               initial_density)
-        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device)
+        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world)
 
 
 class AdvancedParticleFilter(AbstractParticleFilter):
@@ -236,7 +241,7 @@ class AdvancedParticleFilter(AbstractParticleFilter):
 
     def __init__(self, N, dynamics, measurement, measurement_likelihood, dynamics_density, initial_density, *,
                  resample_threshold=0.5, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
-                 scan_mode="fast", device=0, p=None, **_ignored):
+                 scan_mode="fast", device=0, p=None, rank=0, world=1, **_ignored):
         if not isinstance(measurement_likelihood, GaussianLikelihood):
             raise TypeError("measurement_likelihood must be a GaussianLikelihood descriptor")
         self.dynamics, self.measurement = dynamics, measurement
@@ -244,7 +249,7 @@ class AdvancedParticleFilter(AbstractParticleFilter):
         self.dynamics_density, self.initial_density = dynamics_density, initial_density
         model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
                               measurement_likelihood.R2, initial_density)
-        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device)
+        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world)
 
 
 class AuxiliaryParticleFilter(AbstractParticleFilter):
@@ -259,8 +264,8 @@ class AuxiliaryParticleFilter(AbstractParticleFilter):
             self._filter_code = FILTER_AUX_ADVANCED if adv else FILTER_AUX
             for name in ("dynamics", "measurement", "dynamics_density", "initial_density"):
                 setattr(self, name, getattr(inner, name))
-            self._create(inner.N, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
-                         inner.seed, cfg.scan_mode, cfg.device)
+            self._create(inner.N_global, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
+                         inner.seed, cfg.scan_mode, cfg.device, inner.rank, inner.world)
         else:
             self.__init__(ParticleFilter(*args, **kwargs))
 
@@ -351,9 +356,10 @@ def _run(pf, u, y, conv, history, epoch, want_steps=True, want_xhat=True):
         res["xhat"] = np.zeros((T, pf.nx))
         out.xhat = res["xhat"].ctypes.data_as(dp)
     if history:
-        res["x"] = np.zeros((T, pf.N, pf.nx))
-        res["w"] = np.zeros((T, pf.N))
-        res["we"] = np.zeros((T, pf.N))
+        # the device history buffers are indexed by GLOBAL particle number; a sharded rank fills its slice
+        res["x"] = np.zeros((T, pf.N_global, pf.nx))
+        res["w"] = np.zeros((T, pf.N_global))
+        res["we"] = np.zeros((T, pf.N_global))
         out.x_hist = res["x"].ctypes.data_as(dp)
         out.w_hist = res["w"].ctypes.data_as(dp)
         out.we_hist = res["we"].ctypes.data_as(dp)
@@ -363,6 +369,9 @@ def _run(pf, u, y, conv, history, epoch, want_steps=True, want_xhat=True):
     check(pf._lib, pf._lib.llpf_run(pf._h, T, up, yp, conv, int(epoch), C.byref(ll), C.byref(out)))
     res["ll"] = ll.value
     res["u"], res["y"], res["T"] = u, y, T
+    if history and pf.world > 1:
+        sl = slice(pf.first, pf.first + pf.N)
+        res["x"], res["w"], res["we"] = res["x"][:, sl], res["w"][:, sl], res["we"][:, sl]
     return res
 
 
@@ -524,6 +533,34 @@ def logsumexp(w, device=0):
     ll = C.c_double()
     check(lib, lib.llpf_logsumexp(w.size, w.ctypes.data_as(dp), we.ctypes.data_as(dp), C.byref(ll), device))
     return ll.value, w, we
+
+
+def shard_blob(pf):
+    """Opaque IPC descriptor of this rank's device arena (bytes) — exchange with every other rank."""
+    n = C.c_size_t()
+    check(pf._lib, pf._lib.llpf_shard_blob_size(C.byref(n)))
+    buf = C.create_string_buffer(n.value)
+    check(pf._lib, pf._lib.llpf_shard_export(pf._h, buf))
+    return buf.raw
+
+
+def connect_shards(pf, allgather=None):
+    """Wire the ranks of a sharded filter together.  `allgather(bytes) -> list[bytes]` (ordered by rank) is any
+    host-side all-gather; by default torch.distributed.all_gather_object on the default process group (NCCL or
+    gloo: it only carries the 200-byte IPC descriptors — the data path is peer memory over NVLink)."""
+    if pf.world <= 1:
+        return
+    mine = shard_blob(pf)
+    if allgather is None:
+        import torch.distributed as dist
+        blobs = [None] * pf.world
+        dist.all_gather_object(blobs, mine)
+    else:
+        blobs = list(allgather(mine))
+    if len(blobs) != pf.world:
+        raise ValueError("need one blob per rank")
+    joined = b"".join(blobs)
+    check(pf._lib, pf._lib.llpf_shard_connect(pf._h, C.create_string_buffer(joined, len(joined))))
 
 
 def launch_count(pf):
