@@ -1,0 +1,156 @@
+# LLPFB200.jl — the reference-side binding of libllpf_b200.so (ccall).  NOT runnable in the build image
+# (no julia there); shipped so that a maintainer with Julia can drop the GPU path behind the package's own
+# generic functions.  Every method cites the reference method it shadows.
+module LLPFB200
+
+using LowLevelParticleFilters, StaticArrays, LinearAlgebra
+import LowLevelParticleFilters: reset!, predict!, correct!, update!, forward_trajectory, loglik, particles, weights,
+    expweights, num_particles, effective_particles, shouldresample, weighted_mean, index, state
+
+const lib = get(ENV, "LLPF_LIB_PATH", joinpath(@__DIR__, "..", "lowlevelparticlefilters.jl_b200", "csrc", "libllpf_b200.so"))
+
+# ---- include/llpf.h PODs (field order and types must match the header) ---------------------------------
+struct LLPFModel
+    nx::Int32; nu::Int32; ny::Int32; dynamics::Int32
+    A::Ptr{Float64}; B::Ptr{Float64}; C::Ptr{Float64}; R1::Ptr{Float64}; R2::Ptr{Float64}
+    mu0::Ptr{Float64}; Sigma0::Ptr{Float64}
+    dyn_params::NTuple{8,Float64}
+    t_switch::Float64; a1_factor::Float64; integ_Ts::Float64
+    supersample::Int32; _pad::Int32
+end
+struct LLPFConfig
+    N::Int64; filter::Int32; resampling::Int32
+    resample_threshold::Float64; Ts::Float64; seed::UInt64
+    scan_mode::Int32; device::Int32; rank::Int32; world::Int32
+end
+struct LLPFRunOutputs
+    ll_steps::Ptr{Float64}; ess_steps::Ptr{Float64}; resampled::Ptr{Int32}; xhat::Ptr{Float64}
+    x_hist::Ptr{Float64}; w_hist::Ptr{Float64}; we_hist::Ptr{Float64}
+end
+
+# ---- model descriptors (closures cannot cross a C-ABI) ---------------------------------------------------
+"dynamics(x,u,p,t) = A*x .+ B*u ; measurement = C*x ; df = N(0,R1), dg = N(0,R2), d0 = N(mu0,Sigma0)"
+struct LGModel
+    A::Matrix{Float64}; B::Matrix{Float64}; C::Matrix{Float64}
+    R1::Matrix{Float64}; R2::Matrix{Float64}; mu0::Vector{Float64}; Sigma0::Matrix{Float64}
+end
+"rk4(quadtank, Ts; supersample) with additive N(0,R1) noise, y = C*x + N(0,R2)  (examples/example_quadtank.jl)"
+struct QuadtankModel
+    p::NTuple{6,Float64}; Ts::Float64; supersample::Int; t_switch::Float64; a1_factor::Float64
+    C::Matrix{Float64}; R1::Matrix{Float64}; R2::Matrix{Float64}; mu0::Vector{Float64}; Sigma0::Matrix{Float64}
+end
+
+check(rc) = rc == 0 ? nothing : error("llpf status $rc: " * unsafe_string(ccall((:llpf_last_error, lib), Cstring, ())))
+
+mutable struct GPUParticleFilter{M} <: LowLevelParticleFilters.AbstractParticleFilter
+    h::Ptr{Cvoid}
+    model::M
+    N::Int; nx::Int; nu::Int; ny::Int
+    Ts::Float64; resample_threshold::Float64
+    kind::Int32                      # 0 PF, 1 Advanced, 2 Aux, 3 Aux{Advanced}
+    epoch::UInt64
+end
+
+function c_model(m::LGModel)
+    nx, nu, ny = size(m.A, 1), size(m.B, 2), size(m.C, 1)
+    LLPFModel(nx, nu, ny, 0, pointer(m.A), pointer(m.B), pointer(m.C), pointer(m.R1), pointer(m.R2), pointer(m.mu0),
+              pointer(m.Sigma0), ntuple(_ -> 0.0, 8), Inf, 1.0, 1.0, 1, 0), nx, nu, ny
+end
+function c_model(m::QuadtankModel)
+    LLPFModel(4, 2, 2, 1, C_NULL, C_NULL, pointer(m.C), pointer(m.R1), pointer(m.R2), pointer(m.mu0), pointer(m.Sigma0),
+              (m.p..., 0.0, 0.0), m.t_switch, m.a1_factor, m.Ts, m.supersample, 0), 4, 2, 2
+end
+
+"ParticleFilter(N, ...)  src/PFtypes.jl:65-75 (kind=0) / AdvancedParticleFilter :200-210 (kind=1) / AuxiliaryParticleFilter :38-49 (kind=2)"
+function GPUParticleFilter(N::Integer, m; kind=0, resample_threshold=(kind == 1 ? 0.5 : 0.1), Ts=1.0, seed=0,
+                           resampling=0, scan_mode=0, device=0, rank=0, world=1)
+    mdl, nx, nu, ny = c_model(m)
+    cfg = LLPFConfig(N, kind, resampling, resample_threshold, Ts, seed, scan_mode, device, rank, world)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve m check(ccall((:llpf_create, lib), Cint, (Ref{LLPFConfig}, Ref{LLPFModel}, Ref{Ptr{Cvoid}}), cfg, mdl, h))
+    pf = GPUParticleFilter(h[], m, Int(N) ÷ world, nx, nu, ny, Float64(Ts), Float64(resample_threshold), Int32(kind), UInt64(0))
+    finalizer(p -> ccall((:llpf_destroy, lib), Cint, (Ptr{Cvoid},), p.h), pf)
+end
+
+# ---- verbs -------------------------------------------------------------------------------------------------
+"reset!(pf)  src/filtering.jl:4-14"
+function reset!(pf::GPUParticleFilter)
+    pf.epoch += 1
+    check(ccall((:llpf_reset, lib), Cint, (Ptr{Cvoid}, UInt64), pf.h, pf.epoch))
+end
+"index(pf) = state.t[]  src/PFtypes.jl:319"
+function index(pf::GPUParticleFilter)
+    t = Ref{Int64}(0); check(ccall((:llpf_index, lib), Cint, (Ptr{Cvoid}, Ref{Int64}), pf.h, t)); Int(t[])
+end
+vecf(v) = collect(Float64, v)
+"correct!(pf,u,y,p,t) -> (ll,0)  src/filtering.jl:164-174"
+function correct!(pf::GPUParticleFilter, u, y, p=nothing, t=index(pf) * pf.Ts)
+    ll = Ref{Float64}(0.0)
+    check(ccall((:llpf_correct, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}), pf.h, vecf(u), vecf(y), t, ll))
+    ll[], 0
+end
+"predict!(pf,u,p,t)  src/filtering.jl:140-153"
+predict!(pf::GPUParticleFilter, u, p=nothing, t=index(pf) * pf.Ts) =
+    check(ccall((:llpf_predict, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64), pf.h, vecf(u), t))
+"predict!(pfa,u,y1,p,t)  src/filtering.jl:195-234"
+predict!(pf::GPUParticleFilter, u, y1, p, t) =
+    check(ccall((:llpf_predict_aux, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), pf.h, vecf(u), vecf(y1), t))
+"update!(f,u,y,p,t) src/filtering.jl:181-185 ; update!(pfa,u,y,y1,p,t) :187-191"
+function update!(pf::GPUParticleFilter, u, y, p=nothing, t=index(pf) * pf.Ts; y1=nothing)
+    ll = Ref{Float64}(0.0)
+    y1p = y1 === nothing ? Ptr{Float64}(C_NULL) : pointer(vecf(y1))
+    check(ccall((:llpf_update, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}),
+                pf.h, vecf(u), vecf(y), y1p, t, ll))
+    ll[], 0
+end
+(pf::GPUParticleFilter)(u, y, p=nothing, t=index(pf) * pf.Ts) = update!(pf, u, y, p, t)     # src/filtering.jl:238
+
+flat(v::AbstractVector) = reduce(hcat, v)          # n x T column-major == the memory of Vector{SVector{n}}
+
+"loglik(pf,u,y,p)  src/smoothing.jl:227-236"
+function loglik(pf::GPUParticleFilter, u::AbstractVector, y::AbstractVector, p=nothing)
+    U, Y = flat(u), flat(y); ll = Ref{Float64}(0.0); pf.epoch += 1
+    check(ccall((:llpf_run, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, UInt64, Ref{Float64}, Ptr{Cvoid}),
+                pf.h, length(y), U, Y, 1, pf.epoch, ll, C_NULL))
+    ll[]
+end
+"forward_trajectory(pf,u,y,p) -> ParticleFilteringSolution  src/filtering.jl:343-384, src/solutions.jl:334-345"
+function forward_trajectory(pf::GPUParticleFilter, u::AbstractVector, y::AbstractVector, p=nothing)
+    U, Y = flat(u), flat(y); T = length(y); N = pf.N
+    x = Matrix{SVector{pf.nx,Float64}}(undef, N, T); w = Matrix{Float64}(undef, N, T); we = similar(w)
+    out = LLPFRunOutputs(C_NULL, C_NULL, C_NULL, C_NULL, pointer(reinterpret(Float64, x)), pointer(w), pointer(we))
+    ll = Ref{Float64}(0.0); pf.epoch += 1
+    GC.@preserve x w we check(ccall((:llpf_run, lib), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, UInt64, Ref{Float64}, Ref{LLPFRunOutputs}),
+        pf.h, T, U, Y, 0, pf.epoch, ll, out))
+    LowLevelParticleFilters.ParticleFilteringSolution(pf, u, y, x, w, we, ll[])
+end
+
+# ---- accessors (src/PFtypes.jl:296-334, src/resample.jl:1-10, src/filtering.jl:541-568) --------------------
+num_particles(pf::GPUParticleFilter) = pf.N
+function particles(pf::GPUParticleFilter)
+    x = Vector{SVector{pf.nx,Float64}}(undef, pf.N)
+    check(ccall((:llpf_get_particles, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), pf.h, pointer(reinterpret(Float64, x)))); x
+end
+getvec(pf, sym) = (v = Vector{Float64}(undef, pf.N); check(ccall((sym, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), pf.h, v)); v)
+weights(pf::GPUParticleFilter) = getvec(pf, :llpf_get_weights)
+expweights(pf::GPUParticleFilter) = getvec(pf, :llpf_get_expweights)
+function effective_particles(pf::GPUParticleFilter)
+    v = Ref{Float64}(0.0); check(ccall((:llpf_effective_particles, lib), Cint, (Ptr{Cvoid}, Ref{Float64}), pf.h, v)); v[]
+end
+function shouldresample(pf::GPUParticleFilter)
+    v = Ref{Int32}(0); check(ccall((:llpf_shouldresample, lib), Cint, (Ptr{Cvoid}, Ref{Int32}), pf.h, v)); v[] != 0
+end
+function weighted_mean(pf::GPUParticleFilter)
+    v = Vector{Float64}(undef, pf.nx); check(ccall((:llpf_weighted_mean, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}), pf.h, v)); v
+end
+
+"resample(ResampleSystematic, we, j, bins, M) src/resample.jl:17-36 with the rand() of :23 supplied"
+function resample_systematic(we::Vector{Float64}, u01::Float64; M=length(we), j=collect(Int64, 1:M), scan_mode=0, device=0)
+    bins = similar(we)
+    check(ccall((:llpf_resample_systematic, lib), Cint, (Int64, Ptr{Float64}, Float64, Int64, Ptr{Int64}, Ptr{Float64}, Int32, Int32),
+                length(we), we, u01, M, j, bins, scan_mode, device))
+    j, bins
+end
+
+end # module

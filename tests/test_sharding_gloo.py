@@ -1,0 +1,99 @@
+"""world_size-2 (and 4) gloo tests on CPU for the N>1 path's host-visible logic: the partition arithmetic, the exact
+fixed-point global CDF, the source-side slot ownership and the routing of offspring indices to their owner rank
+(llpf_b200/sharding.py mirrors what the kernels do over NVLink).  The sharded result must equal the unsharded one
+bit for bit, and the oracle's serial resample whenever the weights are dyadic."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from llpf_b200 import sharding as S
+from oracle import oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, N, seed, dyadic, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    if dyadic:
+        k = rng.integers(0, 1 << 16, size=N).astype(np.float64)
+        k[rng.integers(0, N, size=max(1, N // 40))] *= 32
+        we = k / 2.0 ** np.ceil(np.log2(k.sum()))
+    else:
+        _, _, we = O.logsumexp(rng.standard_normal(N) * 2.5)
+    u01 = float(rng.random())
+    first, n = S.shard_range(N, rank, world)
+
+    def allgather(v):
+        got = [None] * world
+        dist.all_gather_object(got, v)
+        return got
+
+    def alltoall(lists):
+        got = [None] * world
+        for src in range(world):           # all-to-all out of object scatters (tiny payloads; CPU test only)
+            buf = [None]
+            dist.scatter_object_list(buf, lists if rank == src else None, src=src)
+            got[src] = buf[0]
+        return got
+
+    j, bins, f_total = S.sharded_systematic(we[first:first + n], u01, N, rank, world, allgather, alltoall)
+    np.save(os.path.join(out_dir, f"j_{rank}.npy"), j)
+    np.save(os.path.join(out_dir, f"bins_{rank}.npy"), bins)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "we.npy"), we)
+        np.save(os.path.join(out_dir, "meta.npy"), np.array([u01, f_total]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("N,dyadic", [(64, True), (4096, True), (4096, False), (100_000, False)])
+def test_sharded_resample_equals_unsharded(tmp_path, world, N, dyadic):
+    if N % world:
+        pytest.skip("N not divisible")
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, N, 1234 + N, dyadic, str(tmp_path)), nprocs=world, join=True)
+    j = np.concatenate([np.load(tmp_path / f"j_{r}.npy") for r in range(world)])
+    bins = np.concatenate([np.load(tmp_path / f"bins_{r}.npy") for r in range(world)])
+    we = np.load(tmp_path / "we.npy")
+    u01, f_total = np.load(tmp_path / "meta.npy")
+    # (a) sharding invariance: identical to the same protocol run in ONE process
+    j1, bins1, ft1 = S.sharded_systematic(we, u01, N, 0, 1, lambda v: [v], lambda lists: lists)
+    assert np.array_equal(j, j1) and np.array_equal(bins, bins1) and ft1 == f_total
+    assert np.all(np.diff(j[:int(f_total)]) >= 0) and j.min() >= 0 and j.max() < N
+    # (b) against the reference-order oracle (serial f64 cumsum, two-pointer walk)
+    jo, bo = O.resample_systematic(we, u01)
+    if dyadic:
+        assert np.array_equal(bins, bo)
+        assert np.array_equal(j + 1, jo)
+    else:
+        assert np.max(np.abs(bins - bo)) < 64 * np.sqrt(N) * 2.3e-16
+        d = np.nonzero(j + 1 != jo)[0]
+        assert d.size <= max(2, N // 20000)
+        assert np.all(np.abs(j[d] + 1 - jo[d]) == 1)
+
+
+def test_partition_arithmetic():
+    assert S.shard_range(1 << 20, 3, 8) == (3 << 17, 1 << 17)
+    with pytest.raises(ValueError):
+        S.shard_range(10, 0, 3)
+    f = S.to_fixed(np.array([0.0, 1.0, 0.5, -1.0, np.nan, 2.0]))
+    assert list(f) == [0, 1 << 62, 1 << 61, 0, 0, 1 << 62]
+    # F(v): first slot whose threshold reaches v
+    r, M = 0.3 / 8, 8
+    s = S.thresholds(np.arange(M), r, M)
+    for v in (0.0, s[3], np.nextafter(s[3], 1), 0.99, 2.0):
+        F = int(S.first_slot_ge(np.array([v]), r, M)[0])
+        assert F == int(np.sum(s < v))
