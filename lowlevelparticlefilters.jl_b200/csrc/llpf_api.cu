@@ -386,9 +386,13 @@ struct Dispatch {
 #define DISP(NX, NY, DYN) \
   { NX, NY, DYN, launch_engine<NX, NY, DYN>, launch_init<NX>, occupancy_engine<NX, NY, DYN> }
 static const Dispatch g_dispatch[] = {
+#ifdef LLPF_DISPATCH_MIN   // quick tuning builds: only the headline instantiation
+    DISP(4, 2, 0),
+#else
     DISP(1, 1, 0), DISP(2, 1, 0), DISP(2, 2, 0), DISP(3, 1, 0), DISP(3, 2, 0), DISP(3, 3, 0),
     DISP(4, 1, 0), DISP(4, 2, 0), DISP(4, 3, 0), DISP(4, 4, 0), DISP(6, 2, 0), DISP(6, 3, 0),
     DISP(8, 2, 0), DISP(8, 4, 0), DISP(4, 2, 1),
+#endif
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -528,7 +532,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const size_t o_j = take((size_t)f->ld * 4);
   const size_t o_loc = take((size_t)f->ld * 8);
   const size_t o_part = take((size_t)MAX_BLOCKS * PS * 8), o_tots = take((size_t)MAX_BLOCKS * 8);
-  const size_t o_bar = take(256), o_sc = take(sizeof(Scalars));
+  const size_t o_bar = take((size_t)BAR_TOTAL_WORDS * 4), o_sc = take(sizeof(Scalars));
   const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + MAX_NX) * 8);
   const size_t o_scr = take((size_t)(nx + 2) * f->ld * 8);
   const size_t o_mbox = take((size_t)2 * MAX_WORLD * MBOX_WORDS * 8);
@@ -625,7 +629,7 @@ static void push_aux_correct(llpf_filter* f, EngineP& P, int k) {
 static int launch(llpf_filter* f, const EngineP& P, bool timed) {
   if (f->world > 1 && !f->connected)
     return fail(LLPF_ERR_BAD_ARG, "sharded filter: call llpf_shard_connect with every rank's blob first");
-  CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned), f->stream));
+  CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * BAR_TOTAL_WORDS, f->stream));
   if (timed) CU(cudaEventRecord(f->ev0, f->stream));
   CU(f->launch(f, P));
   f->launches += 1;
@@ -1044,11 +1048,11 @@ static int resample_standalone(int strategy, int64_t N, const double* we, double
   unsigned* d_bar = nullptr;
   long long* d_j = nullptr;
   CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_bins, (size_t)N)); CU(sp.alloc(&d_part, (size_t)MAX_BLOCKS * PS));
-  CU(sp.alloc(&d_tots, (size_t)MAX_BLOCKS)); CU(sp.alloc(&d_bar, 64)); CU(sp.alloc(&d_j, (size_t)M));
+  CU(sp.alloc(&d_tots, (size_t)MAX_BLOCKS)); CU(sp.alloc(&d_bar, BAR_TOTAL_WORDS)); CU(sp.alloc(&d_j, (size_t)M));
   CU(sp.alloc(&d_loc, (size_t)N));
   CU(cudaMemcpy(d_we, we, sizeof(double) * N, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(d_j, j_inout, sizeof(long long) * M, cudaMemcpyHostToDevice));
-  CU(cudaMemset(d_bar, 0, 64 * sizeof(unsigned)));
+  CU(cudaMemset(d_bar, 0, BAR_TOTAL_WORDS * sizeof(unsigned)));
   if (u_slots) {
     CU(sp.alloc(&d_us, (size_t)M));
     CU(cudaMemcpy(d_us, u_slots, sizeof(double) * M, cudaMemcpyHostToDevice));
@@ -1096,9 +1100,9 @@ extern "C" int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int3
   double *d_w = nullptr, *d_we = nullptr, *d_part = nullptr, *d_ll = nullptr;
   unsigned* d_bar = nullptr;
   CU(sp.alloc(&d_w, (size_t)N)); CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_part, (size_t)MAX_BLOCKS * PS));
-  CU(sp.alloc(&d_ll, 1)); CU(sp.alloc(&d_bar, 64));
+  CU(sp.alloc(&d_ll, 1)); CU(sp.alloc(&d_bar, BAR_TOTAL_WORDS));
   CU(cudaMemcpy(d_w, w, sizeof(double) * N, cudaMemcpyHostToDevice));
-  CU(cudaMemset(d_bar, 0, 64 * sizeof(unsigned)));
+  CU(cudaMemset(d_bar, 0, BAR_TOTAL_WORDS * sizeof(unsigned)));
   P.partials = d_part; P.bar = d_bar; P.N = N; P.n = (int)N; P.world = 1;
   void* args[] = {(void*)&P, (void*)&d_w, (void*)&d_we, (void*)&d_ll};
   CU(cudaLaunchCooperativeKernel((const void*)k_logsumexp, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));

@@ -323,6 +323,9 @@ struct Shared {
   double yt[8];
   int skip;
   int pass_id;
+  int is_last;                  // reduce_stats: this block arrived last and runs the combine
+  uint32_t stat_words[32];      // reduce_stats: payload halves of the finished statistics
+  double peer_vals[MAX_WORLD * (3 + MAX_NX)];   // reduce_stats: the ranks' statistics (sharded filters)
   u64 offs[MAX_BLOCKS + 1];     // exclusive block offsets of the fixed-point scan
   alignas(16) MathTab mt;       // log / exp tables + polynomial coefficients of llpf_math.cuh
 };
@@ -413,11 +416,37 @@ struct Stats {
   double sx[MAX_NX];
 };
 
-// Reduce the per-thread online accumulators to one block partial, publish it, meet the grid, and
-// combine all block partials in a fixed order (every block computes bitwise-identical Stats).
+// Layout of the synchronisation words behind EngineP::bar (zeroed by the host before every launch):
+//   bar[0]            grid-barrier arrival counter
+//   bar[32]           reduction arrival counter (its own 128-byte line)
+//   bar[64 .. 191]    64 tagged 8-byte words: the finished statistics of a reduction, [2 parities][32 words]
+constexpr int BAR_RED_CNT = 32;
+constexpr int BAR_RES_WORDS = 64;      // offset in unsigned units
+constexpr int BAR_TOTAL_WORDS = 192;   // unsigned units the host must allocate and zero
+
+__device__ __forceinline__ unsigned atom_add_acq_rel_u32(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(u64* p, u64 v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Reduce the per-thread online accumulators to one block partial and publish it; the LAST block to
+// arrive (atomic counter) combines all block partials in a fixed order — on sharded filters it also
+// performs the per-step exchange with the peer GPUs — and publishes the finished statistics as tagged
+// 8-byte words (4 B payload + 4 B sequence number, NCCL-LL style: a word is valid exactly when its tag
+// matches, so one L2 round trip delivers the data and no flag/fence pair is needed).  Every other block
+// polls those words.  All blocks end up with bitwise-identical Stats, run-to-run deterministic (the
+// combine order is fixed; which block happens to run it does not matter).
+// Replaces (v6) "grid barrier + every block re-reads all partials": one atomic + one polled line per block.
 template <int NX>
 __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Online<NX>& acc,
-                                              bool with_x, unsigned& bar_target, u64& xseq) {
+                                              bool with_x, unsigned& red_seq, u64& xseq) {
+  constexpr int NV = 3 + NX;          // m, s, q, sx[NX]
+  constexpr int NW = 2 * NV;          // tagged words
+  static_assert(NW <= 32, "statistics do not fit the result line");
   const double mb = block_max(acc.m, sh);
   const double sc = exp_nonpos(acc.m - mb, sh.mt);  // 0 for empty threads
   double v[2 + NX];
@@ -427,6 +456,10 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
   for (int d = 0; d < NX; ++d) v[2 + d] = with_x ? acc.sx[d] * sc : 0.0;
   block_sum<2 + NX>(v, sh);
   LLPF_TS(P, sh, 6);
+  red_seq += 1;
+  const unsigned seq = red_seq;
+  if (P.world > 1) xseq += 1;
+  u64* res = reinterpret_cast<u64*>(P.bar + BAR_RES_WORDS) + (size_t)(seq & 1u) * 32;
   if (threadIdx.x == 0) {   // partial = {m, s, q, sx[NX]} as 16-byte pairs
     double2* p = reinterpret_cast<double2*>(P.partials + (size_t)blockIdx.x * PS);
     double pk[2 * ((3 + NX + 1) / 2)];
@@ -436,61 +469,112 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
     if ((3 + NX) & 1) pk[3 + NX] = 0.0;
 #pragma unroll
     for (int k = 0; k < (3 + NX + 1) / 2; ++k) __stcg(p + k, make_double2(pk[2 * k], pk[2 * k + 1]));
+    // release: my partial is visible before the count; acquire: if I am last, everyone's partial is visible to me
+    const unsigned prev = atom_add_acq_rel_u32(P.bar + BAR_RED_CNT, 1u);
+    sh.is_last = (prev + 1u == seq * (unsigned)P.nblocks) ? 1 : 0;
   }
-  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  __syncthreads();
   LLPF_TS(P, sh, 7);
-  // combine: the barrier's acquire invalidated L1, so these (L1-allocating) loads are fresh and the
-  // second sweep over the same lines hits L1
-  double m = -DBL_MAX;
-  for (int b = threadIdx.x; b < P.nblocks; b += BLOCK)
-    m = fmax(m, __ldca(reinterpret_cast<const double2*>(P.partials + (size_t)b * PS)).x);
-  m = block_max(m, sh);
-  double t[2 + NX];
-#pragma unroll
-  for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
-  for (int b = threadIdx.x; b < P.nblocks; b += BLOCK) {
-    const double2* p = reinterpret_cast<const double2*>(P.partials + (size_t)b * PS);
-    double pk[2 * ((3 + NX + 1) / 2)];
-#pragma unroll
-    for (int k = 0; k < (3 + NX + 1) / 2; ++k) {
-      const double2 q2 = (with_x || k < 2) ? __ldca(p + k) : make_double2(0.0, 0.0);
-      pk[2 * k] = q2.x; pk[2 * k + 1] = q2.y;
-    }
-    const double e = exp_nonpos(pk[0] - m, sh.mt);
-    t[0] = fma(pk[1], e, t[0]);
-    t[1] = fma(pk[2], e * e, t[1]);
-    if (with_x) {
-#pragma unroll
-      for (int d = 0; d < NX; ++d) t[2 + d] = fma(pk[3 + d], e, t[2 + d]);
-    }
-  }
-  block_sum<2 + NX>(t, sh);
-  LLPF_TS(P, sh, 9);
-  if (P.world > 1) {
-    // one all-gather of (m, s, q, sx) per rank over NVLink; combined in rank order on every rank
-    double mine[3 + NX], all[MAX_WORLD][3 + NX];
-    mine[0] = m;
-#pragma unroll
-    for (int k = 0; k < 2 + NX; ++k) mine[1 + k] = t[k];
-    peer_allgather<3 + NX>(P, xseq, mine, all);
-    double gm = all[0][0];
-    for (int r = 1; r < P.world; ++r) gm = fmax(gm, all[r][0]);
+  if (sh.is_last) {
+    // combine: thread 0's acquire invalidated L1, so these (L1-allocating) loads are fresh and the second
+    // sweep over the same lines hits L1.  No block overwrites its partial before it has seen the result.
+    double m = -DBL_MAX;
+    for (int b = threadIdx.x; b < P.nblocks; b += BLOCK)
+      m = fmax(m, __ldca(reinterpret_cast<const double2*>(P.partials + (size_t)b * PS)).x);
+    m = block_max(m, sh);
+    double t[2 + NX];
 #pragma unroll
     for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
-    for (int r = 0; r < P.world; ++r) {
-      const double e = exp_nonpos(all[r][0] - gm, sh.mt);
-      t[0] = fma(all[r][1], e, t[0]);
-      t[1] = fma(all[r][2], e * e, t[1]);
+    for (int b = threadIdx.x; b < P.nblocks; b += BLOCK) {
+      const double2* p = reinterpret_cast<const double2*>(P.partials + (size_t)b * PS);
+      double pk[2 * ((3 + NX + 1) / 2)];
 #pragma unroll
-      for (int d = 0; d < NX; ++d) t[2 + d] = fma(all[r][3 + d], e, t[2 + d]);
+      for (int k = 0; k < (3 + NX + 1) / 2; ++k) {
+        const double2 q2 = (with_x || k < 2) ? __ldca(p + k) : make_double2(0.0, 0.0);
+        pk[2 * k] = q2.x; pk[2 * k + 1] = q2.y;
+      }
+      const double e = exp_nonpos(pk[0] - m, sh.mt);
+      t[0] = fma(pk[1], e, t[0]);
+      t[1] = fma(pk[2], e * e, t[1]);
+      if (with_x) {
+#pragma unroll
+        for (int d = 0; d < NX; ++d) t[2 + d] = fma(pk[3 + d], e, t[2 + d]);
+      }
     }
-    m = gm;
+    block_sum<2 + NX>(t, sh);
+    LLPF_TS(P, sh, 9);
+    if (P.world > 1) {
+      // one all-gather of (m, s, q, sx) per rank over NVLink (tagged words written straight into every peer's
+      // mailbox, thread r talks to rank r); combined in rank order on every rank
+      const int par = (int)(xseq & 1ull);
+      const u64 tag = (xseq & 0xffffffffull) << 32;
+      double mine[NV];
+      mine[0] = m;
+#pragma unroll
+      for (int k = 0; k < 2 + NX; ++k) mine[1 + k] = t[k];
+      if (threadIdx.x < P.world) {
+        const int r = threadIdx.x;
+        if (r != P.rank) {
+          u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            const u64 bits = (u64)__double_as_longlong(mine[k]);
+            st_relaxed_sys_u64(out + 2 * k, tag | (bits & 0xffffffffull));
+            st_relaxed_sys_u64(out + 2 * k + 1, tag | (bits >> 32));
+          }
+          const u64* in = reinterpret_cast<const u64*>(P.peer_mbox[P.rank]) + ((size_t)par * MAX_WORLD + r) * MBOX_WORDS;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            u64 lo, hi;
+            do { lo = ld_relaxed_sys_u64(in + 2 * k); } while ((lo & 0xffffffff00000000ull) != tag);
+            do { hi = ld_relaxed_sys_u64(in + 2 * k + 1); } while ((hi & 0xffffffff00000000ull) != tag);
+            sh.peer_vals[r * (3 + MAX_NX) + k] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) sh.peer_vals[r * (3 + MAX_NX) + k] = mine[k];
+        }
+      }
+      __syncthreads();
+      double gm = sh.peer_vals[0];
+      for (int r = 1; r < P.world; ++r) gm = fmax(gm, sh.peer_vals[r * (3 + MAX_NX)]);
+#pragma unroll
+      for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
+      for (int r = 0; r < P.world; ++r) {
+        const double* pv = sh.peer_vals + r * (3 + MAX_NX);
+        const double e = exp_nonpos(pv[0] - gm, sh.mt);
+        t[0] = fma(pv[1], e, t[0]);
+        t[1] = fma(pv[2], e * e, t[1]);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) t[2 + d] = fma(pv[3 + d], e, t[2 + d]);
+      }
+      m = gm;
+    }
+    if (threadIdx.x < NW) {   // publish: word 2k = low half of value k, word 2k+1 = high half
+      double val = m;
+#pragma unroll
+      for (int k = 0; k < 2 + NX; ++k)
+        if ((int)(threadIdx.x >> 1) == 1 + k) val = t[k];
+      const u64 bits = (u64)__double_as_longlong(val);
+      const uint32_t half = (threadIdx.x & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+      sh.stat_words[threadIdx.x] = half;
+      st_relaxed_gpu_u64(res + threadIdx.x, ((u64)seq << 32) | half);
+    }
+  } else if (threadIdx.x < NW) {
+    u64 wv;
+    do { wv = ld_relaxed_gpu_u64(res + threadIdx.x); } while ((uint32_t)(wv >> 32) != seq);
+    sh.stat_words[threadIdx.x] = (uint32_t)wv;
   }
+  __syncthreads();
   LLPF_TS(P, sh, 8);
   Stats st;
-  st.m = m; st.s = t[0]; st.q = t[1];
+  double out[NV];
 #pragma unroll
-  for (int d = 0; d < NX; ++d) st.sx[d] = t[2 + d];
+  for (int k = 0; k < NV; ++k)
+    out[k] = __hiloint2double((int)sh.stat_words[2 * k + 1], (int)sh.stat_words[2 * k]);
+  st.m = out[0]; st.s = out[1]; st.q = out[2];
+#pragma unroll
+  for (int d = 0; d < NX; ++d) st.sx[d] = out[3 + d];
   return st;
 }
 
@@ -1100,11 +1184,17 @@ __device__ __forceinline__ void model_to_shared(const ModelP<NX, NY>& M, Shared&
 // ------------------------------------------------------------------------------------------------
 // per-pass helpers
 // ------------------------------------------------------------------------------------------------
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
+
 struct Ctx {
   int beg, end;        // own chunk (local indices)
   double lwN;          // -log(N)  (filtering.jl:11)
   double lw1N;         // log(1/N) (utils.jl:75)
   unsigned bar_target;
+  unsigned red_seq;    // number of reductions done in this launch (tag of the published statistics)
 };
 
 // by-value snapshot of the lazy weight state
@@ -1296,73 +1386,91 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   const int jid = sc.j_identity;
   Online<NX> acc;
   acc.init();
+  // The sweep is instantiated three times: MODE 1 / MODE 2 are the steady-state passes of a trajectory
+  // (predict!(k) fused with correct!(k+1), no history, no missing measurement, no running mean) without /
+  // with resampling, in which every loop-invariant condition is a compile-time constant; MODE 0 is the
+  // general loop (first/last pass, step verbs, history, NaN measurements, xhat).
   // software pipeline: the ancestor index of the NEXT iteration is fetched one iteration ahead; within an
   // iteration the particle/weight loads are issued first, the (data-independent) noise is computed while
   // they are in flight, and only then are they consumed.
   // resample path: ancestor index fetched TWO iterations ahead, the gathered particle ONE iteration ahead
   // (it may live in a peer GPU's memory: ~2 us over NVLink)
-  int a_n1 = 0, a_n2 = 0;
-  double xn[NX];
+  auto sweep = [&](auto mode_tag) {
+    constexpr int MODE = decltype(mode_tag)::value;
+    const bool res_ = (MODE == 2) ? true : (MODE == 1) ? false : res;
+    const bool prop_ = (MODE != 0) ? true : (k_prop > 0);
+    const bool weigh_ = (MODE != 0) ? true : (k_weigh > 0);
+    const bool hist_w_ = (MODE != 0) ? false : hist_w;
+    const bool hist_x_ = (MODE != 0) ? false : (P.x_hist != nullptr);
+    const bool skip_ = (MODE != 0) ? false : skip;
+    const bool with_x_ = (MODE != 0) ? false : with_x;
+    int a_n1 = 0, a_n2 = 0;
+    double xn[NX];
 #pragma unroll
-  for (int d = 0; d < NX; ++d) xn[d] = 0.0;
-  if (res) {
-    const int i0 = cx.beg + threadIdx.x;
-    if (i0 < cx.end) {
-      a_n1 = __ldcg(P.j + i0);
-      if (P.first + i0 >= f_total) {
-        if (jid) a_n1 = P.first + i0;
-        __stcg(P.j + i0, a_n1);
-      }
-      gather_x<NX>(P, sc.cur, a_n1, xn);
-    }
-    if (i0 + BLOCK < cx.end) a_n2 = __ldcg(P.j + i0 + BLOCK);
-  }
-  for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
-    const int gi = P.first + i;
-    double x[NX];
-    double wraw = 0.0;
-    if (res) {
-#pragma unroll
-      for (int d = 0; d < NX; ++d) x[d] = xn[d];
-      const int in = i + BLOCK;
-      if (in < cx.end) {
-        int a = a_n2;
-        if (P.first + in >= f_total) {     // untouched entry (resample.jl:26-34): keep state.j
-          if (jid) a = P.first + in;
-          __stcg(P.j + in, a);
+    for (int d = 0; d < NX; ++d) xn[d] = 0.0;
+    if (res_) {
+      const int i0 = cx.beg + threadIdx.x;
+      if (i0 < cx.end) {
+        a_n1 = __ldcg(P.j + i0);
+        if (P.first + i0 >= f_total) {
+          if (jid) a_n1 = P.first + i0;
+          __stcg(P.j + i0, a_n1);
         }
-        gather_x<NX>(P, sc.cur, a, xn);
-        if (in + BLOCK < cx.end) a_n2 = __ldcg(P.j + in + BLOCK);
+        gather_x<NX>(P, sc.cur, a_n1, xn);
       }
-    } else {
-      load_x<NX>(src, P.ld, i, x);
-      if (!ws.uniform) wraw = __ldcg(P.w + i);
+      if (i0 + BLOCK < cx.end) a_n2 = __ldcg(P.j + i0 + BLOCK);
     }
-    double z[NX];
-    if (k_prop > 0) noise_vector<NX, NY>(P.key, step_idx, gi, z, sh);
-    double wv;
-    if (res) {
-      wv = cx.lw1N;                    // reset_weights!  utils.jl:75
-    } else {
-      wv = ws.uniform ? ws.wu : (ws.pend ? (wraw - ws.pm) - ws.pls : wraw);
-      if (hist_w) {
-        __stcs(wh + hbase + i, wv);
-        __stcs(weh + hbase + i, ws.expweight(i));
-      }
-    }
-    if (k_prop > 0) {
-      dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
+    for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
+      const int gi = P.first + i;
+      double x[NX];
+      double wraw = 0.0;
+      if (res_) {
 #pragma unroll
-      for (int d = 0; d < NX; ++d) x[d] += z[d];
-      store_x<NX>(dst, P.ld, i, x);
+        for (int d = 0; d < NX; ++d) x[d] = xn[d];
+        const int in = i + BLOCK;
+        if (in < cx.end) {
+          int a = a_n2;
+          if (P.first + in >= f_total) {     // untouched entry (resample.jl:26-34): keep state.j
+            if (jid) a = P.first + in;
+            __stcg(P.j + in, a);
+          }
+          gather_x<NX>(P, sc.cur, a, xn);
+          if (in + BLOCK < cx.end) a_n2 = __ldcg(P.j + in + BLOCK);
+        }
+      } else {
+        load_x<NX>(src, P.ld, i, x);
+        if (!ws.uniform) wraw = __ldcg(P.w + i);
+      }
+      double z[NX];
+      if (prop_) noise_vector<NX, NY>(P.key, step_idx, gi, z, sh);
+      double wv;
+      if (res_) {
+        wv = cx.lw1N;                    // reset_weights!  utils.jl:75
+      } else {
+        wv = ws.uniform ? ws.wu : (ws.pend ? (wraw - ws.pm) - ws.pls : wraw);
+        if (hist_w_) {
+          __stcs(wh + hbase + i, wv);
+          __stcs(weh + hbase + i, ws.expweight(i));
+        }
+      }
+      if (prop_) {
+        dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
+#pragma unroll
+        for (int d = 0; d < NX; ++d) x[d] += z[d];
+        store_x<NX>(dst, P.ld, i, x);
+      }
+      if (weigh_) {
+        if (hist_x_) store_hist_x<NX>(P, k_weigh, gi, x);
+        if (!skip_) wv += meas_loglik<NX, NY>(M, sh, yt, x);
+        __stcg(P.w + i, wv);
+        acc.add(wv, x, with_x_, sh.mt);
+      }
     }
-    if (k_weigh > 0) {
-      if (P.x_hist) store_hist_x<NX>(P, k_weigh, gi, x);
-      if (!skip) wv += meas_loglik<NX, NY>(M, sh, yt, x);
-      __stcg(P.w + i, wv);
-      acc.add(wv, x, with_x, sh.mt);
-    }
-  }
+  };
+  const bool steady = (k_prop > 0) && (k_weigh > 0) && !hist_w && (P.x_hist == nullptr) && !skip && !with_x;
+  if (steady && res) sweep(IntTag<2>{});
+  else if (steady) sweep(IntTag<1>{});
+  else sweep(IntTag<0>{});
   LLPF_TS(P, sh, 5);
   if (k_prop > 0) {
     if (res) {
@@ -1379,7 +1487,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
     sc.t_index += 1;       // filtering.jl:152
   }
   if (k_weigh > 0) {
-    const Stats st = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target, sc.xseq);
+    const Stats st = reduce_stats<NX>(P, sh, acc, with_x, cx.red_seq, sc.xseq);
     publish_step<NX>(P, sc, k_weigh, st);
   }
 }
@@ -1420,7 +1528,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
     __stcg(P.w + i, v);
     acc.add(v, x, false, sh.mt);
   }
-  const Stats s1 = reduce_stats<NX>(P, sh, acc, false, cx.bar_target, sc.xseq);
+  const Stats s1 = reduce_stats<NX>(P, sh, acc, false, cx.red_seq, sc.xseq);
   const double inv1 = 1.0 / s1.s;
   const double m1 = s1.m;
   const double* wraw = P.w;
@@ -1469,7 +1577,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   sc.last_resampled = 1;
   if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k - 1] = 1;
   sc.t_index += 1;                                               // :215
-  const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, cx.bar_target, sc.xseq);
+  const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, cx.red_seq, sc.xseq);
   // stats of the raw w[] are ready; correct! (filtering.jl:170-174) has not been *called* yet
   sc.pend = 0; sc.uniform = 0;
   sc.stats_ahead = 1; sc.stats_valid = 0;
@@ -1518,6 +1626,7 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
   Scalars sc = *P.sc;   // every block carries an identical copy in registers; block 0 writes it back
   Ctx cx;
   cx.bar_target = 0;
+  cx.red_seq = 0;
   {
     long long b = (long long)blockIdx.x * P.chunk;
     long long e = b + P.chunk;
