@@ -800,15 +800,17 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
   long long* d_dbg = nullptr;
   const char* dump = std::getenv("LLPF_PHASE_DUMP");
   if (dump) {
-    CU(cudaMalloc(&d_dbg, sizeof(long long) * 16 * (T + 2)));
-    CU(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * 16 * (T + 2), f->stream));
+    const size_t dbg_words = (size_t)(16 + 4 * MAX_BLOCKS) * (T + 2);   // block 0's phases + per-block (pass start, sweep end, stats seen, indices done)
+    CU(cudaMalloc(&d_dbg, sizeof(long long) * dbg_words));
+    CU(cudaMemsetAsync(d_dbg, 0, sizeof(long long) * dbg_words, f->stream));
     P.dbg = d_dbg;
+    P.dbg_T = (int)T;
   }
 #endif
   int rc = launch(f, P, true);
 #ifdef LLPF_PHASE_TIMING
   if (dump && rc == LLPF_OK) {
-    std::vector<long long> hb((size_t)16 * (T + 2));
+    std::vector<long long> hb((size_t)(16 + 4 * MAX_BLOCKS) * (T + 2));
     cudaMemcpy(hb.data(), d_dbg, sizeof(long long) * hb.size(), cudaMemcpyDeviceToHost);
     FILE* fp = std::fopen(dump, "wb");
     if (fp) { std::fwrite(hb.data(), sizeof(long long), hb.size(), fp); std::fclose(fp); }

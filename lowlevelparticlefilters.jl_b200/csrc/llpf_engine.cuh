@@ -128,6 +128,7 @@ struct EngineP {
   int rank, world;
   RngKey key;
   double fix_scale, fix_inv;  // fixed-point scan scale: 2^62 / 2^-62 for normalised weights
+  int dbg_T;                  // number of time steps of the run (layout of dbg)
   long long* dbg;             // optional phase timestamps [pass][16] (block 0, thread 0; -DLLPF_PHASE_TIMING)
   // ---- sharded filters (world > 1): IPC-mapped views of every rank's arrays, index = rank ----
   double* peer_x[MAX_WORLD][2];   // particle buffers (gather source on resample steps)
@@ -144,8 +145,19 @@ constexpr int MBOX_WORDS = 32;    // mailbox slot: 2 tagged 8-byte words per pay
   do {                                                                                 \
     if ((P).dbg && blockIdx.x == 0 && threadIdx.x == 0) (P).dbg[(size_t)(sh).pass_id * 16 + (k)] = clock64(); \
   } while (0)
+// every block: wall-clock (globaltimer, ns) of event k in {0,1,2,3} of the current pass; the per-block table
+// follows block 0's [pass][16] table: [pass][MAX_BLOCKS][4]  (scripts/skew.py)
+#define LLPF_TSB(P, sh, T_, k)                                                                       \
+  do {                                                                                              \
+    if ((P).dbg && threadIdx.x == 0) {                                                              \
+      unsigned long long gt_;                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                       \
+      (P).dbg[(size_t)16 * ((T_) + 2) + ((size_t)(sh).pass_id * MAX_BLOCKS + blockIdx.x) * 4 + (k)] = (long long)gt_; \
+    }                                                                                               \
+  } while (0)
 #else
 #define LLPF_TS(P, sh, k) do { } while (0)
+#define LLPF_TSB(P, sh, T_, k) do { } while (0)
 #endif
 
 template <int NX, int NY>
@@ -1353,6 +1365,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
 #endif
   stage_step<NX, NY, DYN>(P, M, sh, k_prop, skip_meas ? 0 : k_weigh, bu, yt, nan_y);
   LLPF_TS(P, sh, 0);
+  LLPF_TSB(P, sh, P.dbg_T, 0);
   const bool skip = skip_meas || nan_y;
   // shouldresample(pf)  resample.jl:5-10
   const bool res = (k_prop > 0) && ((P.thr == 1.0) || (sc.ess < (double)P.N * P.thr));
@@ -1378,6 +1391,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
         },
         0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq);
     sc.bins_total = total;
+    LLPF_TSB(P, sh, P.dbg_T, 3);
   }
   const double* src = P.x[sc.cur];
   double* dst = res ? P.x[sc.cur ^ 1] : P.x[sc.cur];
@@ -1472,6 +1486,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   else if (steady) sweep(IntTag<1>{});
   else sweep(IntTag<0>{});
   LLPF_TS(P, sh, 5);
+  LLPF_TSB(P, sh, P.dbg_T, 1);
   if (k_prop > 0) {
     if (res) {
       sc.cur ^= 1;
@@ -1488,6 +1503,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   }
   if (k_weigh > 0) {
     const Stats st = reduce_stats<NX>(P, sh, acc, with_x, cx.red_seq, sc.xseq);
+    LLPF_TSB(P, sh, P.dbg_T, 2);
     publish_step<NX>(P, sc, k_weigh, st);
   }
 }
@@ -1635,6 +1651,13 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
     cx.beg = (int)b; cx.end = (int)e;
     asm volatile("" : "+r"(cx.beg), "+r"(cx.end));   // keep the bounds in registers (no per-iteration re-derivation)
   }
+#ifdef LLPF_PHASE_TIMING
+  if (P.dbg && threadIdx.x == 0) {   // which SM runs this block (row of pass 0, slot 3)
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    P.dbg[(size_t)16 * (P.dbg_T + 2) + (size_t)blockIdx.x * 4 + 3] = (long long)smid;
+  }
+#endif
   cx.lwN = -log((double)P.N);
   cx.lw1N = log(1.0 / (double)P.N);
   for (int r = 0; r < P.nops; ++r) {
