@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LLPF_VERSION 100
+#define LLPF_VERSION 101
 
 /* ---- status codes -------------------------------------------------------------------- */
 enum {
@@ -65,6 +65,15 @@ enum {
                            sums are exactly representable, e.g. dyadic weights)              */
   LLPF_SCAN_SERIAL = 1  /* strict left-to-right f64 adds, the reference's order: bit-exact
                            `bins` and therefore bit-exact indices; verification mode (slow)  */
+};
+
+/* ---- particle element type (the eltype of `initial_density`, PFtypes.jl:66,202) ---------- */
+enum {
+  LLPF_PARTICLE_F64 = 0,  /* Vector{SVector{nx,Float64}}: nx <= 8, SoA in HBM, all filter kinds            */
+  LLPF_PARTICLE_F32 = 1   /* Vector{SVector{nx,Float32}}: nx, ny <= 64, linear-Gaussian, ParticleFilter /
+                             AdvancedParticleFilter (test/test_large.jl regime).  Weights, bins and the
+                             log-likelihood stay Float64 like the reference (PFtypes.jl:68-69); the C-ABI
+                             still exchanges particles as doubles                                          */
 };
 
 /* ---- dynamics descriptors --------------------------------------------------------------- */
@@ -127,6 +136,8 @@ typedef struct llpf_config {
      indices [rank*N/world, (rank+1)*N/world). world==1 for a single-GPU filter.         */
   int32_t rank;
   int32_t world;
+  int32_t particle_dtype;     /* LLPF_PARTICLE_*                                        */
+  int32_t _reserved;          /* must be 0                                              */
 } llpf_config;
 
 /* Optional outputs of llpf_run. Any pointer may be NULL. Host memory. */

@@ -22,6 +22,7 @@ struct LLPFConfig
     N::Int64; filter::Int32; resampling::Int32
     resample_threshold::Float64; Ts::Float64; seed::UInt64
     scan_mode::Int32; device::Int32; rank::Int32; world::Int32
+    particle_dtype::Int32; _reserved::Int32      # 0 = Float64 particles, 1 = Float32 (nx, ny <= 64, linear-Gaussian)
 end
 struct LLPFRunOutputs
     ll_steps::Ptr{Float64}; ess_steps::Ptr{Float64}; resampled::Ptr{Int32}; xhat::Ptr{Float64}
@@ -63,9 +64,10 @@ end
 
 "ParticleFilter(N, ...)  src/PFtypes.jl:65-75 (kind=0) / AdvancedParticleFilter :200-210 (kind=1) / AuxiliaryParticleFilter :38-49 (kind=2)"
 function GPUParticleFilter(N::Integer, m; kind=0, resample_threshold=(kind == 1 ? 0.5 : 0.1), Ts=1.0, seed=0,
-                           resampling=0, scan_mode=0, device=0, rank=0, world=1)
+                           resampling=0, scan_mode=0, device=0, rank=0, world=1, particle_eltype=Float64)
     mdl, nx, nu, ny = c_model(m)
-    cfg = LLPFConfig(N, kind, resampling, resample_threshold, Ts, seed, scan_mode, device, rank, world)
+    cfg = LLPFConfig(N, kind, resampling, resample_threshold, Ts, seed, scan_mode, device, rank, world,
+                     particle_eltype === Float32 ? 1 : 0, 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve m check(ccall((:llpf_create, lib), Cint, (Ref{LLPFConfig}, Ref{LLPFModel}, Ref{Ptr{Cvoid}}), cfg, mdl, h))
     pf = GPUParticleFilter(h[], m, Int(N) ÷ world, nx, nu, ny, Float64(Ts), Float64(resample_threshold), Int32(kind), UInt64(0))

@@ -20,6 +20,8 @@ RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_RESIDUAL = range(3)
 SCAN_FAST, SCAN_SERIAL = range(2)
 # dynamics
 DYN_LINEAR, DYN_QUADTANK_RK4 = range(2)
+# particle element type
+PARTICLE_F64, PARTICLE_F32 = range(2)
 # time convention
 TIME_FORWARD_TRAJECTORY, TIME_LOGLIK = range(2)
 
@@ -44,6 +46,7 @@ class Config(C.Structure):
         ("N", C.c_int64), ("filter", C.c_int32), ("resampling", C.c_int32),
         ("resample_threshold", C.c_double), ("Ts", C.c_double), ("seed", C.c_uint64),
         ("scan_mode", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("particle_dtype", C.c_int32), ("_reserved", C.c_int32),
     ]
 
 

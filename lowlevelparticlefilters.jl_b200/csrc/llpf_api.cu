@@ -13,6 +13,7 @@
 
 #include "../../include/llpf.h"
 #include "llpf_engine.cuh"
+#include "llpf_wide.cuh"
 
 using namespace llpf;
 
@@ -76,17 +77,24 @@ static void inv_lower(const std::vector<double>& L, int n, std::vector<double>& 
 
 struct HostModel {
   int nx = 0, nu = 0, ny = 0, dyn = 0;
+  bool wide = false;   // Float32 particles, nx/ny up to 64: the engine of llpf_wide.cuh
   std::vector<double> A, B, C, mu0, L0, L1, L2, W, G;  // column-major
   double c0 = 0;
   double dynp[8] = {0}, t_switch = 0, a1_factor = 1, integ_Ts = 1;
   int supersample = 1;
 };
 
-static int build_host_model(const llpf_model* m, HostModel& H) {
+static int build_host_model(const llpf_model* m, HostModel& H, bool wide) {
   if (!m) return fail(LLPF_ERR_BAD_ARG, "model is null");
   const int nx = m->nx, nu = m->nu, ny = m->ny;
-  if (nx < 1 || nx > MAX_NX || ny < 1 || ny > 8 || nu < 0 || nu > MAX_NU)
-    return fail(LLPF_ERR_UNSUPPORTED, "supported dimensions: 1<=nx<=8, 1<=ny<=8, 0<=nu<=8");
+  H.wide = wide;
+  if (wide) {
+    if (nx < 1 || nx > WNX || ny < 1 || ny > WNX || nu < 0 || nu > MAX_NU)
+      return fail(LLPF_ERR_UNSUPPORTED, "Float32 particles: supported dimensions 1<=nx<=64, 1<=ny<=64, 0<=nu<=8");
+    if (m->dynamics != LLPF_DYN_LINEAR) return fail(LLPF_ERR_UNSUPPORTED, "Float32 particles: linear dynamics only");
+  } else if (nx < 1 || nx > MAX_NX || ny < 1 || ny > 8 || nu < 0 || nu > MAX_NU)
+    return fail(LLPF_ERR_UNSUPPORTED, "supported dimensions: 1<=nx<=8, 1<=ny<=8, 0<=nu<=8 (Float64 particles); "
+                                      "up to 64 states with particle_dtype = LLPF_PARTICLE_F32");
   if (!m->C || !m->R1 || !m->R2 || !m->mu0 || !m->Sigma0) return fail(LLPF_ERR_BAD_ARG, "null model matrix");
   H.nx = nx; H.nu = nu; H.ny = ny; H.dyn = m->dynamics;
   if (m->dynamics == LLPF_DYN_LINEAR) {
@@ -268,8 +276,12 @@ k_resample(const __grid_constant__ EngineP P, const double* we, double u01, cons
   double total;
   u64 xs = 0;
   // 1-based ids; slots >= f_total keep the caller's value (resample.jl:26-34)
+  // heavy runs are filled by a block partition of the M output slots
+  const long long per = ((long long)M + gridDim.x - 1) / gridDim.x;
+  const long long s0 = (long long)blockIdx.x * per, s1 = s0 + per;
   (void)resample_indices<long long>(P, sh, (int)b, (int)e, bar_target, [=](int i) { return __ldg(we + i); },
-                                    [](int, double v) { return v; }, u01, false, 0u, M, u_slots, j_inout, 1ll, total, xs);
+                                    [](int, double v) { return v; }, u01, false, 0u, M, u_slots, j_inout, 1ll, total, xs,
+                                    (int)(s0 < M ? s0 : M), (int)(s1 < M ? s1 : M));
 }
 
 // logsumexp!(w, we)  utils.jl:18-27 on caller-provided arrays
@@ -330,7 +342,7 @@ struct llpf_filter {
   // sharding (one process per GPU): IPC-mapped peer arenas
   int rank = 0, world = 1;
   bool connected = false;
-  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0;
+  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0, o_heavy = 0;
   char* peer_base[MAX_WORLD] = {nullptr};
   // per-run buffers (grow-only)
   double *d_u = nullptr, *d_y = nullptr, *d_ll = nullptr, *d_ess = nullptr, *d_xhat = nullptr;
@@ -345,6 +357,11 @@ struct llpf_filter {
   int max_blocks = 1;
   launch_fn launch = nullptr;
   init_fn init = nullptr;
+  // wide (Float32-particle) engine: device copies of the model in the layouts of WideP
+  bool wide = false;
+  float *w_At = nullptr, *w_Lt = nullptr, *w_G = nullptr, *w_B = nullptr, *w_mu0 = nullptr, *w_L0 = nullptr;
+  double* w_W = nullptr;
+  int w_diagL = 0;
 };
 
 template <int NX, int NY, int DYN>
@@ -374,6 +391,74 @@ static cudaError_t launch_init(llpf_filter* f, uint64_t epoch) {
   RngKey key{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)epoch << 8};
   const int grid = (int)std::min<long long>((f->n + 255) / 256, (long long)f->num_sms * 8);
   k_init<NX><<<grid > 0 ? grid : 1, 256, 0, f->stream>>>(f->x[0], f->ld, f->n, f->first, key, ip);
+  return cudaGetLastError();
+}
+
+// ---- wide engine (llpf_wide.cuh) -----------------------------------------------------------------------
+static int upload_wide_model(llpf_filter* f) {
+  const HostModel& H = f->hm;
+  const int nx = H.nx, ny = H.ny, nu = H.nu;
+  std::vector<float> At((size_t)WNX * WNX, 0.f), Lt((size_t)WNX * WNX, 0.f), G((size_t)WNX * WNX, 0.f),
+      B((size_t)WNX * MAX_NU, 0.f), mu0(WNX, 0.f), L0((size_t)WNX * WNX, 0.f);
+  std::vector<double> W((size_t)ny * ny, 0.0);
+  int diag = 1;
+  for (int r = 0; r < nx; ++r)
+    for (int c = 0; c < nx; ++c) {
+      At[(size_t)c * WNX + r] = (float)CMH(H.A, r, c, nx);
+      if (c <= r) {
+        Lt[(size_t)c * WNX + r] = (float)CMH(H.L1, r, c, nx);
+        L0[(size_t)r * WNX + c] = (float)CMH(H.L0, r, c, nx);
+        if (c < r && CMH(H.L1, r, c, nx) != 0.0) diag = 0;
+      }
+    }
+  for (int a = 0; a < ny; ++a) {
+    for (int c = 0; c < nx; ++c) G[(size_t)a * WNX + c] = (float)CMH(H.G, a, c, ny);
+    for (int c = 0; c <= a; ++c) W[(size_t)a * ny + c] = CMH(H.W, a, c, ny);
+  }
+  for (int r = 0; r < nx; ++r) {
+    mu0[r] = (float)H.mu0[r];
+    for (int c = 0; c < nu; ++c) B[(size_t)r * MAX_NU + c] = (float)CMH(H.B, r, c, nx);
+  }
+  f->w_diagL = diag;
+  auto up = [&](auto*& dptr, const auto& v) -> cudaError_t {
+    typedef typename std::remove_reference<decltype(v)>::type::value_type T;
+    if (!dptr) {
+      cudaError_t e = cudaMalloc((void**)&dptr, sizeof(T) * v.size());
+      if (e != cudaSuccess) return e;
+    }
+    return cudaMemcpy(dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+  };
+  CU(up(f->w_At, At)); CU(up(f->w_Lt, Lt)); CU(up(f->w_G, G)); CU(up(f->w_B, B));
+  CU(up(f->w_mu0, mu0)); CU(up(f->w_L0, L0)); CU(up(f->w_W, W));
+  return LLPF_OK;
+}
+static cudaError_t launch_engine_wide(llpf_filter* f, const EngineP& P) {
+  WideP Mw;
+  std::memset(&Mw, 0, sizeof(Mw));
+  Mw.At = f->w_At; Mw.Lt = f->w_Lt; Mw.G = f->w_G; Mw.B = f->w_B; Mw.W = f->w_W;
+  Mw.c0 = (float)f->hm.c0;
+  Mw.nx = f->hm.nx; Mw.ny = f->hm.ny; Mw.nu = f->hm.nu;
+  Mw.diagL = f->w_diagL;
+  EngineP Pc = P;
+  Pc.want_xhat = 0; Pc.xhat = nullptr;
+  void* args[] = {(void*)&Pc, (void*)&Mw};
+  return cudaLaunchCooperativeKernel((const void*)k_engine_wide, dim3(P.nblocks), dim3(BLOCK), args,
+                                     sizeof(WideShared), f->stream);
+}
+static int occupancy_engine_wide() {
+  if (cudaFuncSetAttribute(k_engine_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideShared)) !=
+      cudaSuccess)
+    return 0;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_wide, BLOCK, sizeof(WideShared)) != cudaSuccess)
+    return 0;
+  return occ;
+}
+static cudaError_t launch_init_wide(llpf_filter* f, uint64_t epoch) {
+  RngKey key{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)epoch << 8};
+  const int grid = (int)std::min<long long>((f->n + 127) / 128, (long long)f->num_sms * 8);
+  k_init_wide<<<grid > 0 ? grid : 1, 128, 0, f->stream>>>(reinterpret_cast<float*>(f->x[0]), f->n, f->first, key,
+                                                           f->w_mu0, f->w_L0, f->hm.nx);
   return cudaGetLastError();
 }
 
@@ -437,6 +522,8 @@ extern "C" int llpf_destroy(llpf_handle h) {
   cudaFree(h->arena);
   cudaFree(h->d_u); cudaFree(h->d_y); cudaFree(h->d_ll); cudaFree(h->d_ess); cudaFree(h->d_xhat);
   cudaFree(h->d_res);
+  cudaFree(h->w_At); cudaFree(h->w_Lt); cudaFree(h->w_G); cudaFree(h->w_B); cudaFree(h->w_mu0); cudaFree(h->w_L0);
+  cudaFree(h->w_W);
   if (h->pin_sc) cudaFreeHost(h->pin_sc);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -448,10 +535,15 @@ extern "C" int llpf_destroy(llpf_handle h) {
 extern "C" int llpf_set_model(llpf_handle h, const llpf_model* model) {
   OKR(check_handle(h));
   HostModel hm;
-  OKR(build_host_model(model, hm));
+  OKR(build_host_model(model, hm, h->wide));
   if (hm.nx != h->hm.nx || hm.ny != h->hm.ny || hm.nu != h->hm.nu || hm.dyn != h->hm.dyn)
     return fail(LLPF_ERR_BAD_ARG, "llpf_set_model cannot change dimensions or dynamics kind");
   h->hm = hm;
+  if (h->wide) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    OKR(upload_wide_model(h));
+  }
   return LLPF_OK;
 }
 
@@ -476,20 +568,31 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   if (ndev < 1) return fail(LLPF_ERR_NO_DEVICE, "no CUDA device; the product path has no CPU fallback");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(LLPF_ERR_BAD_ARG, "bad device ordinal");
 
+  if (cfg->particle_dtype != LLPF_PARTICLE_F64 && cfg->particle_dtype != LLPF_PARTICLE_F32)
+    return fail(LLPF_ERR_BAD_ARG, "unknown particle_dtype");
+  const bool wide = cfg->particle_dtype == LLPF_PARTICLE_F32;
+  if (wide && cfg->filter != LLPF_FILTER_PF && cfg->filter != LLPF_FILTER_ADVANCED)
+    return fail(LLPF_ERR_UNSUPPORTED, "Float32 particles: ParticleFilter / AdvancedParticleFilter only");
   llpf_filter* f = new llpf_filter();
   f->cfg = *cfg;
   f->cfg.world = world;
-  int rc = build_host_model(model, f->hm);
+  f->wide = wide;
+  int rc = build_host_model(model, f->hm, wide);
   if (rc) { delete f; return rc; }
   const Dispatch* d = nullptr;
-  for (const Dispatch& e : g_dispatch)
-    if (e.nx == f->hm.nx && e.ny == f->hm.ny && e.dyn == f->hm.dyn) d = &e;
-  if (!d) {
-    delete f;
-    return fail(LLPF_ERR_UNSUPPORTED, "no kernel instantiated for this (nx, ny, dynamics)");
+  if (!wide) {
+    for (const Dispatch& e : g_dispatch)
+      if (e.nx == f->hm.nx && e.ny == f->hm.ny && e.dyn == f->hm.dyn) d = &e;
+    if (!d) {
+      delete f;
+      return fail(LLPF_ERR_UNSUPPORTED, "no kernel instantiated for this (nx, ny, dynamics)");
+    }
+    f->launch = d->launch;
+    f->init = d->init;
+  } else {
+    f->launch = launch_engine_wide;
+    f->init = launch_init_wide;
   }
-  f->launch = d->launch;
-  f->init = d->init;
   f->device = cfg->device;
 #define CUF(expr)                                                                       \
   do {                                                                                  \
@@ -507,7 +610,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
     llpf_destroy(f);
     return fail(LLPF_ERR_UNSUPPORTED, "device lacks cooperative launch");
   }
-  const int occ = d->occ();
+  const int occ = wide ? occupancy_engine_wide() : d->occ();
   if (occ < 1) {
     llpf_destroy(f);
     return fail(LLPF_ERR_CUDA, "engine kernel does not fit on an SM (is this an sm_100a device?)");
@@ -527,17 +630,20 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const int nx = f->hm.nx;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  const size_t o_x0 = take((size_t)nx * f->ld * 8), o_x1 = take((size_t)nx * f->ld * 8);
+  // particles: SoA f64 [nx][ld], or (wide) AoS f32 [n][64]
+  const size_t xbytes = wide ? (size_t)WNX * f->ld * 4 : (size_t)nx * f->ld * 8;
+  const size_t o_x0 = take(xbytes), o_x1 = take(xbytes);
   const size_t o_w = take((size_t)f->ld * 8), o_lam = take((size_t)f->ld * 8), o_bins = take((size_t)f->ld * 8);
   const size_t o_j = take((size_t)f->ld * 4);
   const size_t o_loc = take((size_t)f->ld * 8);
   const size_t o_part = take((size_t)MAX_BLOCKS * PS * 8), o_tots = take((size_t)MAX_BLOCKS * 8);
   const size_t o_bar = take((size_t)BAR_TOTAL_WORDS * 4), o_sc = take(sizeof(Scalars));
-  const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + MAX_NX) * 8);
+  const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + WNX) * 8);
   const size_t o_scr = take((size_t)(nx + 2) * f->ld * 8);
   const size_t o_mbox = take((size_t)2 * MAX_WORLD * MBOX_WORDS * 8);
   const size_t o_bcast = take((size_t)2 * MAX_WORLD * MBOX_DOUBLES * 8), o_bflag = take(64);
-  f->o_x0 = o_x0; f->o_x1 = o_x1; f->o_j = o_j; f->o_mbox = o_mbox;
+  const size_t o_heavy = take((size_t)(1 + 3 * HEAVY_MAX) * 4);
+  f->o_x0 = o_x0; f->o_x1 = o_x1; f->o_j = o_j; f->o_mbox = o_mbox; f->o_heavy = o_heavy;
   f->arena_bytes = off;
   CUF(cudaMalloc(&f->arena, f->arena_bytes));
   CUF(cudaMemsetAsync(f->arena, 0, f->arena_bytes, f->stream));
@@ -553,6 +659,10 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   f->bcast = (double*)(f->arena + o_bcast); f->bcast_flag = (u64*)(f->arena + o_bflag);
   f->peer_base[f->rank] = f->arena;
 #undef CUF
+  if (wide) {
+    rc = upload_wide_model(f);
+    if (rc) { llpf_destroy(f); return rc; }
+  }
   rc = llpf_reset(f, 0);
   if (rc) { llpf_destroy(f); return rc; }
   f->hsc.t_index = 0;  // PFstate(...,Ref(0)) PFtypes.jl:70 ; reset! sets 1
@@ -605,12 +715,14 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.rank = f->rank; P.world = f->world;
   P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
   P.bcast = f->bcast; P.bcast_flag = f->bcast_flag;
+  P.heavy = (int*)(f->arena + f->o_heavy);
   for (int r = 0; r < f->world; ++r) {
     char* base = f->peer_base[r];
     P.peer_x[r][0] = base ? (double*)(base + f->o_x0) : nullptr;
     P.peer_x[r][1] = base ? (double*)(base + f->o_x1) : nullptr;
     P.peer_j[r] = base ? (int*)(base + f->o_j) : nullptr;
     P.peer_mbox[r] = base ? (double*)(base + f->o_mbox) : nullptr;
+    P.peer_heavy[r] = base ? (int*)(base + f->o_heavy) : nullptr;
   }
 }
 
@@ -750,6 +862,9 @@ static int ensure_run_buffers(llpf_filter* f, long long T) {
 static int run_impl(llpf_filter* f, long long T, const double* u_dev, const double* y_dev,
                     int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out) {
   if (T < 1 || T > (1ll << 30)) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  if (f->wide && out && (out->xhat || out->x_hist || out->w_hist || out->we_hist))
+    return fail(LLPF_ERR_UNSUPPORTED, "Float32-particle filters: per-step xhat and the x/w/we history are not recorded "
+                                      "in the fused loop (use the step verbs + accessors)");
   OKR(llpf_reset(f, epoch));
   EngineP P;
   base_params(f, P);
@@ -890,7 +1005,11 @@ extern "C" int llpf_get_particles(llpf_handle h, double* x) {
   OKR(check_handle(h));
   if (!x) return fail(LLPF_ERR_BAD_ARG, "null");
   CU(cudaSetDevice(h->device));
-  k_export_x<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->scratch);
+  if (h->wide)
+    k_export_x_wide<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->x[h->hsc.cur]),
+                                                                       h->n, h->hm.nx, h->scratch);
+  else
+    k_export_x<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->scratch);
   CU(cudaGetLastError());
   h->launches += 1;
   CU(cudaMemcpyAsync(x, h->scratch, sizeof(double) * h->n * h->hm.nx, cudaMemcpyDeviceToHost, h->stream));
@@ -947,7 +1066,11 @@ extern "C" int llpf_set_state(llpf_handle h, const double* x, const double* w, i
   if (!x || !w) return fail(LLPF_ERR_BAD_ARG, "null");
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(h->scratch, x, sizeof(double) * h->n * h->hm.nx, cudaMemcpyHostToDevice, h->stream));
-  k_import_x<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->scratch);
+  if (h->wide)
+    k_import_x_wide<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(reinterpret_cast<float*>(h->x[h->hsc.cur]), h->n,
+                                                                       h->hm.nx, h->scratch);
+  else
+    k_import_x<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->scratch);
   CU(cudaGetLastError());
   h->launches += 1;
   CU(cudaMemcpyAsync(h->w, w, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
@@ -962,15 +1085,20 @@ static int weight_stats(llpf_filter* h, double* s, double* q, double* sx) {
   double* dwe = h->scratch + h->ld;
   k_materialise<<<grid_for(h->n, h->num_sms), 256, 0, h->stream>>>(h->w, h->sc, h->n, h->N, nullptr, dwe);
   const int grid = std::min(grid_for(h->n, h->num_sms), 256);
-  k_wstats<<<grid, 256, 0, h->stream>>>(dwe, h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->wstat);
+  const int PW = h->wide ? 2 + WNX : 2 + MAX_NX;
+  if (h->wide)
+    k_wstats_wide<<<grid, 256, 0, h->stream>>>(dwe, reinterpret_cast<const float*>(h->x[h->hsc.cur]), h->n, h->hm.nx,
+                                               h->wstat);
+  else
+    k_wstats<<<grid, 256, 0, h->stream>>>(dwe, h->x[h->hsc.cur], h->ld, h->n, h->hm.nx, h->wstat);
   CU(cudaGetLastError());
   h->launches += 2;
-  std::vector<double> part((size_t)grid * (2 + MAX_NX));
+  std::vector<double> part((size_t)grid * PW);
   CU(cudaMemcpyAsync(part.data(), h->wstat, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  double acc[2 + MAX_NX] = {0};
+  double acc[2 + WNX] = {0};
   for (int b = 0; b < grid; ++b)
-    for (int k = 0; k < 2 + MAX_NX; ++k) acc[k] += part[(size_t)b * (2 + MAX_NX) + k];
+    for (int k = 0; k < PW; ++k) acc[k] += part[(size_t)b * PW + k];
   if (s) *s = acc[0];
   if (q) *q = acc[1];
   if (sx) for (int d = 0; d < h->hm.nx; ++d) sx[d] = acc[2 + d];
@@ -1067,6 +1195,10 @@ static int resample_standalone(int strategy, int64_t N, const double* we, double
   if (e < 0) e = 0;
   P.fix_scale = std::ldexp(1.0, 62 - e);
   P.fix_inv = std::ldexp(1.0, e - 62);
+  int* d_heavy = nullptr;
+  CU(sp.alloc(&d_heavy, (size_t)(1 + 3 * HEAVY_MAX)));
+  CU(cudaMemset(d_heavy, 0, sizeof(int)));
+  P.heavy = d_heavy;
   P.bins = d_bins; P.partials = d_part; P.tots = d_tots; P.bar = d_bar; P.loc = d_loc;
   P.N = N; P.n = (int)N; P.first = 0; P.strategy = strategy; P.scan_mode = scan_mode;
   P.world = 1;

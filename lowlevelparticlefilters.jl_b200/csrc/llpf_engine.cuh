@@ -52,6 +52,8 @@ constexpr int MAX_NX = 8;
 constexpr int MAX_WORLD = 8;
 constexpr int PS = 12;  // doubles per block partial: m, s, q, sx[8], pad
 constexpr int MAX_OPS = 8;
+constexpr int HEAVY_T = 1024;    // offspring runs longer than this go through the grid-wide heavy-run list
+constexpr int HEAVY_MAX = 2048;  // capacity of that list (entries of 3 ints); beyond it runs are written directly
 constexpr int MAX_ROWS = 128;   // rows (of BLOCK particles) per block handled by the 2-barrier scan
 constexpr double FIX_SCALE = 4611686018427387904.0;        // 2^62
 constexpr double FIX_INV = 2.168404344971008868e-19;       // 2^-62
@@ -136,6 +138,9 @@ struct EngineP {
   double* peer_mbox[MAX_WORLD];   // mailboxes: [2 parities][MAX_WORLD senders][MBOX_WORDS] tagged words
   double* bcast;                  // local re-broadcast of a finished exchange: [2][MAX_WORLD][MBOX_DOUBLES]
   u64* bcast_flag;                // [2]
+  // heavy offspring runs of the current resample: [0] = count, then (first slot, length, id) triples
+  int* heavy;
+  int* peer_heavy[MAX_WORLD];
 };
 constexpr int MBOX_DOUBLES = 16;  // broadcast-buffer stride per rank ([1..] payload)
 constexpr int MBOX_WORDS = 32;    // mailbox slot: 2 tagged 8-byte words per payload double
@@ -820,6 +825,7 @@ struct SlotRouter {
   int n;                // slots per rank
   int world;
   int rank;
+  int* heavy;           // grid-wide list for very long runs (nullptr: write everything directly)
   mutable int remote;   // set once this thread has stored into another rank's array
   __device__ __forceinline__ T* at(int slot) const {
     if (world <= 1) return j + slot;
@@ -834,6 +840,19 @@ struct SlotRouter {
 template <class T>
 __device__ __forceinline__ void scatter_runs(const SlotRouter<T>& R, int lo, int cnt, T id) {
   const int lane = threadIdx.x & 31;
+  // A particle that owns thousands of output slots (degenerate weights: the normal state of a high-dimensional
+  // filter) would serialise the whole resample on one warp.  Such runs are queued instead; after the barrier
+  // that closes the scatter every block fills the part of each queued run that falls into its own slots.
+  if (R.heavy != nullptr && cnt > HEAVY_T) {
+    const int idx = atomicAdd(R.heavy, 1);
+    if (idx < HEAVY_MAX) {
+      __stcg(R.heavy + 1 + 3 * idx, lo);
+      __stcg(R.heavy + 2 + 3 * idx, cnt);
+      __stcg(R.heavy + 3 + 3 * idx, (int)id);
+      if (R.world > 1) R.remote = 1;   // peers read this list: make it visible system-wide before the barrier
+      cnt = 0;
+    }
+  }
   if (cnt <= 4) {
     if (cnt > 0) __stcg(R.at(lo), id);
     if (cnt > 1) __stcg(R.at(lo + 1), id);
@@ -958,6 +977,25 @@ __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int 
   }
 }
 
+// After the barrier(s) that close the scatter: fill the queued heavy runs into the slots [slot_lo, slot_hi) this
+// block is responsible for (the engine: exactly the slots its sweep reads next).  jout[s - slot_base] = id.
+template <class JT>
+__device__ __forceinline__ void fill_heavy_runs(const EngineP& P, JT* jout, int slot_base, int slot_lo, int slot_hi) {
+  for (int r = 0; r < P.world; ++r) {
+    const int* list = (P.world > 1) ? P.peer_heavy[r] : P.heavy;
+    if (list == nullptr) continue;
+    int n = __ldcg(list);
+    if (n > HEAVY_MAX) n = HEAVY_MAX;
+    for (int e = 0; e < n; ++e) {
+      const int lo = __ldcg(list + 1 + 3 * e), c = __ldcg(list + 2 + 3 * e);
+      const JT id = (JT)__ldcg(list + 3 + 3 * e);
+      const int a = max(lo, slot_lo), b = min(lo + c, slot_hi);
+      for (int sl = a + threadIdx.x; sl < b; sl += BLOCK) __stcg(jout + (sl - slot_base), id);
+    }
+  }
+  __syncthreads();
+}
+
 // The whole resample: scan(we) -> bins (global) -> per-source slot ranges -> j (global, id = jbase + i).
 // Ends with a grid barrier: afterwards j[s] is valid for every slot s < f_total (returned); the
 // remaining slots are the reference's "untouched" entries (resample.jl:26-34).
@@ -965,8 +1003,12 @@ template <class JT, class LoadFn, class WeFn>
 __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, int beg, int end, unsigned& bar_target,
                                                 LoadFn loadfn, WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
                                                 int Mslots, const double* u_slots, JT* jout_flat, JT jbase,
-                                                double& total_out, u64& xseq) {
+                                                double& total_out, u64& xseq, int slot_lo, int slot_hi) {
+  // [slot_lo, slot_hi): the GLOBAL output slots this block fills from the heavy-run list; jout_flat[0] is global
+  // slot P.first
+  if (P.heavy != nullptr && blockIdx.x == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);   // before the first barrier
   SlotRouter<JT> jout;
+  jout.heavy = P.heavy;
   jout.j = jout_flat;
   jout.peer = reinterpret_cast<JT* const*>(P.peer_j);   // only dereferenced when world > 1 (JT == int there)
   jout.n = P.n;
@@ -1015,6 +1057,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     if (jout.remote) __threadfence_system();   // my peer stores are performed system-wide before I arrive
     grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
     if (P.world > 1) peer_barrier(P, xseq);    // every rank's offspring indices have landed in my j
+    fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi);
     LLPF_TS(P, sh, 4);
     return f_tot;
   }
@@ -1068,6 +1111,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   if (jout.remote) __threadfence_system();
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
   if (P.world > 1) peer_barrier(P, xseq);
+  fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi);
   LLPF_TS(P, sh, 4);
   return f_total;
 }
@@ -1389,7 +1433,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
           }
           return we;
         },
-        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq);
+        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
     sc.bins_total = total;
     LLPF_TSB(P, sh, P.dbg_T, 3);
   }
@@ -1554,7 +1598,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   const int f_total = resample_indices<int>(
       P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return __ldcg(wraw + i); },
       [=](int, double wr) { return exp_nonpos(wr - m1, *mtp) * inv1; }, 0.0, true,
-      step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq);
+      step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
   sc.bins_total = total;
   const bool with_x = (P.want_xhat != 0);
   const double lN = log((double)P.N);

@@ -55,8 +55,12 @@ class MvNormal:
     """MvNormal(mu, Sigma) / MvNormal(Sigma) — Distributions.MvNormal or SimpleMvNormal (src/utils.jl:241-273)."""
     mu: np.ndarray
     Sigma: np.ndarray = None
+    dtype: object = np.float64   # element type of the samples: an `initial_density` of Float32 makes Float32 particles (PFtypes.jl:66)
 
     def __post_init__(self):
+        self.dtype = np.dtype(self.dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("MvNormal dtype must be float64 or float32")
         if self.Sigma is None:
             self.Sigma = np.atleast_2d(np.asarray(self.mu, dtype=np.float64))
             self.mu = np.zeros(self.Sigma.shape[0])
@@ -168,7 +172,7 @@ class AbstractParticleFilter:
     _filter_code = FILTER_PF
 
     def _create(self, N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device,
-                rank=0, world=1):
+                rank=0, world=1, particle_dtype=np.float64):
         """N is the GLOBAL particle count; with world > 1 this process owns the contiguous slice
         [rank*N/world, (rank+1)*N/world) and must call connect_shards() before the first step."""
         self._lib = _abi.load_library()
@@ -182,6 +186,8 @@ class AbstractParticleFilter:
         cfg.seed = int(seed)
         cfg.scan_mode = SCAN_SERIAL if scan_mode in (SCAN_SERIAL, "serial") else SCAN_FAST
         cfg.device, cfg.rank, cfg.world = int(device), int(rank), int(world)
+        self.particle_dtype = np.dtype(particle_dtype)
+        cfg.particle_dtype = _abi.PARTICLE_F32 if self.particle_dtype == np.dtype(np.float32) else _abi.PARTICLE_F64
         self._cfg = cfg
         self._h = C.c_void_p()
         check(self._lib, self._lib.llpf_create(C.byref(cfg), C.byref(model.struct), C.byref(self._h)))
@@ -233,7 +239,8 @@ class ParticleFilter(AbstractParticleFilter):
         self.initial_density = initial_density
         model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
                               initial_density)
-        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world)
+        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
+                     particle_dtype=getattr(initial_density, "dtype", np.float64))
 
 
 class AdvancedParticleFilter(AbstractParticleFilter):
@@ -249,7 +256,8 @@ class AdvancedParticleFilter(AbstractParticleFilter):
         self.dynamics_density, self.initial_density = dynamics_density, initial_density
         model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
                               measurement_likelihood.R2, initial_density)
-        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world)
+        self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
+                     particle_dtype=getattr(initial_density, "dtype", np.float64))
 
 
 class AuxiliaryParticleFilter(AbstractParticleFilter):
@@ -265,7 +273,8 @@ class AuxiliaryParticleFilter(AbstractParticleFilter):
             for name in ("dynamics", "measurement", "dynamics_density", "initial_density"):
                 setattr(self, name, getattr(inner, name))
             self._create(inner.N_global, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
-                         inner.seed, cfg.scan_mode, cfg.device, inner.rank, inner.world)
+                         inner.seed, cfg.scan_mode, cfg.device, inner.rank, inner.world,
+                         particle_dtype=inner.particle_dtype)
         else:
             self.__init__(ParticleFilter(*args, **kwargs))
 
@@ -379,9 +388,11 @@ def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None):
     """forward_trajectory(pf,u,y,p) -> ParticleFilteringSolution   filtering.jl:343-384.
     history=False skips the N x T x/w/we arrays (they are then None); the per-step ll, ESS,
     resample flags and weighted means are always returned in `sol.extra`."""
-    r = _run(pf, u, y, TIME_FORWARD_TRAJECTORY, history, epoch)
+    # Float32-particle (wide) filters do not reduce the 64-component weighted mean inside the fused loop
+    wide = pf.particle_dtype == np.dtype(np.float32)
+    r = _run(pf, u, y, TIME_FORWARD_TRAJECTORY, history, epoch, want_xhat=not wide)
     t = np.arange(r["T"]) * pf.Ts  # range(0, step=Ts, length=T)  solutions.jl:345
-    extra = {k: r[k] for k in ("ll_steps", "ess", "resampled", "xhat")}
+    extra = {k: r.get(k) for k in ("ll_steps", "ess", "resampled", "xhat")}
     return ParticleFilteringSolution(pf, r["u"], r["y"], r.get("x"), r.get("w"), r.get("we"), r["ll"], t, extra)
 
 

@@ -4,6 +4,7 @@ config 1: examples/example_lineargaussian.jl:10-29  (nx=2 in the file; BASELINE 
 config 2: ParticleFilter, 4-state LG, N=2^20, T=1000, Float64
 config 3: AdvancedParticleFilter, quadtank RK4 (examples/example_quadtank.jl), N=2^18, T=2000
 config 4: AuxiliaryParticleFilter, 4-state LG, N=2^22
+config 5: ParticleFilter, 64-state LG (test/test_large.jl regime), N=2^20, T=500, Float32 particles
 """
 from dataclasses import dataclass
 
@@ -24,10 +25,11 @@ class LGSpec:
     R2: np.ndarray
     mu0: np.ndarray
     Sigma0: np.ndarray
+    dtype: object = np.float64     # particle element type (eltype of the initial density, PFtypes.jl:66)
 
     def _parts(self):
         return (F.LinearDynamics(self.A, self.B), F.LinearMeasurement(self.C), F.MvNormal(np.zeros(self.nx), self.R1),
-                F.MvNormal(np.zeros(self.ny), self.R2), F.MvNormal(self.mu0, self.Sigma0))
+                F.MvNormal(np.zeros(self.ny), self.R2), F.MvNormal(self.mu0, self.Sigma0, dtype=self.dtype))
 
     def particle_filter(self, N, **kw):
         dyn, meas, df, dg, d0 = self._parts()
@@ -52,6 +54,17 @@ def lg_spec(nx=4, nu=2, ny=2, seed=0, r1=1.0, r2=1.0):
     C_ = rng.standard_normal((ny, nx))
     mu0 = rng.standard_normal(nx)
     return LGSpec(nx, nu, ny, A, B, C_, r1 * np.eye(nx), r2 * np.eye(ny), mu0, 4.0 * np.eye(nx))
+
+
+def lg_large_spec(nx=64, nu=2, ny=58, seed=0, dtype=np.float32):
+    """BASELINE config 5 — the regime of test/test_large.jl:8-22 moved to a ParticleFilter with Float32 particles:
+    A = 0.1*randn(nx,nx), B = randn(nx,nu), C = randn(ny,nx) with ny = 0.9*nx rounded (58 for nx = 64, as the test's
+    90/100), R1 = I, R2 = I, d0 = N(0, I)."""
+    rng = np.random.default_rng(seed)
+    A = 0.1 * rng.standard_normal((nx, nx))
+    B = rng.standard_normal((nx, nu))
+    C_ = rng.standard_normal((ny, nx))
+    return LGSpec(nx, nu, ny, A, B, C_, np.eye(nx), np.eye(ny), np.zeros(nx), np.eye(nx), dtype=dtype)
 
 
 @dataclass

@@ -332,6 +332,11 @@ typedef struct orc_pf {
   /* scratch */
   double* lambda;      /* APF: the reference aliases s.we; kept separately addressable here */
   int64_t resample_count;
+  /* Float32-particle mode (llpf_config.particle_dtype == LLPF_PARTICLE_F32): see the f32 section below */
+  int f32;
+  float *Af, *Bf, *L1f, *L0f, *mu0f, *Gf;   /* row-major f32 copies; Gf = (float)(inv(chol(R2)) * C) */
+  double* Wd;                               /* row-major lower inv(chol(R2)) */
+  float c0f;
 } orc_pf;
 
 static double* dup_d(const double* p, size_t n) {
@@ -345,10 +350,132 @@ void orc_destroy(orc_pf* f) {
   free(f->x); free(f->xprev); free(f->w); free(f->we); free(f->bins); free(f->j);
   free(f->A); free(f->B); free(f->C); free(f->L1); free(f->L2); free(f->L0); free(f->mu0);
   free(f->lambda);
+  free(f->Af); free(f->Bf); free(f->L1f); free(f->L0f); free(f->mu0f); free(f->Gf); free(f->Wd);
   free(f);
 }
 
 void orc_reset(orc_pf* f, uint64_t epoch);
+
+/* ------------------------------------------------------------------------------------------
+ * Float32 particles (BASELINE config 5: 64-state linear-Gaussian, test/test_large.jl:8-22 regime)
+ *
+ * The particle eltype of the reference comes from `initial_density` (PFtypes.jl:66,202); with Float32
+ * densities and matrices `dynamics`, `rand!` and `logpdf` run in Float32 while w/we/bins stay Float64
+ * (PFtypes.jl:68-69: `w = fill(log(1/N), N)`), so `w[i] += logpdf(...)` (PFtypes.jl:116) promotes a
+ * Float32 log-likelihood.  At this size the reference's `A*x` is a BLAS sgemv and `logpdf` a PDMats
+ * triangular solve, whose summation orders are unspecified; the order below is OURS (documented in
+ * llpf_wide.cuh) and every operation is a correctly rounded f32 fmaf/add, so the CUDA path can match
+ * it bit for bit.  Values are kept in the double arrays of orc_pf (exactly representable).
+ *   x'_r   = fmaf-chain_c(A[r,c] x[c]) from 0 ; x'_r += (B u)_r ; x'_r = fmaf(L1[r,c], z[c], x'_r) for c <= r
+ *   loglik = fmaf(-1/2, sum_a v_a^2 (fmaf chain), c0),  v_a = yt_a - (even-column chain + odd-column chain of G[a,:] x')
+ *   yt = (float)(W y) with W = inv(chol(R2)) (f64), G = (float)(W C) (f64 product, rounded once)
+ * ---------------------------------------------------------------------------------------- */
+static void build_f32_model(orc_pf* f) {
+  const int nx = f->nx, nu = f->nu, ny = f->ny;
+  free(f->Af); free(f->Bf); free(f->L1f); free(f->L0f); free(f->mu0f); free(f->Gf); free(f->Wd);
+  f->Af = (float*)calloc((size_t)nx * nx, sizeof(float));
+  f->Bf = (float*)calloc((size_t)nx * (nu ? nu : 1), sizeof(float));
+  f->L1f = (float*)calloc((size_t)nx * nx, sizeof(float));
+  f->L0f = (float*)calloc((size_t)nx * nx, sizeof(float));
+  f->mu0f = (float*)calloc((size_t)nx, sizeof(float));
+  f->Gf = (float*)calloc((size_t)ny * nx, sizeof(float));
+  f->Wd = (double*)calloc((size_t)ny * ny, sizeof(double));
+  for (int r = 0; r < nx; ++r) {
+    f->mu0f[r] = (float)f->mu0[r];
+    for (int c = 0; c < nx; ++c) {
+      f->Af[r * nx + c] = (float)CM(f->A, r, c, nx);
+      f->L1f[r * nx + c] = (float)CM(f->L1, r, c, nx);
+      f->L0f[r * nx + c] = (float)CM(f->L0, r, c, nx);
+    }
+    for (int c = 0; c < nu; ++c) f->Bf[r * nu + c] = (float)CM(f->B, r, c, nx);
+  }
+  /* W = inv(L2), column by column (forward substitution) */
+  double* W = (double*)calloc((size_t)ny * ny, sizeof(double));   /* column-major */
+  for (int c = 0; c < ny; ++c) {
+    CM(W, c, c, ny) = 1.0 / CM(f->L2, c, c, ny);
+    for (int r = c + 1; r < ny; ++r) {
+      double acc = 0.0;
+      for (int k = c; k < r; ++k) acc += CM(f->L2, r, k, ny) * CM(W, k, c, ny);
+      CM(W, r, c, ny) = -acc / CM(f->L2, r, r, ny);
+    }
+  }
+  for (int a = 0; a < ny; ++a) {
+    for (int c = 0; c <= a; ++c) f->Wd[a * ny + c] = CM(W, a, c, ny);
+    for (int c = 0; c < nx; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k <= a; ++k) acc += CM(W, a, k, ny) * CM(f->C, k, c, ny);
+      f->Gf[a * nx + c] = (float)acc;
+    }
+  }
+  free(W);
+  f->c0f = (float)f->c0_meas;
+}
+
+/* reset!(pf) filtering.jl:4-14, f32: x0_r = mu0_r + fmaf-chain_{c<=r}(L0[r,c] z[c]) */
+static void reset_particles_f32(orc_pf* f) {
+  const int nx = f->nx;
+  double z[64];
+  for (int64_t i = 0; i < f->N; ++i) {
+    orc_normals(f->seed, f->epoch, STREAM_INIT, 0, (uint64_t)i, 64, z);   /* 16 counter blocks, as on the device */
+    for (int r = 0; r < nx; ++r) {
+      float acc = 0.f;
+      for (int c = 0; c <= r; ++c) acc = fmaf(f->L0f[r * nx + c], (float)z[c], acc);
+      acc = f->mu0f[r] + acc;
+      f->xprev[(size_t)i * nx + r] = (double)acc;
+      f->x[(size_t)i * nx + r] = (double)acc;
+    }
+  }
+}
+
+/* propagate_particles!  PFtypes.jl:122-139 / ext:83-93 / PFtypes.jl:242-289, f32 */
+static void propagate_particles_f32(orc_pf* f, const double* u, int use_j, int with_noise) {
+  const int nx = f->nx, nu = f->nu;
+  float bu[64];
+  for (int r = 0; r < nx; ++r) {
+    float acc = 0.f;
+    for (int c = 0; c < nu; ++c) acc = fmaf(f->Bf[r * nu + c], (float)u[c], acc);
+    bu[r] = acc;
+  }
+  double z[64];
+  for (int64_t i = 0; i < f->N; ++i) {
+    const int64_t src = use_j ? f->j[i] - 1 : i;
+    const double* xp = f->xprev + (size_t)src * nx;
+    if (with_noise) orc_normals(f->seed, f->epoch, STREAM_DYN, (uint32_t)f->t, (uint64_t)i, 64, z);
+    for (int r = 0; r < nx; ++r) {
+      float acc = 0.f;
+      for (int c = 0; c < nx; ++c) acc = fmaf(f->Af[r * nx + c], (float)xp[c], acc);
+      acc = acc + bu[r];
+      if (with_noise)
+        for (int c = 0; c <= r; ++c) acc = fmaf(f->L1f[r * nx + c], (float)z[c], acc);
+      f->x[(size_t)i * nx + r] = (double)acc;
+    }
+  }
+}
+
+/* measurement_equation!  PFtypes.jl:107-120 / :226-239, f32 log-likelihood promoted to f64 on `+=` */
+static void measurement_equation_f32(const orc_pf* f, const double* y, double* w) {
+  const int nx = f->nx, ny = f->ny;
+  float yt[64];
+  for (int a = 0; a < ny; ++a) {
+    double acc = 0.0;
+    for (int c = 0; c <= a; ++c) acc = fma(f->Wd[a * ny + c], y[c], acc);
+    yt[a] = (float)acc;
+  }
+  for (int64_t i = 0; i < f->N; ++i) {
+    const double* x = f->x + (size_t)i * nx;
+    float q = 0.f;
+    for (int a = 0; a < ny; ++a) {
+      float de = 0.f, dd = 0.f;
+      for (int c = 0; c < nx; c += 2) {
+        de = fmaf(f->Gf[a * nx + c], (float)x[c], de);
+        if (c + 1 < nx) dd = fmaf(f->Gf[a * nx + c + 1], (float)x[c + 1], dd);
+      }
+      const float v = yt[a] - (de + dd);
+      q = fmaf(v, v, q);
+    }
+    w[i] += (double)fmaf(-0.5f, q, f->c0f);
+  }
+}
 
 static int set_model(orc_pf* f, const llpf_model* m) {
   const int nx = m->nx, nu = m->nu, ny = m->ny;
@@ -372,6 +499,7 @@ static int set_model(orc_pf* f, const llpf_model* m) {
   memcpy(f->dyn_params, m->dyn_params, sizeof(f->dyn_params));
   f->t_switch = m->t_switch; f->a1_factor = m->a1_factor;
   f->integ_Ts = m->integ_Ts; f->supersample = m->supersample;
+  if (f->f32) build_f32_model(f);
   return LLPF_OK;
 }
 
@@ -381,6 +509,8 @@ int orc_create(const llpf_config* cfg, const llpf_model* m, orc_pf** out) {
   orc_pf* f = (orc_pf*)calloc(1, sizeof(orc_pf));
   f->N = cfg->N; f->filter = cfg->filter; f->resampling = cfg->resampling;
   f->threshold = cfg->resample_threshold; f->Ts = cfg->Ts; f->seed = cfg->seed;
+  f->f32 = (cfg->particle_dtype == LLPF_PARTICLE_F32);
+  if (f->f32 && (m->dynamics != LLPF_DYN_LINEAR || f->filter > LLPF_FILTER_ADVANCED)) { orc_destroy(f); return LLPF_ERR_UNSUPPORTED; }
   const int rc = set_model(f, m);
   if (rc) { orc_destroy(f); return rc; }
   const size_t N = (size_t)f->N;
@@ -412,7 +542,8 @@ static void sample_mvn(const double* mu, const double* L, int n, const double* z
 void orc_reset(orc_pf* f, uint64_t epoch) {
   f->epoch = epoch;
   double z[64];
-  for (int64_t i = 0; i < f->N; ++i) {
+  if (f->f32) reset_particles_f32(f);
+  else for (int64_t i = 0; i < f->N; ++i) {
     orc_normals(f->seed, epoch, STREAM_INIT, 0, (uint64_t)i, f->nx, z);
     sample_mvn(f->mu0, f->L0, f->nx, z, f->xprev + (size_t)i * f->nx);
     memcpy(f->x + (size_t)i * f->nx, f->xprev + (size_t)i * f->nx, sizeof(double) * f->nx);
@@ -525,6 +656,7 @@ static int any_nan(const double* y, int n) {
 static void measurement_equation(const orc_pf* f, const double* u, const double* y, double t, double* w) {
   (void)u; (void)t;
   if (any_nan(y, f->ny)) return;
+  if (f->f32) { measurement_equation_f32(f, y, w); return; }
   double g[64], r[64];
   for (int64_t i = 0; i < f->N; ++i) {
     matvec(f->C, f->ny, f->nx, f->x + (size_t)i * f->nx, g);
@@ -547,6 +679,7 @@ static void dyn_noise(const orc_pf* f, int64_t i, double* noise) {
    use_j: gather through j (1-based); with_noise: add L*z                                        */
 static void propagate_particles(orc_pf* f, const double* u, int use_j, double t, int with_noise) {
   double fx[64], nz[64];
+  if (f->f32) { propagate_particles_f32(f, u, use_j, with_noise); return; }
   for (int64_t i = 0; i < f->N; ++i) {
     const int64_t src = use_j ? f->j[i] - 1 : i;
     dynamics_mean(f, f->xprev + (size_t)src * f->nx, u, t, fx);

@@ -242,9 +242,10 @@ class ModelArrays:
 
 
 class OracleFilter:
-    def __init__(self, model, N, filter=0, resampling=0, resample_threshold=0.1, Ts=1.0, seed=0):
+    def __init__(self, model, N, filter=0, resampling=0, resample_threshold=0.1, Ts=1.0, seed=0, particle_dtype=np.float64):
         self.model = model
         cfg = Config()
+        cfg.particle_dtype = 1 if np.dtype(particle_dtype) == np.dtype(np.float32) else 0
         cfg.N, cfg.filter, cfg.resampling = N, filter, resampling
         cfg.resample_threshold, cfg.Ts, cfg.seed = resample_threshold, Ts, seed
         cfg.scan_mode, cfg.device, cfg.rank, cfg.world = 1, 0, 0, 1

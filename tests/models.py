@@ -18,11 +18,21 @@ class _LG(W.LGSpec):
                              A=self.A, B=self.B, dynamics=0)
 
     def oracle_filter(self, N, filter=0, **kw):
+        kw.setdefault("particle_dtype", self.dtype)
         return O.OracleFilter(self.oracle_model(), N, filter=filter, **kw)
 
 
 def lg_model(nx=4, nu=2, ny=2, seed=0, r1=1.0, r2=1.0):
     s = W.lg_spec(nx, nu, ny, seed, r1, r2)
+    return _LG(**s.__dict__)
+
+
+def lg_large_model(nx=64, nu=2, ny=58, seed=0, dtype=np.float32, r1_offdiag=0.0):
+    """config 5 model (Float32 particles); r1_offdiag != 0 makes R1 non-diagonal (general Cholesky path)."""
+    s = W.lg_large_spec(nx, nu, ny, seed, dtype)
+    if r1_offdiag:
+        R1 = np.eye(nx) + r1_offdiag * (np.ones((nx, nx)) - np.eye(nx))
+        s.R1 = R1
     return _LG(**s.__dict__)
 
 

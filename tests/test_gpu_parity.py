@@ -9,7 +9,7 @@ scans, the closed-form Kalman filter).
 import numpy as np
 import pytest
 
-from models import lg_model, quadtank_model, ref_model_2state
+from models import lg_large_model, lg_model, quadtank_model, ref_model_2state
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -466,6 +466,80 @@ def test_pf_and_apf_loglik_vs_kalman_on_device(gpu):   # test/runtests.jl:412-44
     llpf, llapf, llkf = map(np.array, (llpf, llapf, llkf))
     assert 4 <= np.argmax(llpf) <= 6 and 4 <= np.argmax(llapf) <= 6 and 4 <= np.argmax(llkf) <= 6
     assert np.max(np.abs(llkf - llpf)) < 20 and np.max(np.abs(llkf - llapf)) < 20
+
+
+# ---------------------------------------------------------------------------------------------
+# Float32 particles, wide models (BASELINE config 5; llpf_wide.cuh)
+# ---------------------------------------------------------------------------------------------
+F32_LL_RTOL = 1e-6     # oracle and device run the same f32 operation sequence; only a f64->f32 double rounding of a
+F32_X_ATOL = 1e-5      # normal variate (p ~ 1e-7 per variate) can differ, by one f32 ulp
+
+
+@pytest.mark.parametrize("nx,nu,ny,offdiag", [(64, 2, 58, 0.0), (64, 2, 58, 0.01), (5, 1, 3, 0.0), (33, 0, 17, 0.02)])
+def test_f32_wide_stepwise_verbs_match_oracle(gpu, nx, nu, ny, offdiag):
+    L = gpu
+    s = lg_large_model(nx, nu, ny, seed=nx + ny, r1_offdiag=offdiag)
+    N = 600
+    pf = s.particle_filter(N, seed=9, scan_mode="serial", resample_threshold=0.5)
+    of = s.oracle_filter(N, seed=9, resample_threshold=0.5)
+    L.reset(pf, 2); of.reset(2)
+    x0, x0o = L.particles(pf), of.particles
+    assert x0.shape == (N, nx) and np.abs(x0 - x0o).max() <= F32_X_ATOL
+    assert np.array_equal(x0.astype(np.float32).astype(np.float64), x0)      # values are Float32
+    rng = np.random.default_rng(3)
+    n_res = 0
+    for k in range(8):
+        u = rng.standard_normal(nu)
+        y = of.particles[0] @ s.C.T + 0.3 * rng.standard_normal(ny)
+        ll, _ = L.correct(pf, u, y, None, float(k))
+        llo = of.correct(u, y, float(k))
+        assert abs(ll - llo) <= F32_LL_RTOL * max(1.0, abs(llo)), (k, ll, llo)
+        assert np.allclose(L.expweights(pf), of.expweights, rtol=1e-5, atol=1e-12)
+        assert L.shouldresample(pf) == of.shouldresample()
+        assert np.allclose(L.weighted_mean(pf), of.weighted_mean(), rtol=0, atol=1e-5)
+        n_res += of.shouldresample()
+        L.predict(pf, u, None, float(k)); of.predict(u, float(k))
+        assert np.array_equal(L.ancestors(pf), of.ancestors)
+        x, xo = L.particles(pf), of.particles
+        assert np.abs(x - xo).max() <= F32_X_ATOL * max(1.0, np.abs(xo).max()), np.abs(x - xo).max()
+        assert (x != xo).mean() < 1e-4          # bit-identical except for the rare double-rounding case
+        assert L.index(pf) == of.index
+    assert n_res > 0
+
+
+@pytest.mark.parametrize("scan_mode,thr", [("serial", 0.5), ("fast", 0.5), ("fast", 1.0), ("fast", 0.0)])
+def test_f32_wide_loglik_matches_oracle(gpu, scan_mode, thr):
+    """config-5 model (64 states, 58 outputs, Float32 particles) at an oracle-affordable size."""
+    L = gpu
+    s = lg_large_model(seed=1)
+    N, T = 2048, 12
+    u, y = _data(s, T, 5)
+    pf = s.particle_filter(N, seed=21, scan_mode=scan_mode, resample_threshold=thr)
+    of = s.oracle_filter(N, seed=21, resample_threshold=thr)
+    got = L.loglik(pf, u, y, epoch=1, details=True)
+    ref = of.loglik(u, y, epoch=1)
+    assert abs(got["ll"] - ref["ll"]) <= F32_LL_RTOL * abs(ref["ll"]), (got["ll"], ref["ll"])
+    assert np.array_equal(got["resampled"], ref["resampled"])
+    assert np.allclose(got["ll_steps"], ref["ll_steps"], rtol=1e-6, atol=1e-6)
+    if scan_mode == "serial":
+        assert np.abs(L.particles(pf) - of.particles).max() <= F32_X_ATOL * max(1.0, np.abs(of.particles).max())
+    # the same call through forward_trajectory semantics (time-invariant model: same numbers)
+    sol = L.forward_trajectory(pf, u, y, epoch=1, history=False)
+    assert abs(sol.ll - got["ll"]) <= 1e-12 * abs(got["ll"])
+
+
+def test_f32_wide_unsupported_combinations_fail_loudly(gpu):
+    L = gpu
+    s = lg_large_model(seed=2)
+    with pytest.raises(L.LLPFError):
+        s.aux_filter(256, seed=1)                       # APF over Float32 particles: not built
+    pf = s.particle_filter(256, seed=1)
+    u, y = _data(s, 4, 1)
+    with pytest.raises(L.LLPFError):
+        L.forward_trajectory(pf, u, y)                  # x/w/we history of a wide filter: not recorded in the loop
+    s8 = lg_model(4, 2, 2, seed=0)
+    with pytest.raises(L.LLPFError):
+        lg_large_model(65, 2, 4).particle_filter(64)    # nx > 64
 
 
 def test_full_size_config2_properties(gpu):
