@@ -255,76 +255,6 @@ __device__ __forceinline__ void st_release_gpu_u64(u64* p, u64 v) {
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// All-gather of NV doubles per rank.  Every block of every rank calls it with identical `mine` (the
-// values every block derived from the same local data after a local grid barrier).
-//   block 0, thread r (r != rank): writes the rank's values into peer r's mailbox (plain stores over
-//     NVLink, then a release flag), waits for peer r's flag in the LOCAL mailbox (relaxed polling, one
-//     system-scope acquire), copies peer r's payload into a local broadcast buffer;
-//   block 0, thread 0: publishes the broadcast buffer with a gpu-scope release flag;
-//   every other block: waits for that flag (gpu scope only — no system-scope traffic outside block 0).
-// Slots are double-buffered by the parity of the sequence number; a rank can never be more than one
-// exchange ahead of a peer (it needs that peer's post to get past the current one), and a post is only
-// made after a local grid barrier, i.e. after all of the rank's blocks finished reading the previous
-// exchange of the same parity.
-template <int NV>
-__device__ __forceinline__ void peer_allgather(const EngineP& P, u64& xseq, const double (&mine)[NV],
-                                               double (&all)[MAX_WORLD][NV]) {
-  static_assert(NV < MBOX_DOUBLES, "payload too large");
-  xseq += 1;
-  const int par = (int)(xseq & 1ull);
-  double* bc = P.bcast + (size_t)par * MAX_WORLD * MBOX_DOUBLES;
-  u64* bflag = P.bcast_flag + par;
-  if (blockIdx.x == 0) {
-    if (threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
-      // "LL" protocol (as in NCCL's low-latency path): every 8-byte word carries 4 bytes of payload and the
-      // 4-byte sequence number, 8-byte stores are single NVLink transactions, so no fence is needed: a word
-      // is valid exactly when its flag half equals the expected sequence number.
-      const int r = threadIdx.x;
-      const u64 tag = (xseq & 0xffffffffull) << 32;
-      u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const u64 bits = (u64)__double_as_longlong(mine[k]);
-        st_relaxed_sys_u64(out + 2 * k, tag | (bits & 0xffffffffull));
-        st_relaxed_sys_u64(out + 2 * k + 1, tag | (bits >> 32));
-      }
-      const u64* in = reinterpret_cast<const u64*>(P.peer_mbox[P.rank]) + ((size_t)par * MAX_WORLD + r) * MBOX_WORDS;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        u64 lo, hi;
-        do { lo = ld_relaxed_sys_u64(in + 2 * k); } while ((lo & 0xffffffff00000000ull) != tag);
-        do { hi = ld_relaxed_sys_u64(in + 2 * k + 1); } while ((hi & 0xffffffff00000000ull) != tag);
-        __stcg(bc + r * MBOX_DOUBLES + 1 + k, __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull))));
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      st_release_gpu_u64(bflag, xseq);
-    }
-  } else {
-    if (threadIdx.x == 0) {
-      while (ld_relaxed_gpu_u64(bflag) != xseq) {
-      }
-      (void)ld_acquire_gpu_u64(bflag);
-    }
-    __syncthreads();
-  }
-  for (int r = 0; r < P.world; ++r) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) all[r][k] = (r == P.rank) ? mine[k] : __ldcg(bc + r * MBOX_DOUBLES + 1 + k);
-  }
-}
-
-// cross-GPU barrier.  Call right after a local grid barrier; every thread that stored into peer memory
-// must have executed __threadfence_system() before arriving at that barrier, so all of this rank's peer
-// stores are performed before block 0 posts.
-__device__ __forceinline__ void peer_barrier(const EngineP& P, u64& xseq) {
-  const double none[1] = {0.0};
-  double all[MAX_WORLD][1];
-  peer_allgather<1>(P, xseq, none, all);
-}
-
 struct Shared {
   // model matrices, read with volatile 16-byte shared loads inside the particle loop (see llpf_math.cuh:
   // the compiler would otherwise hoist ~35 loop-invariant constant loads into registers and spill them)
@@ -346,6 +276,64 @@ struct Shared {
   u64 offs[MAX_BLOCKS + 1];     // exclusive block offsets of the fixed-point scan
   alignas(16) MathTab mt;       // log / exp tables + polynomial coefficients of llpf_math.cuh
 };
+
+// All-gather of NV doubles per rank.  Every block of every rank calls it with identical `mine` (the
+// values every block derived from the same local data after a local grid barrier).
+//   block 0, thread r (r != rank): writes the rank's values into peer r's mailbox — "LL" protocol as in NCCL's
+//     low-latency path: every 8-byte word carries 4 bytes of payload and the 4-byte sequence number, 8-byte
+//     stores are single NVLink transactions, so a word is valid exactly when its tag equals the expected
+//     sequence number and no fence / flag is needed;
+//   EVERY block: polls the words the peers wrote into the LOCAL mailbox (one thread per word).  (v6 had block 0
+//     poll and re-broadcast through a flag: one more fence + L2 hop on the critical path of every exchange.)
+// Slots are double-buffered by the parity of the sequence number; a rank can never be more than one
+// exchange ahead of a peer (it needs that peer's post to get past the current one), and a post is only
+// made after a local grid-wide synchronisation, i.e. after all of the rank's blocks finished reading the
+// previous exchange of the same parity.
+template <int NV>
+__device__ __forceinline__ void peer_allgather(const EngineP& P, Shared& sh, u64& xseq, const double (&mine)[NV],
+                                               double (&all)[MAX_WORLD][NV]) {
+  static_assert(2 * NV <= MBOX_WORDS && NV <= 3 + MAX_NX, "payload too large");
+  xseq += 1;
+  const int par = (int)(xseq & 1ull);
+  const u64 tag = (xseq & 0xffffffffull) << 32;
+  if (blockIdx.x == 0 && threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+    const int r = threadIdx.x;
+    u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const u64 bits = (u64)__double_as_longlong(mine[k]);
+      st_relaxed_sys_u64(out + 2 * k, tag | (bits & 0xffffffffull));
+      st_relaxed_sys_u64(out + 2 * k + 1, tag | (bits >> 32));
+    }
+  }
+  uint32_t* words = reinterpret_cast<uint32_t*>(sh.peer_vals);   // [world][2*NV] payload halves
+  __syncthreads();                                               // earlier readers of sh.peer_vals are done
+  if ((int)threadIdx.x < P.world * 2 * NV) {
+    const int r = threadIdx.x / (2 * NV), wd = threadIdx.x % (2 * NV);
+    if (r != P.rank) {
+      const u64* in = reinterpret_cast<const u64*>(P.peer_mbox[P.rank]) + ((size_t)par * MAX_WORLD + r) * MBOX_WORDS + wd;
+      u64 v;
+      do { v = ld_relaxed_sys_u64(in); } while ((v & 0xffffffff00000000ull) != tag);
+      words[threadIdx.x] = (uint32_t)v;
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < P.world; ++r) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      all[r][k] = (r == P.rank) ? mine[k]
+                                : __hiloint2double((int)words[r * 2 * NV + 2 * k + 1], (int)words[r * 2 * NV + 2 * k]);
+  }
+}
+
+// cross-GPU barrier carrying one value per rank (the length of the rank's heavy-run list).  Call right after a
+// local grid barrier; every thread that stored into peer memory must have executed __threadfence_system()
+// before arriving at that barrier, so all of this rank's peer stores are performed before block 0 posts.
+__device__ __forceinline__ void peer_barrier(const EngineP& P, Shared& sh, u64& xseq, double payload,
+                                             double (&all)[MAX_WORLD][1]) {
+  const double mine[1] = {payload};
+  peer_allgather<1>(P, sh, xseq, mine, all);
+}
 
 template <int K>
 __device__ __forceinline__ void lds_row(const double* row, double (&out)[K]) {   // row is 16-byte aligned, padded
@@ -980,11 +968,16 @@ __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int 
 // After the barrier(s) that close the scatter: fill the queued heavy runs into the slots [slot_lo, slot_hi) this
 // block is responsible for (the engine: exactly the slots its sweep reads next).  jout[s - slot_base] = id.
 template <class JT>
-__device__ __forceinline__ void fill_heavy_runs(const EngineP& P, JT* jout, int slot_base, int slot_lo, int slot_hi) {
+__device__ __forceinline__ void fill_heavy_runs(const EngineP& P, JT* jout, int slot_base, int slot_lo, int slot_hi,
+                                                const double (&counts)[MAX_WORLD][1]) {
+  // counts[r] = length of rank r's list (travelled with the cross-GPU barrier; single GPU: counts[0] is the local one)
+  bool any = false;
+  for (int r = 0; r < P.world; ++r) any = any || (counts[r][0] > 0.0);
+  if (!any) return;   // block-uniform
   for (int r = 0; r < P.world; ++r) {
     const int* list = (P.world > 1) ? P.peer_heavy[r] : P.heavy;
     if (list == nullptr) continue;
-    int n = __ldcg(list);
+    int n = (int)counts[r][0];
     if (n > HEAVY_MAX) n = HEAVY_MAX;
     for (int e = 0; e < n; ++e) {
       const int lo = __ldcg(list + 1 + 3 * e), c = __ldcg(list + 2 + 3 * e);
@@ -1036,7 +1029,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
       // global CDF offset of this rank: all-gather of the ranks' fixed-point totals (exact integers, so the
       // global bins are bit-identical to a single-GPU scan of the same weights)
       double mine[1] = {__longlong_as_double((long long)gtot)}, all[MAX_WORLD][1];
-      peer_allgather<1>(P, xseq, mine, all);
+      peer_allgather<1>(P, sh, xseq, mine, all);
       gtot = 0;
       for (int r = 0; r < P.world; ++r) {
         const u64 tr = (u64)__double_as_longlong(all[r][0]);
@@ -1056,8 +1049,10 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     LLPF_TS(P, sh, 3);
     if (jout.remote) __threadfence_system();   // my peer stores are performed system-wide before I arrive
     grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-    if (P.world > 1) peer_barrier(P, xseq);    // every rank's offspring indices have landed in my j
-    fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi);
+    double hcnt[MAX_WORLD][1];
+    hcnt[0][0] = (P.heavy != nullptr) ? (double)__ldcg(P.heavy) : 0.0;
+    if (P.world > 1) peer_barrier(P, sh, xseq, hcnt[0][0], hcnt);    // every rank's offspring indices have landed in my j
+    fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi, hcnt);
     LLPF_TS(P, sh, 4);
     return f_tot;
   }
@@ -1110,8 +1105,10 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   LLPF_TS(P, sh, 3);
   if (jout.remote) __threadfence_system();
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-  if (P.world > 1) peer_barrier(P, xseq);
-  fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi);
+  double hcnt[MAX_WORLD][1];
+  hcnt[0][0] = (P.heavy != nullptr) ? (double)__ldcg(P.heavy) : 0.0;
+  if (P.world > 1) peer_barrier(P, sh, xseq, hcnt[0][0], hcnt);
+  fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi, hcnt);
   LLPF_TS(P, sh, 4);
   return f_total;
 }

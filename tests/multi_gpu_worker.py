@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import llpf_b200 as L  # noqa: E402
-from models import lg_model  # noqa: E402
+from models import lg_large_model, lg_model  # noqa: E402
 
 
 def main():
@@ -21,10 +21,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")          # only carries the IPC descriptors; the data path is peer memory
-    s = lg_model(4, 2, 2, seed=0)
+    s4 = lg_model(4, 2, 2, seed=0)
+    s64 = lg_large_model(seed=1)      # config 5: 64 states, Float32 particles; weights degenerate -> heavy offspring runs
     ok = True
     for (N, T, thr, kind) in [(4096, 60, 0.1, "pf"), (1 << 16, 80, 0.5, "pf"), (1 << 16, 40, 1.0, "pf"),
-                              (1 << 14, 50, 0.1, "aux"), (1 << 20, 50, 0.1, "pf")]:
+                              (1 << 14, 50, 0.1, "aux"), (1 << 20, 50, 0.1, "pf"), (1 << 13, 10, 0.5, "wide"),
+                              (1 << 18, 6, 0.5, "wide")]:
+        s = s64 if kind == "wide" else s4
         u = np.random.default_rng(3).standard_normal((T, 2))
         gen = s.oracle_filter(64, seed=1)
         _, y = gen.simulate(u, 17)
@@ -51,7 +54,7 @@ def main():
             nj = int((J != j1).sum())
             msg = f"{kind} N={N} T={T} thr={thr} world={world}: ll={lls[0]:.10f} vs 1-GPU {r1['ll']:.10f} rel={rel:.2e} " \
                   f"resampled_equal={same_res} max|dx|={dx:.2e} j_mismatch={nj} ms={L.last_run_ms(pf):.2f} (1-GPU {L.last_run_ms(one):.2f})"
-            if N <= (1 << 16):
+            if N <= (1 << 16) and kind != "wide" or N <= (1 << 13):
                 ref = (s.oracle_filter(N, filter=2 if kind == "aux" else 0, seed=5, resample_threshold=thr)).loglik(u, y, epoch=2)
                 relo = abs(lls[0] - ref["ll"]) / abs(ref["ll"])
                 msg += f" | oracle rel={relo:.2e}"
