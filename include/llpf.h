@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LLPF_VERSION 101
+#define LLPF_VERSION 102
 
 /* ---- status codes -------------------------------------------------------------------- */
 enum {
@@ -55,7 +55,7 @@ enum {
 enum {
   LLPF_RESAMPLE_SYSTEMATIC = 0, /* resample.jl:17-36  */
   LLPF_RESAMPLE_STRATIFIED = 1, /* resample.jl:38-61  */
-  LLPF_RESAMPLE_RESIDUAL = 2    /* resample.jl:63-117 (stand-alone entry point only) */
+  LLPF_RESAMPLE_RESIDUAL = 2    /* resample.jl:63-117 (single-GPU filters)           */
 };
 
 /* ---- how the cumulative sum `bins` is formed (resample.jl:19-22) ----------------------- */
@@ -126,7 +126,7 @@ typedef struct llpf_model {
 typedef struct llpf_config {
   int64_t N;                  /* number of particles                                   */
   int32_t filter;             /* LLPF_FILTER_*                                         */
-  int32_t resampling;         /* LLPF_RESAMPLE_SYSTEMATIC | LLPF_RESAMPLE_STRATIFIED   */
+  int32_t resampling;         /* LLPF_RESAMPLE_* (RESIDUAL: world == 1 only)            */
   double  resample_threshold; /* resample.jl:5-10 ; ==1 means always                   */
   double  Ts;                 /* sample time                                           */
   uint64_t seed;
@@ -219,6 +219,12 @@ int llpf_resample_systematic(int64_t N, const double* we, double u01, int64_t M,
 /* resample(ResampleStratified, ...) resample.jl:38-61 with the M rand() draws supplied as u01[M] */
 int llpf_resample_stratified(int64_t N, const double* we, const double* u01, int64_t M,
                              int64_t* j_inout, double* bins_out, int32_t scan_mode, int32_t device);
+/* resample(ResampleResidual, ...) resample.jl:63-117 with the rand() draws of :106 supplied in draw order as
+   u01[M] (only the first M - sum(floor(we_i/sum(we)*M)) are consumed).  bins_out receives the reference's `bins`
+   after the call: the normalised cumulative residuals (or the raw residuals when no draw was needed, :85-87).
+   LLPF_SCAN_SERIAL performs the three sums (:66-69, :89-92, :99-102) left to right like the reference.        */
+int llpf_resample_residual(int64_t N, const double* we, const double* u01, int64_t M,
+                           int64_t* j_inout, double* bins_out, int32_t scan_mode, int32_t device);
 /* logsumexp!(w, we) utils.jl:18-27 : in-place on host arrays w[N] (normalised log-weights out),
    we[N] out, returns ll = log(sum(exp(w_in)))                                                  */
 int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int32_t device);

@@ -155,4 +155,20 @@ function resample_systematic(we::Vector{Float64}, u01::Float64; M=length(we), j=
     j, bins
 end
 
+"resample(ResampleStratified, ...) src/resample.jl:38-61 with the M rand() draws of :49 supplied"
+function resample_stratified(we::Vector{Float64}, u01::Vector{Float64}; M=length(we), j=collect(Int64, 1:M), scan_mode=0, device=0)
+    bins = similar(we)
+    check(ccall((:llpf_resample_stratified, lib), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}, Int32, Int32),
+                length(we), we, u01, M, j, bins, scan_mode, device))
+    j, bins
+end
+
+"resample(ResampleResidual, ...) src/resample.jl:63-117 with the rand() draws of :106 supplied in draw order (length M)"
+function resample_residual(we::Vector{Float64}, u01::Vector{Float64}; M=length(we), j=collect(Int64, 1:M), scan_mode=0, device=0)
+    bins = similar(we)
+    check(ccall((:llpf_resample_residual, lib), Cint, (Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int64}, Ptr{Float64}, Int32, Int32),
+                length(we), we, u01, M, j, bins, scan_mode, device))
+    j, bins
+end
+
 end # module

@@ -106,6 +106,7 @@ def load_library(path=None):
         "llpf_weighted_mean": [H, dp],
         "llpf_resample_systematic": [C.c_int64, dp, C.c_double, C.c_int64, ip, dp, C.c_int32, C.c_int32],
         "llpf_resample_stratified": [C.c_int64, dp, dp, C.c_int64, ip, dp, C.c_int32, C.c_int32],
+        "llpf_resample_residual": [C.c_int64, dp, dp, C.c_int64, ip, dp, C.c_int32, C.c_int32],
         "llpf_logsumexp": [C.c_int64, dp, dp, dp, C.c_int32],
         "llpf_shard_blob_size": [C.POINTER(C.c_size_t)],
         "llpf_shard_export": [H, C.c_void_p],
@@ -115,6 +116,8 @@ def load_library(path=None):
         "llpf_device_pointers": [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)],
     }
     for name, args in protos.items():
+        if os.environ.get("LLPF_LIB_ALLOW_MISSING") and not hasattr(lib, name):
+            continue             # A/B timing against an older build of the library (scripts/tune.py only)
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.argtypes = args
         fn.restype = C.c_int

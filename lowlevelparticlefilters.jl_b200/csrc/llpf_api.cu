@@ -13,6 +13,7 @@
 
 #include "../../include/llpf.h"
 #include "llpf_engine.cuh"
+#include "llpf_engine_list.h"
 #include "llpf_wide.cuh"
 
 using namespace llpf;
@@ -284,6 +285,26 @@ k_resample(const __grid_constant__ EngineP P, const double* we, double u01, cons
                                     (int)(s0 < M ? s0 : M), (int)(s1 < M ? s1 : M));
 }
 
+// resample(ResampleResidual, we, j, bins, M)  resample.jl:63-117 ; the rand() draws of :106 supplied in order
+__global__ void __launch_bounds__(BLOCK)
+k_resample_residual(const __grid_constant__ EngineP P, const double* we, const double* u_draws, int M,
+                    long long* j_inout) {
+  __shared__ Shared sh;
+  unsigned bar_target = 0;
+  long long b = (long long)blockIdx.x * P.chunk, e = b + P.chunk;
+  if (e > P.n) e = P.n;
+  if (b > P.n) b = P.n;
+  const long long per = ((long long)M + gridDim.x - 1) / gridDim.x;
+  const long long s0 = (long long)blockIdx.x * per, s1 = s0 + per;
+  WeSrc src;
+  src.w = we; src.mode = 0;
+  src.pm = src.pls = src.inv_s = src.weu = src.wu = 0.0;
+  src.T = nullptr; src.hist_w = nullptr; src.hist_we = nullptr;
+  double total;
+  resample_residual<long long>(P, sh, (int)b, (int)e, bar_target, src, u_draws, 0u, M, j_inout, 1ll, 0,
+                               (int)(s0 < M ? s0 : M), (int)(s1 < M ? s1 : M), total);
+}
+
 // logsumexp!(w, we)  utils.jl:18-27 on caller-provided arrays
 __global__ void __launch_bounds__(BLOCK)
 k_logsumexp(const __grid_constant__ EngineP P, double* w, double* we, double* ll_out) {
@@ -342,7 +363,7 @@ struct llpf_filter {
   // sharding (one process per GPU): IPC-mapped peer arenas
   int rank = 0, world = 1;
   bool connected = false;
-  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0, o_heavy = 0;
+  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0, o_heavy = 0, o_tots2 = 0;
   char* peer_base[MAX_WORLD] = {nullptr};
   // per-run buffers (grow-only)
   double *d_u = nullptr, *d_y = nullptr, *d_ll = nullptr, *d_ess = nullptr, *d_xhat = nullptr;
@@ -364,20 +385,44 @@ struct llpf_filter {
   int w_diagL = 0;
 };
 
+// the k_engine<NX, NY, DYN, RESID> instantiations live in llpf_engine_inst.cu (one translation unit per group of
+// llpf_engine_list.h); this file only sees them as host-side kernel handles
+namespace llpf {
+const void* engine_kernel_group0(int, int, int, int);
+const void* engine_kernel_group1(int, int, int, int);
+const void* engine_kernel_group2(int, int, int, int);
+const void* engine_kernel_group3(int, int, int, int);
+const void* engine_kernel_group4(int, int, int, int);
+const void* engine_kernel_group5(int, int, int, int);
+const void* engine_kernel_group6(int, int, int, int);
+const void* engine_kernel_group7(int, int, int, int);
+}  // namespace llpf
+static_assert(LLPF_INST_GROUPS == 8, "update the group list");
+static const void* engine_kernel(int nx, int ny, int dyn, int resid) {
+  typedef const void* (*group_fn)(int, int, int, int);
+  static const group_fn groups[] = {engine_kernel_group0, engine_kernel_group1, engine_kernel_group2,
+                                    engine_kernel_group3, engine_kernel_group4, engine_kernel_group5,
+                                    engine_kernel_group6, engine_kernel_group7};
+  for (group_fn g : groups)
+    if (const void* k = g(nx, ny, dyn, resid)) return k;
+  return nullptr;
+}
+static int resid_of(const llpf_filter* f);
+
 template <int NX, int NY, int DYN>
 static cudaError_t launch_engine(llpf_filter* f, const EngineP& P) {
   ModelP<NX, NY> M;
   fill_modelp<NX, NY>(f->hm, M);
   EngineP Pc = P;
   void* args[] = {(void*)&Pc, (void*)&M};
-  return cudaLaunchCooperativeKernel((const void*)k_engine<NX, NY, DYN>, dim3(P.nblocks), dim3(BLOCK),
-                                     args, 0, f->stream);
+  const void* k = engine_kernel(NX, NY, DYN, resid_of(f));
+  if (!k) return cudaErrorInvalidDeviceFunction;
+  return cudaLaunchCooperativeKernel(k, dim3(P.nblocks), dim3(BLOCK), args, 0, f->stream);
 }
-template <int NX, int NY, int DYN>
-static int occupancy_engine() {
+static int occupancy_engine(int nx, int ny, int dyn, int resid) {
+  const void* k = engine_kernel(nx, ny, dyn, resid);
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine<NX, NY, DYN>, BLOCK, 0) != cudaSuccess)
-    return 0;
+  if (!k || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, BLOCK, 0) != cudaSuccess) return 0;
   return occ;
 }
 template <int NX>
@@ -462,22 +507,20 @@ static cudaError_t launch_init_wide(llpf_filter* f, uint64_t epoch) {
   return cudaGetLastError();
 }
 
+static int resid_of(const llpf_filter* f) { return f->cfg.resampling == LLPF_RESAMPLE_RESIDUAL ? 1 : 0; }
+
+// host-side half of the dispatch (model packing + init kernel); the device half is llpf_engine_list.h
 struct Dispatch {
   int nx, ny, dyn;
   launch_fn launch;
   init_fn init;
-  occ_fn occ;
 };
 #define DISP(NX, NY, DYN) \
-  { NX, NY, DYN, launch_engine<NX, NY, DYN>, launch_init<NX>, occupancy_engine<NX, NY, DYN> }
+  { NX, NY, DYN, launch_engine<NX, NY, DYN>, launch_init<NX> }
 static const Dispatch g_dispatch[] = {
-#ifdef LLPF_DISPATCH_MIN   // quick tuning builds: only the headline instantiation
-    DISP(4, 2, 0),
-#else
     DISP(1, 1, 0), DISP(2, 1, 0), DISP(2, 2, 0), DISP(3, 1, 0), DISP(3, 2, 0), DISP(3, 3, 0),
     DISP(4, 1, 0), DISP(4, 2, 0), DISP(4, 3, 0), DISP(4, 4, 0), DISP(6, 2, 0), DISP(6, 3, 0),
     DISP(8, 2, 0), DISP(8, 4, 0), DISP(4, 2, 1),
-#endif
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -554,9 +597,12 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   *out = nullptr;
   if (cfg->N < 1 || cfg->N >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "need 1 <= N < 2^31");
   if (cfg->filter < 0 || cfg->filter > 3) return fail(LLPF_ERR_BAD_ARG, "unknown filter kind");
-  if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED)
-    return fail(LLPF_ERR_UNSUPPORTED, "in-loop resampling: systematic or stratified");
+  if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED &&
+      cfg->resampling != LLPF_RESAMPLE_RESIDUAL)
+    return fail(LLPF_ERR_BAD_ARG, "unknown resampling strategy");
   const int world = cfg->world < 1 ? 1 : cfg->world;
+  if (world > 1 && cfg->resampling == LLPF_RESAMPLE_RESIDUAL)
+    return fail(LLPF_ERR_UNSUPPORTED, "residual resampling is single-GPU (sharded filters: systematic or stratified)");
   if (world > MAX_WORLD) return fail(LLPF_ERR_UNSUPPORTED, "at most 8 ranks (one box)");
   if (world > 1) {
     if (cfg->rank < 0 || cfg->rank >= world) return fail(LLPF_ERR_BAD_ARG, "bad rank");
@@ -583,6 +629,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   if (!wide) {
     for (const Dispatch& e : g_dispatch)
       if (e.nx == f->hm.nx && e.ny == f->hm.ny && e.dyn == f->hm.dyn) d = &e;
+    if (d && !engine_kernel(d->nx, d->ny, d->dyn, resid_of(f))) d = nullptr;
     if (!d) {
       delete f;
       return fail(LLPF_ERR_UNSUPPORTED, "no kernel instantiated for this (nx, ny, dynamics)");
@@ -610,7 +657,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
     llpf_destroy(f);
     return fail(LLPF_ERR_UNSUPPORTED, "device lacks cooperative launch");
   }
-  const int occ = wide ? occupancy_engine_wide() : d->occ();
+  const int occ = wide ? occupancy_engine_wide() : occupancy_engine(d->nx, d->ny, d->dyn, resid_of(f));
   if (occ < 1) {
     llpf_destroy(f);
     return fail(LLPF_ERR_CUDA, "engine kernel does not fit on an SM (is this an sm_100a device?)");
@@ -643,6 +690,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const size_t o_mbox = take((size_t)2 * MAX_WORLD * MBOX_WORDS * 8);
   const size_t o_bcast = take((size_t)2 * MAX_WORLD * MBOX_DOUBLES * 8), o_bflag = take(64);
   const size_t o_heavy = take((size_t)(1 + 3 * HEAVY_MAX) * 4);
+  f->o_tots2 = take((size_t)MAX_BLOCKS * 8);
   f->o_x0 = o_x0; f->o_x1 = o_x1; f->o_j = o_j; f->o_mbox = o_mbox; f->o_heavy = o_heavy;
   f->arena_bytes = off;
   CUF(cudaMalloc(&f->arena, f->arena_bytes));
@@ -716,6 +764,7 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
   P.bcast = f->bcast; P.bcast_flag = f->bcast_flag;
   P.heavy = (int*)(f->arena + f->o_heavy);
+  P.tots2 = (u64*)(f->arena + f->o_tots2);
   for (int r = 0; r < f->world; ++r) {
     char* base = f->peer_base[r];
     P.peer_x[r][0] = base ? (double*)(base + f->o_x0) : nullptr;
@@ -1220,6 +1269,52 @@ extern "C" int llpf_resample_stratified(int64_t N, const double* we, const doubl
                                         int64_t* j_inout, double* bins_out, int32_t scan_mode, int32_t device) {
   if (!u01) return fail(LLPF_ERR_BAD_ARG, "u01 is null");
   return resample_standalone(LLPF_RESAMPLE_STRATIFIED, N, we, 0.0, u01, M, j_inout, bins_out, scan_mode, device);
+}
+
+extern "C" int llpf_resample_residual(int64_t N, const double* we, const double* u01, int64_t M, int64_t* j_inout,
+                                      double* bins_out, int32_t scan_mode, int32_t device) {
+  if (N < 1 || M < 1 || !we || !j_inout || !u01) return fail(LLPF_ERR_BAD_ARG, "bad argument");
+  if (N >= (1ll << 31) || M >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "N, M < 2^31");
+  int ndev = 0;
+  OKR(llpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(LLPF_ERR_NO_DEVICE, "no such CUDA device");
+  EngineP P;
+  std::memset(&P, 0, sizeof(P));
+  OKR(standalone_geometry(device, N, P, (const void*)k_resample_residual));
+  Scratchpad sp;
+  double *d_we = nullptr, *d_bins = nullptr, *d_part = nullptr, *d_u = nullptr;
+  u64 *d_tots = nullptr, *d_tots2 = nullptr, *d_loc = nullptr;
+  unsigned* d_bar = nullptr;
+  long long* d_j = nullptr;
+  int* d_heavy = nullptr;
+  CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_bins, (size_t)N)); CU(sp.alloc(&d_part, (size_t)MAX_BLOCKS * PS));
+  CU(sp.alloc(&d_tots, (size_t)MAX_BLOCKS)); CU(sp.alloc(&d_tots2, (size_t)MAX_BLOCKS));
+  CU(sp.alloc(&d_bar, BAR_TOTAL_WORDS)); CU(sp.alloc(&d_j, (size_t)M)); CU(sp.alloc(&d_loc, (size_t)N));
+  CU(sp.alloc(&d_u, (size_t)M)); CU(sp.alloc(&d_heavy, (size_t)(1 + 3 * HEAVY_MAX)));
+  CU(cudaMemcpy(d_we, we, sizeof(double) * N, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_u, u01, sizeof(double) * M, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d_j, j_inout, sizeof(long long) * M, cudaMemcpyHostToDevice));
+  CU(cudaMemset(d_bar, 0, BAR_TOTAL_WORDS * sizeof(unsigned)));
+  CU(cudaMemset(d_heavy, 0, sizeof(int)));
+  double sum = 0.0;
+  for (int64_t i = 0; i < N; ++i) sum += (we[i] > 0 ? we[i] : 0.0);
+  int e = 0;
+  if (sum > 0 && std::isfinite(sum)) std::frexp(sum * (1.0 + 1e-9), &e);   // sum < 2^e
+  if (e < 0) e = 0;
+  P.fix_scale = std::ldexp(1.0, 62 - e);
+  P.fix_inv = std::ldexp(1.0, e - 62);
+  P.heavy = d_heavy;
+  P.bins = d_bins; P.partials = d_part; P.tots = d_tots; P.tots2 = d_tots2; P.bar = d_bar; P.loc = d_loc;
+  P.N = N; P.n = (int)N; P.first = 0; P.strategy = LLPF_RESAMPLE_RESIDUAL; P.scan_mode = scan_mode;
+  P.world = 1;
+  const double* d_u_c = d_u;
+  int Mi = (int)M;
+  void* args[] = {(void*)&P, (void*)&d_we, (void*)&d_u_c, (void*)&Mi, (void*)&d_j};
+  CU(cudaLaunchCooperativeKernel((const void*)k_resample_residual, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(j_inout, d_j, sizeof(long long) * M, cudaMemcpyDeviceToHost));
+  if (bins_out) CU(cudaMemcpy(bins_out, d_bins, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  return LLPF_OK;
 }
 
 extern "C" int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int32_t device) {

@@ -141,6 +141,7 @@ struct EngineP {
   // heavy offspring runs of the current resample: [0] = count, then (first slot, length, id) triples
   int* heavy;
   int* peer_heavy[MAX_WORLD];
+  u64* tots2;             // [MAX_BLOCKS] second per-block total (residual resampling: the integer offspring counts)
 };
 constexpr int MBOX_DOUBLES = 16;  // broadcast-buffer stride per rank ([1..] payload)
 constexpr int MBOX_WORDS = 32;    // mailbox slot: 2 tagged 8-byte words per payload double
@@ -674,15 +675,14 @@ __device__ __forceinline__ bool scan_stage1(const EngineP& P, Shared& sh, int be
 
 // After the grid barrier that follows stage 1 (FAST): exclusive block offsets into sh.offs[0..nb]
 // (exact integer arithmetic: any summation order gives the same bits).
-__device__ __forceinline__ void scan_block_offsets(const EngineP& P, Shared& sh, u64 base_fixed) {
-  const int nb = P.nblocks;
+__device__ __forceinline__ void scan_block_offsets_from(const u64* tots, int nb, Shared& sh, u64 base_fixed) {
   constexpr int PER = (MAX_BLOCKS + BLOCK - 1) / BLOCK;
   u64 t4[PER];
   u64 mine = 0;
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int b = threadIdx.x * PER + k;
-    t4[k] = (b < nb) ? __ldcg(P.tots + b) : 0ull;
+    t4[k] = (b < nb) ? __ldcg(tots + b) : 0ull;
     mine += t4[k];
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -708,9 +708,12 @@ __device__ __forceinline__ void scan_block_offsets(const EngineP& P, Shared& sh,
   }
   __syncthreads();
 }
+__device__ __forceinline__ void scan_block_offsets(const EngineP& P, Shared& sh, u64 base_fixed) {
+  scan_block_offsets_from(P.tots, P.nblocks, sh, base_fixed);
+}
 
 // SERIAL mode: the reference's cumsum (resample.jl:19-22), one thread, strict left-to-right f64 adds.
-__device__ __noinline__ void scan_serial(double* bins, int n) {
+static __device__ __noinline__ void scan_serial(double* bins, int n) {
   double acc = __ldcg(bins);
   int i = 1;
   for (; i + 8 <= n; i += 8) {
@@ -1113,6 +1116,10 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   return f_total;
 }
 
+}  // namespace llpf
+#include "llpf_residual.cuh"   // resample(ResampleResidual, ...) — uses the scan / scatter helpers above
+namespace llpf {
+
 // ------------------------------------------------------------------------------------------------
 // models
 // ------------------------------------------------------------------------------------------------
@@ -1394,7 +1401,9 @@ __device__ __forceinline__ void publish_step(const EngineP& P, Scalars& sc, int 
 
 // ---- PF / AdvancedPF pass: [predict!(k_prop)] fused with [correct!(k_weigh)] -----------------------
 // k_prop / k_weigh are 1-based step numbers, 0 = phase absent.
-template <int NX, int NY, int DYN>
+// RESID != 0: the kernel instantiation for resampling_strategy = ResampleResidual (a separate instantiation, so the
+// systematic / stratified kernels carry none of its code: adding it as a run-time branch cost 2-4 % on resample steps)
+template <int NX, int NY, int DYN, int RESID>
 __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh, Scalars& sc,
                                         Ctx& cx, int k_prop, int k_weigh, int flags) {
   if (flags & OPF_RAW_WEIGHTS) { sc.pend = 0; sc.stats_ahead = 0; }
@@ -1417,7 +1426,20 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   double* const wh = P.w_hist;
   double* const weh = P.we_hist;
   int f_total = 0;
-  if (res) {
+  if constexpr (RESID != 0) {
+   if (res) {   // ResampleResidual  resample.jl:63-117
+    WeSrc rs;
+    rs.w = ws.w; rs.mode = ws.uniform ? 1 : (ws.pend ? 3 : 2);
+    rs.pm = ws.pm; rs.pls = ws.pls; rs.inv_s = ws.inv_s; rs.weu = ws.weu; rs.wu = ws.wu; rs.T = &sh.mt;
+    rs.hist_w = hist_w ? wh + hbase : nullptr;
+    rs.hist_we = hist_w ? weh + hbase : nullptr;
+    double total;
+    resample_residual<int>(P, sh, cx.beg, cx.end, cx.bar_target, rs, nullptr, step_idx, (int)P.N, P.j, P.first,
+                           sc.j_identity, P.first + cx.beg, P.first + cx.end, total);
+    f_total = (int)P.N;
+    sc.bins_total = total;
+   }
+  } else if (res) {
     double total;
     f_total = resample_indices<int>(
         P, sh, cx.beg, cx.end, cx.bar_target,
@@ -1553,7 +1575,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
 // A: xbar = f(x) (no noise) ; lam = logpdf(y1 - C xbar) ; v = w + lam ; expnormalize!(v)  -> W
 // scan(W) -> bins -> j
 // B: x = xbar[j] + L z ; w = lam - log N (UNresampled lam, :210-213) ; stats of the new w == next correct!
-template <int NX, int NY, int DYN>
+template <int NX, int NY, int DYN, int RESID>
 __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh, Scalars& sc,
                                          Ctx& cx, int k, int k_y1) {
   double bu[NX], yt[NY];
@@ -1592,10 +1614,21 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   const MathTab* mtp = &sh.mt;
   // expnormalize!(w): exp(w-offset)*1/(s+1)   utils.jl:57-63 ; then resample (always)  :205
   double total;
-  const int f_total = resample_indices<int>(
-      P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return __ldcg(wraw + i); },
-      [=](int, double wr) { return exp_nonpos(wr - m1, *mtp) * inv1; }, 0.0, true,
-      step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
+  int f_total;
+  if constexpr (RESID != 0) {   // ResampleResidual
+    WeSrc rs;
+    rs.w = wraw; rs.mode = 3;
+    rs.pm = m1; rs.pls = 0.0; rs.inv_s = inv1; rs.weu = 0.0; rs.wu = 0.0; rs.T = mtp;
+    rs.hist_w = nullptr; rs.hist_we = nullptr;
+    resample_residual<int>(P, sh, cx.beg, cx.end, cx.bar_target, rs, nullptr, step_idx, (int)P.N, P.j, P.first,
+                           sc.j_identity, P.first + cx.beg, P.first + cx.end, total);
+    f_total = (int)P.N;
+  } else {
+    f_total = resample_indices<int>(
+        P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return __ldcg(wraw + i); },
+        [=](int, double wr) { return exp_nonpos(wr - m1, *mtp) * inv1; }, 0.0, true,
+        step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
+  }
   sc.bins_total = total;
   const bool with_x = (P.want_xhat != 0);
   const double lN = log((double)P.N);
@@ -1673,7 +1706,7 @@ __device__ __forceinline__ void flush_weight_history(const EngineP& P, Shared& s
   }
 }
 
-template <int NX, int NY, int DYN>
+template <int NX, int NY, int DYN, int RESID>
 __global__ void __launch_bounds__(BLOCK, LLPF_MIN_BLOCKS)
 k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, NY> M) {
   __shared__ Shared sh;
@@ -1708,9 +1741,9 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
       int a = a0 + c * da, b = b0 + c * db, fl = flags;
       asm volatile("" : "+r"(a), "+r"(b), "+r"(fl));   // keep the decoded op in registers (no re-decode per particle)
       if (kind == OP_PF) {
-        pf_pass<NX, NY, DYN>(P, M, sh, sc, cx, a, b, fl);
+        pf_pass<NX, NY, DYN, RESID>(P, M, sh, sc, cx, a, b, fl);
       } else if (kind == OP_AUX_STEP) {
-        aux_step<NX, NY, DYN>(P, M, sh, sc, cx, a, b);
+        aux_step<NX, NY, DYN, RESID>(P, M, sh, sc, cx, a, b);
         if (fl & OPF_POST_CSTATS) aux_correct_from_stats<NX>(P, sc, a + 1);
       } else if (kind == OP_AUX_CSTATS) {
         aux_correct_from_stats<NX>(P, sc, a);

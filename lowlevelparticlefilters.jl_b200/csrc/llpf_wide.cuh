@@ -140,7 +140,17 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
   const WState wst = make_wstate(P, sc, cx, sh.mt);
   const uint32_t step_idx = (uint32_t)sc.t_index;
   int f_total = 0;
-  if (res) {
+  if (res && P.strategy == 2) {   // ResampleResidual  resample.jl:63-117
+    WeSrc rs;
+    rs.w = wst.w; rs.mode = wst.uniform ? 1 : (wst.pend ? 3 : 2);
+    rs.pm = wst.pm; rs.pls = wst.pls; rs.inv_s = wst.inv_s; rs.weu = wst.weu; rs.wu = wst.wu; rs.T = &sh.mt;
+    rs.hist_w = nullptr; rs.hist_we = nullptr;
+    double total;
+    resample_residual<int>(P, sh, cx.beg, cx.end, cx.bar_target, rs, nullptr, step_idx, (int)P.N, P.j, P.first,
+                           sc.j_identity, P.first + cx.beg, P.first + cx.end, total);
+    f_total = (int)P.N;
+    sc.bins_total = total;
+  } else if (res) {
     double total;
     f_total = resample_indices<int>(
         P, sh, cx.beg, cx.end, cx.bar_target,

@@ -531,8 +531,14 @@ def resample(strategy, we, u01, M=None, j0=None, scan_mode="fast", device=0, ret
             raise ValueError("stratified resampling needs M uniforms")
         check(lib, lib.llpf_resample_stratified(N, we.ctypes.data_as(dp), u.ctypes.data_as(dp), M,
                                                  j.ctypes.data_as(_abi.c_int64_p), b.ctypes.data_as(dp), mode, device))
+    elif strategy is ResampleResidual:   # resample.jl:63-117 ; u01[M]: the rand() of :106 in draw order
+        u = np.ascontiguousarray(np.asarray(u01, dtype=np.float64).reshape(-1))
+        if u.size != M:
+            raise ValueError("residual resampling needs M uniforms (only the first M - num are consumed)")
+        check(lib, lib.llpf_resample_residual(N, we.ctypes.data_as(dp), u.ctypes.data_as(dp), M,
+                                               j.ctypes.data_as(_abi.c_int64_p), b.ctypes.data_as(dp), mode, device))
     else:
-        raise NotImplementedError("ResampleResidual is not on the device path")
+        raise TypeError("strategy must be ResampleSystematic, ResampleStratified or ResampleResidual")
     return (j, b) if return_bins else j
 
 

@@ -719,7 +719,14 @@ int orc_shouldresample(const orc_pf* f) {
 
 /* resample(strategy, we, j, bins)  resample.jl:12-15 dispatch; rand() from the counter streams */
 static void resample_dispatch(orc_pf* f, const double* we) {
-  if (f->resampling == LLPF_RESAMPLE_STRATIFIED) {
+  if (f->resampling == LLPF_RESAMPLE_RESIDUAL) {
+    /* draw k (0-based, in the order of the rand() calls at resample.jl:106) = counter k of STREAM_RESID */
+    double* u = (double*)malloc(sizeof(double) * f->N);
+    for (int64_t i = 0; i < f->N; ++i)
+      u[i] = orc_uniform53(f->seed, f->epoch, STREAM_RESID, (uint32_t)f->t, (uint64_t)i);
+    orc_resample_residual(we, f->N, u, f->N, f->j, f->bins);
+    free(u);
+  } else if (f->resampling == LLPF_RESAMPLE_STRATIFIED) {
     double* u = (double*)malloc(sizeof(double) * f->N);
     for (int64_t i = 0; i < f->N; ++i)
       u[i] = orc_uniform53(f->seed, f->epoch, STREAM_STRAT, (uint32_t)f->t, (uint64_t)i);

@@ -182,15 +182,15 @@ def resample_stratified(we, u01, M=None, j0=None):
     return j, bins
 
 
-def resample_residual(we, u01, M=None):
+def resample_residual(we, u01, M=None, j0=None, return_bins=False):
     we = _f64(we)
     N = we.size
     M = N if M is None else M
     u01 = _f64(u01)
-    j = np.zeros(M, dtype=np.int64)
+    j = np.zeros(M, dtype=np.int64) if j0 is None else np.array(j0, dtype=np.int64)
     bins = np.zeros(N)
     lib().orc_resample_residual(_p(we), N, _p(u01), M, j.ctypes.data_as(ip), _p(bins))
-    return j
+    return (j, bins) if return_bins else j
 
 
 def rk4_constant_rhs(c, x0, Ts, supersample=1):

@@ -31,6 +31,12 @@ if __name__ == "__main__":
         for thr in (0.0, 0.1, 1.0):
             run(20, 300, thr)
         run(10, 300, 0.0)
+    elif mode == "residual":
+        for strat in (L.ResampleSystematic, L.ResampleStratified, L.ResampleResidual):
+            print(strat.__name__, flush=True)
+            for thr in (0.1, 1.0):
+                run(20, 300, thr, resampling_strategy=strat)
+            run(20, 300, 0.1, filt="aux", resampling_strategy=strat)
     else:
         for thr in (0.0, 0.1, 1.0):
             run(20, 300, thr)

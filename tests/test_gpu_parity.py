@@ -126,7 +126,65 @@ def test_stratified_matches_oracle(gpu, N, M):
         assert j[1] == 2 and j[2] == 2
 
 
-@pytest.mark.parametrize("kind", ["systematic", "stratified"])
+@pytest.mark.parametrize("N,M", [(5, 5), (10, 10), (777, 777), (4096, 4096), (3000, 1234), (300, 1000), (20_000, 20_000)])
+def test_residual_bit_exact_serial_sums(gpu, N, M):
+    """resample(ResampleResidual) resample.jl:63-117: bit-exact indices AND bins against the reference-order oracle
+    (LLPF_SCAN_SERIAL performs the three sums left to right), draws supplied in the reference's draw order."""
+    L = gpu
+    rng = np.random.default_rng(11 * N + M)
+    for rep in range(2):
+        _, _, we = O.logsumexp(rng.standard_normal(N) * (1 + 2 * rep))
+        u = rng.random(M)
+        j0 = np.full(M, -7, dtype=np.int64)
+        jo, bo = O.resample_residual(we, u, M, j0=j0, return_bins=True)
+        j, b = L.resample(L.ResampleResidual, we, u, M, j0=j0, scan_mode="serial", return_bins=True)
+        assert np.array_equal(b, bo)
+        assert np.array_equal(j, jo)
+        assert j.min() >= 1 and j.max() <= N          # every slot assigned (no stale entry for generic weights)
+
+
+@pytest.mark.parametrize("N", [16, 4096, 1 << 16, 1 << 20])
+def test_residual_fast_scan_dyadic_and_properties(gpu, N):
+    """FAST mode (fixed-point grid sums): with dyadic weights that sum to exactly 1 the counts floor(we*N) and the
+    residuals are exact, so the deterministic part must equal the oracle's bit for bit at any size; the multinomial
+    part is checked by definition (first i with u < bins[i]) against the device's own bins, at full size too."""
+    L = gpu
+    rng = np.random.default_rng(N + 5)
+    k = rng.integers(0, 1 << 12, size=N).astype(np.float64)
+    k[rng.integers(0, N, size=max(1, N // 50))] *= 64
+    k[0] += 2.0 ** np.ceil(np.log2(k.sum())) - k.sum()            # sum is a power of two
+    we = k / k.sum()
+    u = rng.random(N)
+    j, b = L.resample(L.ResampleResidual, we, u, scan_mode="fast", return_bins=True)
+    cnt = np.floor(we * N).astype(np.int64)
+    num = int(cnt.sum())
+    assert np.array_equal(j[:num], np.repeat(np.arange(1, N + 1), cnt))
+    assert np.all(np.diff(b) >= 0) and b[-1] == 1.0
+    resid = we * N - cnt
+    assert np.max(np.abs(b - np.cumsum(resid) / resid.sum())) < 1e-12
+    assert np.array_equal(j[num:], np.searchsorted(b, u[:N - num], side="right") + 1)
+    if N <= 4096:
+        jo, bo = O.resample_residual(we, u, N, return_bins=True)
+        assert np.max(np.abs(b - bo)) < 1e-13
+        assert np.mean(j != jo) < 0.01
+
+
+def test_residual_no_draw_needed_and_stale_slots(gpu):
+    L = gpu
+    # every nw is an integer: num == M, early return (resample.jl:85-87), bins holds the (zero) residuals
+    we = np.array([0.25, 0.5, 0.0, 0.25])
+    for mode in ("serial", "fast"):
+        j, b = L.resample(L.ResampleResidual, we, np.full(4, 0.5), scan_mode=mode, return_bins=True)
+        assert list(j) == [1, 2, 2, 4] and np.all(b == 0)
+    # u >= bins[end] finds no bin: the slot keeps the caller's value (the `break` at :110 never runs)
+    we = np.array([0.3, 0.3, 0.4])
+    u = np.array([2.0, 0.1, 0.5])
+    jo = O.resample_residual(we, u, 3, j0=[9, 9, 9])
+    j = L.resample(L.ResampleResidual, we, u, j0=[9, 9, 9], scan_mode="serial")
+    assert np.array_equal(j, jo) and 9 in list(j)
+
+
+@pytest.mark.parametrize("kind", ["systematic", "stratified", "residual"])
 def test_resample_proportions_on_device(gpu, kind):     # test/runtests.jl:108-143 (fewer draws: launch cost)
     L = gpu
     we = np.array([0.1, 0.5, 0.1, 0.15, 0.15])
@@ -135,6 +193,8 @@ def test_resample_proportions_on_device(gpu, kind):     # test/runtests.jl:108-1
     for _ in range(600):
         if kind == "systematic":
             j = L.resample(L.ResampleSystematic, we, rng.random())
+        elif kind == "residual":
+            j = L.resample(L.ResampleResidual, we, rng.random(5))
         else:
             j = L.resample(L.ResampleStratified, we, rng.random(5))
         counts += np.bincount(j - 1, minlength=5)
@@ -330,6 +390,41 @@ def test_stratified_in_loop(gpu):
     assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
     assert np.array_equal(got["resampled"], ref["resampled"])
     _assert_state_close(L, pf, of)
+
+
+@pytest.mark.parametrize("kind", ["pf", "apf", "advanced"])
+@pytest.mark.parametrize("scan_mode", ["serial", "fast"])
+def test_residual_in_loop(gpu, kind, scan_mode):
+    """ResampleResidual inside predict! (filtering.jl:143 / :205): trajectory parity with the oracle; in serial mode
+    the ancestors of the last resample are identical."""
+    L = gpu
+    N, T = 3000, 60
+    if kind == "advanced":
+        s = quadtank_model()
+        u, y = s.inputs(T), None
+        of = s.oracle_filter(N, seed=8, resampling=2)
+        _, y = of.simulate(u, sim_seed=2)
+        pf = s.advanced_filter(N, seed=8, scan_mode=scan_mode, resampling_strategy=L.ResampleResidual)
+    else:
+        s = lg_model()
+        u, y = _data(s, T, 5)
+        filt = 2 if kind == "apf" else 0
+        of = s.oracle_filter(N, filter=filt, seed=8, resampling=2)
+        pf = s.particle_filter(N, seed=8, scan_mode=scan_mode, resampling_strategy=L.ResampleResidual)
+        if kind == "apf":
+            pf = L.AuxiliaryParticleFilter(pf)
+    got, ref = L.loglik(pf, u, y, epoch=1, details=True), of.loglik(u, y, epoch=1)
+    assert ref["resampled"].sum() >= 5
+    if scan_mode == "serial":
+        assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+        assert np.array_equal(got["resampled"], ref["resampled"])
+        assert np.array_equal(L.ancestors(pf), of.ancestors)
+        _assert_state_close(L, pf, of)
+    else:
+        # re-associated sums may move a count across an integer boundary: a different but equally valid draw
+        assert abs(got["ll"] - ref["ll"]) <= 0.02 * abs(ref["ll"])
+        j = L.ancestors(pf)
+        assert j.min() >= 1 and j.max() <= N
 
 
 def test_always_resample_threshold_one(gpu):   # resample.jl:6

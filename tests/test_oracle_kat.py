@@ -313,6 +313,23 @@ def test_pf_converges_to_kalman_on_config2_model():
     assert abs(ll - kf) < 0.5
 
 
+@pytest.mark.parametrize("resampling", [1, 2])
+def test_stratified_and_residual_in_loop_vs_kalman(resampling):
+    """resampling_strategy = ResampleStratified / ResampleResidual inside predict! (resample.jl:12-15 dispatch):
+    the filter is still consistent with the closed-form Kalman log-likelihood."""
+    s = lg_model(nx=4, nu=2, ny=2, seed=0)
+    T = 60
+    u = np.random.default_rng(1).standard_normal((T, 2))
+    of = s.oracle_filter(8000, seed=9, resampling=resampling)
+    _, y = of.simulate(u, 4)
+    kf = O.kalman_loglik(s.oracle_model(), u, y)
+    r = of.loglik(u, y)
+    assert r["resampled"].sum() > 3
+    assert abs(r["ll"] - kf) < 0.8
+    j = of.ancestors
+    assert j.min() >= 1 and j.max() <= 8000
+
+
 def test_advanced_filter_tracks_state():   # test/runtests.jl:553-599, error bound < 5
     A = np.array([[0.99, 0.1], [0, 0.2]])
     rng = np.random.default_rng(0)
