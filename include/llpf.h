@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LLPF_VERSION 102
+#define LLPF_VERSION 103
 
 /* ---- status codes -------------------------------------------------------------------- */
 enum {
@@ -194,6 +194,22 @@ int llpf_run(llpf_handle h, int64_t T, const double* u, const double* y,
 /* same, with u (nu*T) and y (ny*T) already resident in device memory; nothing is copied H2D */
 int llpf_run_dev(llpf_handle h, int64_t T, const double* u_dev, const double* y_dev,
                  int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out);
+
+/* ---- particle smoother: forward filtering, backward simulation -------------- */
+/* xb, ll = smooth(pf, M, u, y, p)  smoothing.jl:104-107 : forward_trajectory (the N x T history of x, w, we stays in
+   device memory) followed by M backward-simulation trajectories (smoothing.jl:116-143, draw_one_categorical
+   resample.jl:128-152).  xb_out: [T][M][nx] doubles (the reference's M x T Matrix{SVector}, column-major).
+   `out` (may be NULL) receives the forward pass's optional outputs as in llpf_run.  Needs 1 <= M <= N (:122).
+   rand() draws come from the (seed, epoch) counter streams: DESIGN.md "RNG contract", stream 6.
+   Single-GPU, Float64-particle filters.                                                                      */
+int llpf_smooth(llpf_handle h, int64_t T, const double* u, const double* y, int64_t M, uint64_t epoch,
+                double* ll, double* xb_out, const llpf_run_outputs* out);
+/* xb, ll = smooth(pf, xf, wf, wef, ll, M, u, y, p)  smoothing.jl:116-143 with a caller-provided forward history:
+   xf [T][N][nx], wf / wef [T][N] (ParticleFilteringSolution x / w / we, host memory)                        */
+int llpf_smooth_history(llpf_handle h, int64_t T, const double* u, const double* xf, const double* wf,
+                        const double* wef, int64_t M, uint64_t epoch, double* xb_out);
+/* device time of the last backward-simulation kernel (ms, CUDA events on the handle's stream) */
+int llpf_last_smooth_ms(llpf_handle h, float* ms);
 
 /* ---- accessors (PFtypes.jl:296-334) ------------------------------------------------------- */
 int llpf_num_particles(llpf_handle h, int64_t* N);      /* global N                           */

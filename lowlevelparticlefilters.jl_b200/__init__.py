@@ -12,4 +12,5 @@ from .filters import (  # noqa: F401
     ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, connect_shards, correct,
     effective_particles, expweights, forward_trajectory, index, last_run_ms, launch_count, loglik, logsumexp,
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
-    shard_blob, shouldresample, state, update, weighted_mean, weights)
+    shard_blob, shouldresample, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
+    weighted_mean, weights)

@@ -91,6 +91,9 @@ def load_library(path=None):
         "llpf_update": [H, dp, dp, dp, C.c_double, dp],
         "llpf_run": [H, C.c_int64, dp, dp, C.c_int32, C.c_uint64, dp, C.POINTER(RunOutputs)],
         "llpf_run_dev": [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, dp, C.POINTER(RunOutputs)],
+        "llpf_smooth": [H, C.c_int64, dp, dp, C.c_int64, C.c_uint64, dp, dp, C.POINTER(RunOutputs)],
+        "llpf_smooth_history": [H, C.c_int64, dp, dp, dp, dp, C.c_int64, C.c_uint64, dp],
+        "llpf_last_smooth_ms": [H, C.POINTER(C.c_float)],
         "llpf_num_particles": [H, ip],
         "llpf_local_particles": [H, ip, ip],
         "llpf_index": [H, ip],

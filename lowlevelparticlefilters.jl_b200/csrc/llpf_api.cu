@@ -14,6 +14,7 @@
 #include "../../include/llpf.h"
 #include "llpf_engine.cuh"
 #include "llpf_engine_list.h"
+#include "llpf_smooth.cuh"
 #include "llpf_wide.cuh"
 
 using namespace llpf;
@@ -374,7 +375,7 @@ struct llpf_filter {
   Scalars* pin_sc = nullptr;  // pinned staging
   uint64_t epoch = 0;
   long long launches = 0;
-  float last_ms = 0.f;
+  float last_ms = 0.f, last_smooth_ms = 0.f;
   int max_blocks = 1;
   launch_fn launch = nullptr;
   init_fn init = nullptr;
@@ -908,8 +909,14 @@ static int ensure_run_buffers(llpf_filter* f, long long T) {
   return LLPF_OK;
 }
 
+struct DevHistory {   // forward history left on the device for a consumer (the smoother); owner frees
+  double *x = nullptr, *w = nullptr, *we = nullptr;
+  void release() { cudaFree(x); cudaFree(w); cudaFree(we); x = w = we = nullptr; }
+};
+
 static int run_impl(llpf_filter* f, long long T, const double* u_dev, const double* y_dev,
-                    int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out) {
+                    int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out,
+                    DevHistory* keep = nullptr) {
   if (T < 1 || T > (1ll << 30)) return fail(LLPF_ERR_BAD_ARG, "bad T");
   if (f->wide && out && (out->xhat || out->x_hist || out->w_hist || out->we_hist))
     return fail(LLPF_ERR_UNSUPPORTED, "Float32-particle filters: per-step xhat and the x/w/we history are not recorded "
@@ -960,6 +967,14 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
     }
     if (P.resampled) CU(cudaMemsetAsync(f->d_res, 0, sizeof(int) * T, f->stream));
   }
+  if (keep) {
+    if (!xh) { CU(cudaMalloc(&xh, NT * f->hm.nx * 8)); P.x_hist = xh; }
+    if (!wh) {
+      CU(cudaMalloc(&wh, NT * 8));
+      CU(cudaMalloc(&weh, NT * 8));
+      P.w_hist = wh; P.we_hist = weh;
+    }
+  }
 #ifdef LLPF_PHASE_TIMING
   long long* d_dbg = nullptr;
   const char* dump = std::getenv("LLPF_PHASE_DUMP");
@@ -993,7 +1008,11 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
     if (!e) e = cudaStreamSynchronize(f->stream);
     if (e) rc = fail(LLPF_ERR_CUDA, std::string("copying run outputs: ") + cudaGetErrorString(e));
   }
-  cudaFree(xh); cudaFree(wh); cudaFree(weh);
+  if (keep && rc == LLPF_OK) {
+    keep->x = xh; keep->w = wh; keep->we = weh;
+  } else {
+    cudaFree(xh); cudaFree(wh); cudaFree(weh);
+  }
   if (rc) return rc;
   if (ll) *ll = f->hsc.ll_total;
   if (f->hsc.nonfinite) return fail(LLPF_ERR_NONFINITE, "log-likelihood is not finite (weight collapse)");
@@ -1021,6 +1040,167 @@ extern "C" int llpf_run_dev(llpf_handle h, int64_t T, const double* u_dev, const
   CU(cudaSetDevice(h->device));
   OKR(ensure_run_buffers(h, T));
   return run_impl(h, T, u_dev, y_dev, time_convention, epoch, ll, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// particle smoother (FFBS)  smoothing.jl:104-143
+// ------------------------------------------------------------------------------------------------
+struct Scratchpad {  // tiny RAII arena for the stand-alone calls
+  std::vector<void*> ptrs;
+  ~Scratchpad() { for (void* p : ptrs) cudaFree(p); }
+  template <class T>
+  cudaError_t alloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
+__global__ void k_fill_uniform53(double* out, long long n, RngKey key, uint32_t stream, uint32_t step) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = rng_block(key, stream, step, (unsigned long long)i, 0);
+    out[i] = uniform53(r.x, r.y);
+  }
+}
+
+// backward simulation on a forward history resident in device memory; xb_out is host memory [T][M][nx]
+static int smooth_backward(llpf_filter* f, long long T, const double* u_dev, const DevHistory& H, long long M,
+                           uint64_t epoch, double* xb_out) {
+  const long long N = f->N;
+  const int nx = f->hm.nx;
+  if (M < 1 || M > N) return fail(LLPF_ERR_BAD_ARG, "smooth: need 1 <= M <= N (smoothing.jl:122)");
+  Scratchpad sp;
+  double *d_us = nullptr, *d_xb = nullptr;
+  long long* d_j = nullptr;
+  CU(sp.alloc(&d_us, (size_t)M)); CU(sp.alloc(&d_j, (size_t)M)); CU(sp.alloc(&d_xb, (size_t)T * M * nx));
+  CU(cudaMemsetAsync(d_j, 0, sizeof(long long) * M, f->stream));   // resample.jl:14: fresh j = zeros(Int, M)
+  RngKey key{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)epoch << 8};
+  k_fill_uniform53<<<(int)std::min<long long>((M + 255) / 256, 1024), 256, 0, f->stream>>>(d_us, M, key, ST_SMOOTH, 0u);
+  CU(cudaGetLastError());
+  // j = resample(pf.resampling_strategy, wef[:,T], M)   smoothing.jl:124 — the same kernels as the stand-alone entries,
+  // on the filter's own scratch arrays and stream
+  EngineP P;
+  base_params(f, P);
+  P.strategy = f->cfg.resampling;
+  const double* d_weT = H.we + (size_t)(T - 1) * N;
+  int Mi = (int)M;
+  CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * BAR_TOTAL_WORDS, f->stream));
+  if (f->cfg.resampling == LLPF_RESAMPLE_RESIDUAL) {
+    const double* d_us_c = d_us;
+    void* args[] = {(void*)&P, (void*)&d_weT, (void*)&d_us_c, (void*)&Mi, (void*)&d_j};
+    CU(cudaLaunchCooperativeKernel((const void*)k_resample_residual, dim3(P.nblocks), dim3(BLOCK), args, 0, f->stream));
+  } else {
+    double u01 = 0.0;
+    const double* d_slots = nullptr;
+    if (f->cfg.resampling == LLPF_RESAMPLE_SYSTEMATIC) {
+      CU(cudaMemcpyAsync(&u01, d_us, sizeof(double), cudaMemcpyDeviceToHost, f->stream));
+      CU(cudaStreamSynchronize(f->stream));
+    } else {
+      d_slots = d_us;
+    }
+    void* args[] = {(void*)&P, (void*)&d_weT, (void*)&u01, (void*)&d_slots, (void*)&Mi, (void*)&d_j};
+    CU(cudaLaunchCooperativeKernel((const void*)k_resample, dim3(P.nblocks), dim3(BLOCK), args, 0, f->stream));
+  }
+  f->launches += 2;
+  SmoothP S;
+  std::memset(&S, 0, sizeof(S));
+  S.xf = H.x; S.wf = H.w; S.u = u_dev; S.j0 = d_j; S.xb = d_xb;
+  S.N = (int)N; S.M = (int)M; S.T = (int)T;
+  S.Ts = f->cfg.Ts;
+  double ld = 0.0;
+  for (int i = 0; i < nx; ++i) ld += std::log(CMH(f->hm.L1, i, i, nx));
+  S.c0 = -((double)nx * std::log(2 * M_PI) + 2 * ld) / 2;
+  S.key = key;
+  SmoothModelG G;
+  std::memset(&G, 0, sizeof(G));
+  std::vector<double> Winv;
+  inv_lower(f->hm.L1, nx, Winv);
+  for (int r = 0; r < nx; ++r) {
+    for (int c = 0; c < nx; ++c) {
+      if (!f->hm.A.empty()) G.A[r * MAX_NX + c] = CMH(f->hm.A, r, c, nx);
+      G.Winv[r * MAX_NX + c] = CMH(Winv, r, c, nx);
+    }
+    for (int c = 0; c < f->hm.nu; ++c)
+      if (!f->hm.B.empty()) G.B[r * MAX_NU + c] = CMH(f->hm.B, r, c, nx);
+  }
+  if (f->hm.dyn == LLPF_DYN_QUADTANK_RK4) {   // the quadtank coefficients, as fill_modelp packs them
+    const HostModel& hq = f->hm;
+    const double k1 = hq.dynp[1], k2 = hq.dynp[2], Aa = hq.dynp[3], a = hq.dynp[4], g = hq.dynp[5];
+    G.qt[0] = -a / Aa; G.qt[1] = -(a * hq.a1_factor) / Aa; G.qt[2] = a / Aa; G.qt[3] = 2 * 9.81;
+    G.qt[4] = g * k1 / Aa; G.qt[5] = g * k2 / Aa; G.qt[6] = (1 - g) * k2 / Aa; G.qt[7] = (1 - g) * k1 / Aa;
+  }
+  G.t_switch = f->hm.t_switch;
+  G.integ_h = f->hm.integ_Ts / (double)f->hm.supersample;
+  G.supersample = f->hm.supersample;
+  G.nu = f->hm.nu;
+  const int grid = (int)std::min<long long>(M, (long long)f->num_sms * 8);
+  CU(cudaEventRecord(f->ev0, f->stream));
+  CU(smooth_launch(nx, f->hm.dyn, S, G, grid, f->stream));
+  CU(cudaEventRecord(f->ev1, f->stream));
+  f->launches += 1;
+  CU(cudaMemcpyAsync(xb_out, d_xb, sizeof(double) * (size_t)T * M * nx, cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  CU(cudaEventElapsedTime(&f->last_smooth_ms, f->ev0, f->ev1));
+  return LLPF_OK;
+}
+
+static int smooth_supported(llpf_filter* f) {
+  if (f->wide) return fail(LLPF_ERR_UNSUPPORTED, "smooth: Float32-particle filters keep no history");
+  if (f->world > 1) return fail(LLPF_ERR_UNSUPPORTED, "smooth: single-GPU filters only (the history is not sharded)");
+  return LLPF_OK;
+}
+
+extern "C" int llpf_smooth(llpf_handle h, int64_t T, const double* u, const double* y, int64_t M, uint64_t epoch,
+                           double* ll, double* xb_out, const llpf_run_outputs* out) {
+  OKR(check_handle(h));
+  OKR(smooth_supported(h));
+  if (!y || (h->hm.nu > 0 && !u) || !xb_out) return fail(LLPF_ERR_BAD_ARG, "u / y / xb_out is null");
+  if (T < 1) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  if (M < 1 || M > h->N) return fail(LLPF_ERR_BAD_ARG, "smooth: need 1 <= M <= N (smoothing.jl:122)");
+  CU(cudaSetDevice(h->device));
+  OKR(ensure_run_buffers(h, T));
+  if (h->hm.nu > 0)
+    CU(cudaMemcpyAsync(h->d_u, u, sizeof(double) * T * h->hm.nu, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_y, y, sizeof(double) * T * h->hm.ny, cudaMemcpyHostToDevice, h->stream));
+  DevHistory H;
+  // sol = forward_trajectory(pf, u, y, p)   smoothing.jl:105 — the history stays in HBM
+  int rc = run_impl(h, T, h->d_u, h->d_y, LLPF_TIME_FORWARD_TRAJECTORY, epoch, ll, out, &H);
+  if (rc == LLPF_OK) rc = smooth_backward(h, T, h->d_u, H, M, epoch, xb_out);
+  H.release();
+  return rc;
+}
+
+extern "C" int llpf_smooth_history(llpf_handle h, int64_t T, const double* u, const double* xf, const double* wf,
+                                   const double* wef, int64_t M, uint64_t epoch, double* xb_out) {
+  OKR(check_handle(h));
+  OKR(smooth_supported(h));
+  if (!xf || !wf || !wef || (h->hm.nu > 0 && !u) || !xb_out) return fail(LLPF_ERR_BAD_ARG, "null argument");
+  if (T < 1) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  if (M < 1 || M > h->N) return fail(LLPF_ERR_BAD_ARG, "smooth: need 1 <= M <= N (smoothing.jl:122)");
+  CU(cudaSetDevice(h->device));
+  OKR(ensure_run_buffers(h, T));
+  if (h->hm.nu > 0)
+    CU(cudaMemcpyAsync(h->d_u, u, sizeof(double) * T * h->hm.nu, cudaMemcpyHostToDevice, h->stream));
+  DevHistory H;
+  const size_t NT = (size_t)h->N * (size_t)T;
+  int rc = LLPF_OK;
+  cudaError_t e = cudaMalloc(&H.x, NT * h->hm.nx * 8);
+  if (!e) e = cudaMalloc(&H.w, NT * 8);
+  if (!e) e = cudaMalloc(&H.we, NT * 8);
+  if (!e) e = cudaMemcpyAsync(H.x, xf, NT * h->hm.nx * 8, cudaMemcpyHostToDevice, h->stream);
+  if (!e) e = cudaMemcpyAsync(H.w, wf, NT * 8, cudaMemcpyHostToDevice, h->stream);
+  if (!e) e = cudaMemcpyAsync(H.we, wef, NT * 8, cudaMemcpyHostToDevice, h->stream);
+  if (e) rc = fail(LLPF_ERR_CUDA, std::string("smooth: staging the history: ") + cudaGetErrorString(e));
+  if (rc == LLPF_OK) rc = smooth_backward(h, T, h->d_u, H, M, epoch, xb_out);
+  H.release();
+  return rc;
+}
+
+extern "C" int llpf_last_smooth_ms(llpf_handle h, float* ms) {
+  OKR(check_handle(h));
+  if (!ms) return fail(LLPF_ERR_BAD_ARG, "null");
+  *ms = h->last_smooth_ms;
+  return LLPF_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1183,16 +1363,6 @@ extern "C" int llpf_weighted_mean(llpf_handle h, double* xhat) {
 // ------------------------------------------------------------------------------------------------
 // stand-alone numerics
 // ------------------------------------------------------------------------------------------------
-struct Scratchpad {  // tiny RAII arena for the stand-alone calls
-  std::vector<void*> ptrs;
-  ~Scratchpad() { for (void* p : ptrs) cudaFree(p); }
-  template <class T>
-  cudaError_t alloc(T** p, size_t count) {
-    cudaError_t e = cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
-    if (e == cudaSuccess) ptrs.push_back(*p);
-    return e;
-  }
-};
 
 static int standalone_geometry(int device, long long n, EngineP& P, const void* kernel) {
   CU(cudaSetDevice(device));

@@ -20,7 +20,7 @@
 
 namespace llpf {
 
-enum : uint32_t { ST_INIT = 0, ST_DYN = 1, ST_RESAMPLE = 2, ST_STRAT = 3, ST_RESID = 4 };
+enum : uint32_t { ST_INIT = 0, ST_DYN = 1, ST_RESAMPLE = 2, ST_STRAT = 3, ST_RESID = 4, ST_SMOOTH = 6 };   // 5: data simulation (oracle)
 
 struct RngKey {
   uint32_t k0, k1;    // seed

@@ -433,6 +433,70 @@ def mode_trajectory(sol):
 
 
 # ---------------------------------------------------------------------------------------------
+# particle smoother (FFBS)  smoothing.jl:104-143, helpers :350-385
+# ---------------------------------------------------------------------------------------------
+def smooth(pf, *args, p=None, epoch=None):
+    """xb, ll = smooth(pf, M, u, y)                       smoothing.jl:104-107
+       xb, ll = smooth(pf, xf, wf, wef, ll, M, u, y)      smoothing.jl:116-143
+    xb is [T][M][nx] (the reference's M x T matrix of state vectors, column-major).  The forward history never
+    leaves the device in the first form."""
+    if len(args) == 3:
+        M, u, y = args
+        u, up, y, yp, T = _traj_inputs(pf, u, y)
+        if epoch is None:
+            pf._epoch += 1
+            epoch = pf._epoch
+        else:
+            pf._epoch = int(epoch)
+        xb = np.zeros((T, int(M), pf.nx))
+        ll = C.c_double()
+        check(pf._lib, pf._lib.llpf_smooth(pf._h, T, up, yp, int(M), int(epoch), C.byref(ll), xb.ctypes.data_as(dp),
+                                           None))
+        return xb, ll.value
+    if len(args) == 7:
+        xf, wf, wef, ll, M, u, y = args
+        xf = np.ascontiguousarray(np.asarray(xf, dtype=np.float64))
+        wf = np.ascontiguousarray(np.asarray(wf, dtype=np.float64))
+        wef = np.ascontiguousarray(np.asarray(wef, dtype=np.float64))
+        T = wf.shape[0]
+        if xf.shape != (T, pf.N_global, pf.nx) or wf.shape != (T, pf.N_global) or wef.shape != wf.shape:
+            raise ValueError("history must be x [T][N][nx], w / we [T][N]")
+        if pf.nu > 0:
+            u = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(T, pf.nu))
+            up = u.ctypes.data_as(dp)
+        else:
+            up = C.cast(None, dp)
+        epoch = pf._epoch if epoch is None else int(epoch)
+        xb = np.zeros((T, int(M), pf.nx))
+        check(pf._lib, pf._lib.llpf_smooth_history(pf._h, T, up, xf.ctypes.data_as(dp), wf.ctypes.data_as(dp),
+                                                   wef.ctypes.data_as(dp), int(M), epoch, xb.ctypes.data_as(dp)))
+        return xb, ll
+    raise TypeError("smooth(pf, M, u, y) or smooth(pf, xf, wf, wef, ll, M, u, y)")
+
+
+def last_smooth_ms(pf):
+    ms = C.c_float()
+    check(pf._lib, pf._lib.llpf_last_smooth_ms(pf._h, C.byref(ms)))
+    return ms.value
+
+
+def smoothed_mean(xb):
+    """smoothed_mean(xb)  smoothing.jl:356-361 -> nx x T"""
+    return np.asarray(xb).mean(axis=1).T
+
+
+def smoothed_cov(xb):
+    """smoothed_cov(xb)  smoothing.jl:368-372 -> list of T (nx x nx) sample covariances over the M trajectories"""
+    xb = np.asarray(xb)
+    return [np.atleast_2d(np.cov(xb[t].T)) for t in range(xb.shape[0])]
+
+
+def smoothed_trajs(xb):
+    """smoothed_trajs(xb)  smoothing.jl:379-383 -> (nx, M, T) array"""
+    return np.ascontiguousarray(np.transpose(np.asarray(xb), (2, 1, 0)))
+
+
+# ---------------------------------------------------------------------------------------------
 # accessors (PFtypes.jl:296-334)
 # ---------------------------------------------------------------------------------------------
 def num_particles(pf):

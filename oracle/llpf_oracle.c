@@ -37,7 +37,7 @@
  * RNG contract (ours, not the reference's)
  * ---------------------------------------------------------------------------------------- */
 enum { STREAM_INIT = 0, STREAM_DYN = 1, STREAM_RESAMPLE = 2, STREAM_STRAT = 3, STREAM_RESID = 4,
-       STREAM_SIM = 5 };
+       STREAM_SIM = 5, STREAM_SMOOTH = 6 };
 
 static inline void philox_round(uint32_t c[4], const uint32_t k[2]) {
   const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
@@ -880,6 +880,97 @@ double orc_loglik(orc_pf* f, int64_t T, const double* u, const double* y, uint64
 }
 
 /* accessors */
+/* ------------------------------------------------------------------------------------------
+ * particle smoother: forward filtering, backward simulation   src/smoothing.jl:104-143
+ * ---------------------------------------------------------------------------------------- */
+/* logpdf(df, x, xp, t) = logpdf(df, x - xp)  ext/...DistributionsExt.jl:15 ; the Gaussian as in utils.jl:252-257 */
+static double dyn_logpdf(const orc_pf* f, double c0_dyn, const double* r) {
+  double v[64];
+  const int n = f->nx;
+  double q = 0;
+  for (int i = 0; i < n; ++i) {
+    double acc = r[i];
+    for (int k = 0; k < i; ++k) acc -= CM(f->L1, i, k, n) * v[k];
+    v[i] = acc / CM(f->L1, i, i, n);
+    q += v[i] * v[i];
+  }
+  return c0_dyn - q / 2;
+}
+
+/* draw_one_categorical(pf, w)  resample.jl:128-152 : w are LOG-weights (normalised in place by logsumexp!),
+   bins <- cumsum(exp weights), s = rand()*bins[end], two-sided linear search around the midpoint. 1-based result. */
+static int64_t draw_one_categorical(double* w, double* bins, int64_t N, double u01) {
+  orc_logsumexp(w, bins, N, NULL);
+  for (int64_t i = 1; i < N; ++i) bins[i] += bins[i - 1];
+  const double s = u01 * bins[N - 1];
+  const int64_t midpoint = N / 2;                        /* 1-based index length(bins)÷2 */
+  if (midpoint >= 1 && s < bins[midpoint - 1]) {
+    for (int64_t b = 1; b <= midpoint; ++b)
+      if (s <= bins[b - 1]) return b;
+  } else {
+    for (int64_t b = (midpoint >= 1 ? midpoint : 1); b <= N; ++b)
+      if (s <= bins[b - 1]) return b;
+  }
+  return N;
+}
+
+/* smooth(pf, xf, wf, wef, ll, M, u, y, p)  smoothing.jl:116-143.
+   xf [T][N][nx], wf / wef [T][N] (the ParticleFilteringSolution fields), xb out [T][M][nx] (M x T Matrix{SVector}).
+   rand() draws: the initial resample uses counter step 0 of STREAM_SMOOTH with the strategy's usual indexing
+   (systematic: index 0; stratified: slot i; residual: draw k); draw_one_categorical at (t, m), t 1-based: step t,
+   index m (0-based).  Returns 0, or LLPF_ERR_BAD_ARG when M > N (the reference asserts, :122). */
+int orc_smooth(orc_pf* f, int64_t T, int64_t M, const double* u, const double* xf, const double* wf,
+               const double* wef, uint64_t epoch, double* xb) {
+  const int64_t N = f->N;
+  const int nx = f->nx;
+  if (M > N || M < 1 || T < 1) return LLPF_ERR_BAD_ARG;
+  double ld = 0;
+  for (int i = 0; i < nx; ++i) ld += log(CM(f->L1, i, i, nx));
+  ld *= 2;
+  const double c0_dyn = -((double)nx * log(2 * M_PI) + ld) / 2;
+  /* j = resample(pf.resampling_strategy, wef[:,T], M)  :124 -> resample.jl:14 (fresh j = zeros(Int,M), bins = zeros(N)) */
+  int64_t* j = (int64_t*)calloc((size_t)M, sizeof(int64_t));
+  double* bins = (double*)calloc((size_t)N, sizeof(double));
+  const double* weT = wef + (size_t)(T - 1) * N;
+  if (f->resampling == LLPF_RESAMPLE_SYSTEMATIC) {
+    orc_resample_systematic(weT, N, orc_uniform53(f->seed, epoch, STREAM_SMOOTH, 0, 0), M, j, bins);
+  } else {
+    double* us = (double*)malloc(sizeof(double) * (size_t)M);
+    for (int64_t i = 0; i < M; ++i) us[i] = orc_uniform53(f->seed, epoch, STREAM_SMOOTH, 0, (uint64_t)i);
+    if (f->resampling == LLPF_RESAMPLE_STRATIFIED) orc_resample_stratified(weT, N, us, M, j, bins);
+    else orc_resample_residual(weT, N, us, M, j, bins);
+    free(us);
+  }
+  for (int64_t i = 0; i < M; ++i) {
+    /* a slot the resampler left untouched holds 0 (zeros(Int,M)): xf[0,T] is a BoundsError in the reference;
+       the restatement takes the last particle instead (cannot happen for weights that sum to one) */
+    const int64_t a = (j[i] >= 1 && j[i] <= N) ? j[i] : N;
+    memcpy(xb + ((size_t)(T - 1) * M + i) * nx, xf + ((size_t)(T - 1) * N + (a - 1)) * nx, sizeof(double) * nx);
+  }
+  double* wb = (double*)malloc(sizeof(double) * (size_t)N);
+  double* fx = (double*)malloc(sizeof(double) * (size_t)N * nx);
+  double r[64];
+  for (int64_t t = T - 1; t >= 1; --t) {                 /* t is the reference's 1-based index, :130 */
+    const double ti = (double)(t - 1) * f->Ts;           /* :131 */
+    const double* ut = u + (size_t)(t - 1) * f->nu;
+    const double* xft = xf + (size_t)(t - 1) * N * nx;
+    const double* wft = wf + (size_t)(t - 1) * N;
+    /* f(xf[n,t],u[t],p,ti) does not depend on m: evaluated once per n (same values as the reference's M evaluations) */
+    for (int64_t n = 0; n < N; ++n) dynamics_mean(f, xft + (size_t)n * nx, ut, ti, fx + (size_t)n * nx);
+    for (int64_t m = 0; m < M; ++m) {
+      const double* xbn = xb + ((size_t)t * M + m) * nx; /* xb[m,t+1] */
+      for (int64_t n = 0; n < N; ++n) {
+        for (int k = 0; k < nx; ++k) r[k] = xbn[k] - fx[(size_t)n * nx + k];
+        wb[n] = wft[n] + dyn_logpdf(f, c0_dyn, r);       /* :135 */
+      }
+      const int64_t i = draw_one_categorical(wb, bins, N, orc_uniform53(f->seed, epoch, STREAM_SMOOTH, (uint32_t)t, (uint64_t)m));
+      memcpy(xb + ((size_t)(t - 1) * M + m) * nx, xft + (size_t)(i - 1) * nx, sizeof(double) * nx);   /* :139 */
+    }
+  }
+  free(wb); free(fx); free(j); free(bins);
+  return LLPF_OK;
+}
+
 int64_t orc_num_particles(const orc_pf* f) { return f->N; }
 int64_t orc_index(const orc_pf* f) { return f->t; }
 double* orc_particles(orc_pf* f) { return f->x; }

@@ -93,6 +93,8 @@ def lib():
         L.orc_resample_stratified.restype = None
         L.orc_resample_residual.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, dp]
         L.orc_resample_residual.restype = C.c_int64
+        L.orc_smooth.argtypes = [H, C.c_int64, C.c_int64, dp, dp, dp, dp, C.c_uint64, dp]
+        L.orc_smooth.restype = C.c_int
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.orc_philox4x32_10.restype = None
         L.orc_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, dp]
@@ -360,6 +362,17 @@ class OracleFilter:
                               out["resampled"].ctypes.data_as(i32p))
         out["ll"] = ll
         return out
+
+    def smooth(self, M, u, xf, wf, wef, epoch=0):
+        """smooth(pf, xf, wf, wef, ll, M, u, y)  smoothing.jl:116-143 -> xb [T][M][nx]"""
+        xf, wf, wef = _f64(xf), _f64(wf), _f64(wef)
+        T = wf.reshape(-1, self.N).shape[0]
+        u = _f64(u).reshape(-1, max(self.nu, 1))
+        xb = np.zeros((T, M, self.nx))
+        rc = lib().orc_smooth(self.h, T, M, _p(np.ascontiguousarray(u)), _p(xf), _p(wf), _p(wef), epoch, _p(xb))
+        if rc:
+            raise RuntimeError(f"orc_smooth failed: {rc}")
+        return xb
 
     def simulate(self, u, sim_seed=1):
         u = _f64(u).reshape(-1, max(self.nu, 1))

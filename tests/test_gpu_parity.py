@@ -637,6 +637,100 @@ def test_f32_wide_unsupported_combinations_fail_loudly(gpu):
         lg_large_model(65, 2, 4).particle_filter(64)    # nx > 64
 
 
+# ---------------------------------------------------------------------------------------------
+# particle smoother (FFBS)  smoothing.jl:104-143  
+# ---------------------------------------------------------------------------------------------
+def _traj_mismatch(xb, ref, tol=0.0):
+    """fraction of (t, m) entries that differ (a backward draw that flips changes the rest of that trajectory)"""
+    return float(np.mean(np.any(np.abs(xb - ref) > tol, axis=2)))
+
+
+@pytest.mark.parametrize("nx,nu,ny,N,T,M,strategy", [(4, 2, 2, 500, 40, 32, 0), (2, 1, 1, 5000, 30, 100, 0),
+                                                      (3, 2, 2, 777, 25, 777, 1), (6, 2, 3, 1000, 20, 50, 2),
+                                                      (1, 1, 1, 64, 50, 64, 0), (8, 2, 4, 2048, 12, 33, 0)])
+def test_smoother_backward_pass_matches_oracle_on_identical_history(gpu, nx, nu, ny, N, T, M, strategy):
+    """smooth(pf, xf, wf, wef, ll, M, u, y) with the ORACLE's forward history as input: the backward simulation on
+    identical inputs and identical rand() draws picks the same particles (bit-equal rows of xf)."""
+    L = gpu
+    s = lg_model(nx, nu, ny, seed=2)
+    u, y = _data(s, T, 3)
+    strat = [L.ResampleSystematic, L.ResampleStratified, L.ResampleResidual][strategy]
+    of = s.oracle_filter(N, seed=6, resampling=strategy)
+    sol = of.forward_trajectory(u, y, epoch=4, history=True)
+    ref = of.smooth(M, u, sol["x"], sol["w"], sol["we"], epoch=4)
+    pf = s.particle_filter(N, seed=6, scan_mode="serial", resampling_strategy=strat)
+    xb, ll = L.smooth(pf, sol["x"], sol["w"], sol["we"], sol["ll"], M, u, y, epoch=4)
+    assert xb.shape == (T, M, nx) and ll == sol["ll"]
+    assert _traj_mismatch(xb, ref) <= 0.002
+    assert np.array_equal(xb[-1], ref[-1])                     # the resample at T is bit-exact (serial scan)
+    assert L.last_smooth_ms(pf) > 0
+
+
+def test_smoother_end_to_end_matches_oracle(gpu):
+    """xb, ll = smooth(pf, M, u, y): forward pass on the device (history stays in HBM) + backward simulation."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    N, T, M = 2000, 60, 100                                    # test/runtests.jl:264-333 uses N=2000, M=100
+    u, y = _data(s, T, 9)
+    of = s.oracle_filter(N, seed=3)
+    sol = of.forward_trajectory(u, y, epoch=2, history=True)
+    ref = of.smooth(M, u, sol["x"], sol["w"], sol["we"], epoch=2)
+    pf = s.particle_filter(N, seed=3, scan_mode="serial")
+    xb, ll = L.smooth(pf, M, u, y, epoch=2)
+    assert abs(ll - sol["ll"]) <= LL_RTOL_TIGHT * abs(sol["ll"])
+    assert _traj_mismatch(xb, ref, tol=1e-9) <= 0.01
+    # helpers smoothing.jl:350-385
+    assert L.smoothed_mean(xb).shape == (4, T) and L.smoothed_trajs(xb).shape == (4, M, T)
+    assert len(L.smoothed_cov(xb)) == T and L.smoothed_cov(xb)[0].shape == (4, 4)
+    # APF forward pass + the same backward simulation (test/runtests.jl:319)
+    apf = L.AuxiliaryParticleFilter(s.particle_filter(N, seed=3, scan_mode="serial"))
+    oa = s.oracle_filter(N, filter=2, seed=3)
+    sola = oa.forward_trajectory(u, y, epoch=2, history=True)
+    refa = oa.smooth(M, u, sola["x"], sola["w"], sola["we"], epoch=2)
+    xba, lla = L.smooth(apf, M, u, y, epoch=2)
+    assert abs(lla - sola["ll"]) <= LL_RTOL_TIGHT * abs(sola["ll"])
+    assert _traj_mismatch(xba, refa, tol=1e-9) <= 0.01
+
+
+def test_smoother_quadtank_and_errors(gpu):
+    L = gpu
+    q = quadtank_model()
+    N, T, M = 1024, 30, 40
+    u = q.inputs(T)
+    of = q.oracle_filter(N, seed=4)
+    _, y = of.simulate(u, 9)
+    sol = of.forward_trajectory(u, y, epoch=2, history=True)
+    ref = of.smooth(M, u, sol["x"], sol["w"], sol["we"], epoch=2)
+    pf = q.advanced_filter(N, seed=4, scan_mode="serial")
+    xb, _ = L.smooth(pf, sol["x"], sol["w"], sol["we"], sol["ll"], M, u, y, epoch=2)
+    assert _traj_mismatch(xb, ref) <= 0.005
+    with pytest.raises(L.LLPFError):                           # @assert M <= N   smoothing.jl:122
+        L.smooth(pf, N + 1, u, y)
+
+
+def test_smoother_large_properties(gpu):
+    """Beyond oracle size (N = 2^16, M = 256): every smoothed state is a filtered particle of its step, trajectories are
+    distinct draws, and the smoothed mean is at least as close to the truth as the filter mean."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    N, T, M = 1 << 16, 40, 256
+    u = np.random.default_rng(2).standard_normal((T, 2))
+    gen = s.oracle_filter(64, seed=1)
+    xs, y = gen.simulate(u, 11)
+    pf = s.particle_filter(N, seed=3)
+    sol = L.forward_trajectory(pf, u, y, epoch=5)
+    xb, ll = L.smooth(pf, sol.x, sol.w, sol.we, sol.ll, M, u, y, epoch=5)
+    for t in (0, T // 2, T - 1):
+        keys = {row.tobytes() for row in sol.x[t]}
+        assert all(xb[t, m].tobytes() in keys for m in range(M))
+    assert len({xb[0, m].tobytes() for m in range(M)}) > M // 4
+    err_f = np.mean((L.mean_trajectory(sol) - xs) ** 2)
+    err_s = np.mean((xb.mean(axis=1) - xs) ** 2)
+    assert err_s < 1.05 * err_f
+    xb2, ll2 = L.smooth(pf, M, u, y, epoch=5)                  # same seed/epoch -> same forward pass -> same draws
+    assert ll2 == sol.ll and np.array_equal(xb2, xb)
+
+
 def test_full_size_config2_properties(gpu):
     """N = 2^20 (BASELINE config 2 particle count), T = 100: the oracle is too slow here, so check
     size-independent properties: the log-likelihood converges to the closed-form Kalman filter

@@ -383,3 +383,59 @@ def test_oracle_f32_loglik_vs_kalman():
     ll = of.loglik(u, y, epoch=1)["ll"]
     kf = O.kalman_loglik(s.oracle_model(), u, y)
     assert abs(ll - kf) < 8.0, (ll, kf)
+
+
+# ---- particle smoother (FFBS)  smoothing.jl:104-143 ; test/runtests.jl:264-333 ----------------------------------
+def _py_smooth(of, M, u, xf, wf, wef, uni0, uni):
+    """Independent NumPy restatement of smoothing.jl:116-143 + resample.jl:128-152 (systematic initial resample)."""
+    T, N, nx = xf.shape
+    m = of.model
+    L1 = np.linalg.cholesky(np.asarray(m.R1).reshape(nx, nx))
+    c0 = -(nx * np.log(2 * np.pi) + 2 * np.log(np.diag(L1)).sum()) / 2
+    j, _ = O.resample_systematic(wef[T - 1], uni0, M, j0=np.zeros(M, dtype=np.int64))
+    xb = np.zeros((T, M, nx))
+    xb[T - 1] = xf[T - 1][j - 1]
+    for t in range(T - 1, 0, -1):                      # reference's 1-based t
+        fx = np.array([of.dynamics(xf[t - 1, n], u[t - 1], (t - 1) * 1.0) for n in range(N)])
+        for mm in range(M):
+            r = xb[t, mm][None, :] - fx
+            v = np.linalg.solve(L1, r.T).T
+            wb = wf[t - 1] + c0 - 0.5 * (v * v).sum(axis=1)
+            _, _, we = O.logsumexp(wb)
+            bins = np.cumsum(we)
+            s = uni[t, mm] * bins[-1]
+            i = int(np.searchsorted(bins, s, side="left"))
+            xb[t - 1, mm] = xf[t - 1, min(i, N - 1)]
+    return xb
+
+
+def test_smoother_matches_numpy_restatement():
+    s = lg_model(nx=2, nu=1, ny=1, seed=3)
+    N, T, M = 60, 12, 7
+    u = np.random.default_rng(0).standard_normal((T, 1))
+    of = s.oracle_filter(N, seed=4)
+    _, y = of.simulate(u, 5)
+    sol = of.forward_trajectory(u, y, epoch=1, history=True)
+    xb = of.smooth(M, u, sol["x"], sol["w"], sol["we"], epoch=1)
+    uni0 = O.uniform53(4, 1, 6, 0, 0)
+    uni = np.array([[O.uniform53(4, 1, 6, t, mm) for mm in range(M)] for t in range(T)])
+    ref = _py_smooth(of, M, u, sol["x"], sol["w"], sol["we"], uni0, uni)
+    assert np.array_equal(xb, ref)
+    # every smoothed state is one of the filtered particles of its time step
+    for t in range(T):
+        for mm in range(M):
+            assert np.any(np.all(sol["x"][t] == xb[t, mm], axis=1))
+
+
+def test_smoother_improves_on_filter_mean():   # the (disabled) expectation at test/runtests.jl:346, on an easy model
+    s = lg_model(nx=2, nu=1, ny=1, seed=3)
+    N, T, M = 300, 60, 40
+    u = np.random.default_rng(1).standard_normal((T, 1))
+    of = s.oracle_filter(N, seed=2)
+    xs, y = of.simulate(u, 8)
+    sol = of.forward_trajectory(u, y, epoch=1, history=True)
+    xb = of.smooth(M, u, sol["x"], sol["w"], sol["we"], epoch=1)
+    xf_mean = np.einsum("tnd,tn->td", sol["x"], sol["we"])
+    err_f = np.mean((xf_mean - xs) ** 2)
+    err_s = np.mean((xb.mean(axis=1) - xs) ** 2)
+    assert err_s < 1.1 * err_f
