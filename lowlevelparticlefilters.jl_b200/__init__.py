@@ -14,3 +14,6 @@ from .filters import (  # noqa: F401
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
     shard_blob, shouldresample, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
     weighted_mean, weights)
+from .estimation import (  # noqa: F401
+    Normal, Uniform, log_likelihood_fun, metropolis, metropolis_threaded, naive_sampler, set_model, weighted_cov,
+    weighted_quantile)

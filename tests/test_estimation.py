@@ -1,0 +1,117 @@
+"""Host-side logic around the hot path: PMMH driver (smoothing.jl:266-347) and weighted statistics
+(filtering.jl:570-595).  CPU tests use analytic log-likelihoods; the GPU tests drive the device `loglik`."""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import llpf_b200 as L  # noqa: E402
+from models import lg_model  # noqa: E402
+
+
+def test_weighted_quantile_and_cov_reduce_to_plain_statistics():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 101, 2))
+    we = np.full((3, 101), 1 / 101)
+    for q in (0.1, 0.5, 0.9):
+        assert np.allclose(L.weighted_quantile(x, we, q), np.quantile(x, q, axis=1))
+    cov = L.weighted_cov(x, we)
+    for t in range(3):
+        assert np.allclose(cov[t], np.cov(x[t].T))
+    # zero-weight samples are ignored; a point mass gives that point
+    w2 = np.zeros((1, 5)); w2[0, 3] = 1.0
+    xs = np.arange(5.0).reshape(1, 5, 1)
+    assert L.weighted_quantile(xs, w2, 0.3)[0, 0] == 3.0
+    # integer-ratio weights == repeated samples (ProbabilityWeights interpolate on cumulative weight)
+    v = np.array([1.0, 2.0, 4.0]).reshape(1, 3, 1)
+    w = np.array([[0.25, 0.25, 0.5]])
+    assert L.weighted_quantile(v, w, 0.0)[0, 0] == 1.0 and L.weighted_quantile(v, w, 1.0)[0, 0] == 4.0
+
+
+def test_metropolis_samples_a_gaussian_target():
+    rng = np.random.default_rng(1)
+    target = lambda th: -0.5 * float(((th[0] - 1.5) / 0.3) ** 2)
+    draw = lambda th: th + 0.3 * rng.standard_normal(1)
+    p, l = L.metropolis(target, 6000, np.array([0.5]), draw, rng)
+    assert p.shape == (6000, 1) and l.shape == (6000,)
+    assert abs(p[1000:].mean() - 1.5) < 0.05 and abs(p[1000:].std() - 0.3) < 0.05
+    assert np.all(l == np.array([target(t) for t in p]))            # the stored ll belongs to the stored sample
+    with pytest.raises(ValueError):
+        L.naive_sampler(np.array([0.0, 1.0]))
+
+
+def test_log_likelihood_fun_prior_short_circuit_and_threads():
+    calls = []
+
+    class FakePF:
+        pass
+
+    def ffp(theta, pf=None):
+        calls.append(pf)
+        return FakePF()
+
+    ll = L.log_likelihood_fun(ffp, [L.Uniform(0, 1)], None, None)
+    assert ll(np.array([2.0])) == -math.inf and calls == []        # outside the prior: the filter is never built
+    with pytest.raises(ValueError):
+        ll(np.array([0.1, 0.2]))
+    target = lambda th: -0.5 * float((th[0] / 0.5) ** 2)
+    out = L.metropolis_threaded(100, target, 400, np.array([0.3]), None, nthreads=3, seed=5)
+    assert out.shape == (3 * 300, 2)
+    assert np.allclose(out[:, 1], -0.5 * (out[:, 0] / 0.5) ** 2)
+
+
+# ---- on the device ------------------------------------------------------------------------------------------------
+def _pmmh_problem(T=100, dims=(2, 1, 1)):
+    s = lg_model(*dims, seed=3 if dims == (2, 1, 1) else 0)
+    u = np.random.default_rng(0).standard_normal((T, dims[1]))
+    gen = s.oracle_filter(16, seed=1)
+    _, y = gen.simulate(u, 7)
+    return s, u, y
+
+
+@pytest.mark.gpu
+def test_set_model_equals_fresh_filter(gpu):
+    s, u, y = _pmmh_problem()
+    pf = s.particle_filter(1000, seed=2)
+    a = L.loglik(pf, u, y, epoch=1)
+    L.set_model(pf, dynamics_density=L.MvNormal(0.25 * np.eye(2)), measurement_density=L.MvNormal(2.0 * np.eye(1)))
+    b = L.loglik(pf, u, y, epoch=1)
+    s2 = lg_model(2, 1, 1, seed=3, r1=0.25, r2=2.0)
+    c = L.loglik(s2.particle_filter(1000, seed=2), u, y, epoch=1)
+    assert b == c and a != b
+
+
+@pytest.mark.gpu
+def test_pmmh_on_device_finds_the_noise_level(gpu):
+    """example_lineargaussian.jl:195-223 in miniature: θ = log of the dynamics / measurement noise variances, the data
+    were simulated with variances (1, 1): the chain concentrates around θ = 0."""
+    s, u, y = _pmmh_problem(T=200, dims=(2, 2, 2))
+    Np = 2000
+
+    def ffp(theta, pf=None):
+        d1, d2 = L.MvNormal(math.exp(theta[0]) * np.eye(2)), L.MvNormal(math.exp(theta[1]) * np.eye(2))
+        if pf is None:
+            return L.ParticleFilter(Np, L.LinearDynamics(s.A, s.B), L.LinearMeasurement(s.C), d1, d2,
+                                    L.MvNormal(s.mu0, s.Sigma0), seed=4)
+        return L.set_model(pf, dynamics_density=d1, measurement_density=d2)
+
+    priors = [L.Normal(0, 1.0), L.Normal(0, 1.0)]
+    ll = L.log_likelihood_fun(ffp, priors, u, y)
+    rng = np.random.default_rng(3)
+    draw = lambda th: th + 0.1 * rng.standard_normal(2)
+    p, l = L.metropolis(ll, 500, np.array([0.5, -0.5]), draw, rng)
+    assert np.all(np.isfinite(l))
+    post = p[150:]
+    accept = np.mean(np.any(np.diff(p, axis=0) != 0, axis=1))
+    assert accept > 0.03
+    assert np.all(np.abs(post.mean(axis=0)) < 0.5)
+    assert l[150:].mean() > l[0]
+    # independent chains on their own handles / streams
+    out = L.metropolis_threaded(50, lambda: L.log_likelihood_fun(ffp, priors, u, y), 120, np.array([0.3, -0.3]),
+                                None, nthreads=4, seed=1)
+    assert out.shape == (4 * 70, 3) and np.all(np.isfinite(out))
+    assert np.all(np.abs(out[:, :2].mean(axis=0)) < 1.0)
