@@ -820,8 +820,11 @@ struct SlotRouter {
   mutable int remote;   // set once this thread has stored into another rank's array
   __device__ __forceinline__ T* at(int slot) const {
     if (world <= 1) return j + slot;
+    // almost every slot belongs to this rank: no division on that path (it cost the sharded scatter ~6 us per step)
+    const int ls = slot - rank * n;
+    if ((unsigned)ls < (unsigned)n) return peer[rank] + ls;
     const int r = slot / n;
-    if (r != rank) remote = 1;
+    remote = 1;
     return peer[r] + (slot - r * n);
   }
 };
@@ -1350,9 +1353,13 @@ __device__ __forceinline__ void gather_x(const EngineP& P, int buf_id, int a, do
   const double* buf;
   int li;
   if (P.world > 1) {
-    const int r = a / P.n;
-    li = a - r * P.n;
-    buf = P.peer_x[r][buf_id];
+    li = a - P.first;
+    buf = P.x[buf_id];
+    if ((unsigned)li >= (unsigned)P.n) {   // an ancestor on another GPU (rare: only near the shard edges)
+      const int r = a / P.n;
+      li = a - r * P.n;
+      buf = P.peer_x[r][buf_id];
+    }
   } else {
     li = a - P.first;
     buf = P.x[buf_id];

@@ -12,10 +12,15 @@ local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
 dist.init_process_group("gloo")
 spec = W.lg_spec(4, 2, 2, seed=0)
-for (log2n, T, thr, kind) in [(20, 500, 0.0, "pf"), (20, 500, 0.1, "pf"), (20, 500, 1.0, "pf"), (12, 500, 0.1, "pf"), (19, 300, 0.1, "aux")]:
-    u = np.random.default_rng(0).standard_normal((T, 2)); _, y = W.simulate_lg(spec, u, seed=1)
+wide = W.lg_large_spec(seed=0)   # config 5: 64 states, Float32 particles
+# per-GPU sizes; config 4 = APF with N=2^22 over 8 GPUs (2^19 each), config 5 = wide PF with N=2^20 over 8 GPUs (2^17 each)
+for (log2n, T, thr, kind) in [(20, 300, 0.0, "pf"), (20, 300, 0.1, "pf"), (20, 300, 1.0, "pf"), (12, 300, 0.1, "pf"),
+                              (19, 300, 0.1, "aux"), (17, 60, 0.1, "wide"), (20, 20, 0.1, "wide")]:
+    sp = wide if kind == "wide" else spec
+    u = np.random.default_rng(0).standard_normal((T, 2))
+    _, y = W.simulate_lg(sp, u, seed=1)
     N = (1 << log2n) * world
-    mk = spec.aux_filter if kind == "aux" else spec.particle_filter
+    mk = sp.aux_filter if kind == "aux" else sp.particle_filter
     pf = mk(N, seed=1, resample_threshold=thr, device=local, rank=rank, world=world)
     L.connect_shards(pf)
     best = 1e9

@@ -638,6 +638,74 @@ def test_f32_wide_unsupported_combinations_fail_loudly(gpu):
 
 
 # ---------------------------------------------------------------------------------------------
+# edge cases: smallest and ragged sizes, no input, weight collapse, a large filter
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,T", [(1, 5), (2, 1), (3, 7), (31, 3), (33, 9), (257, 4), (1000, 1)])
+def test_tiny_and_ragged_sizes_match_oracle(gpu, N, T):
+    L = gpu
+    s = lg_model(3, 1, 2, seed=1)
+    u, y = _data(s, T, 2)
+    for kind in ("pf", "apf"):
+        filt = 2 if kind == "apf" else 0
+        of = s.oracle_filter(N, filter=filt, seed=3, resample_threshold=0.5)
+        pf = s.particle_filter(N, seed=3, scan_mode="serial", resample_threshold=0.5)
+        if kind == "apf":
+            pf = L.AuxiliaryParticleFilter(pf)
+        got, ref = L.loglik(pf, u, y, epoch=1, details=True), of.loglik(u, y, epoch=1)
+        assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * max(1.0, abs(ref["ll"]))
+        assert np.array_equal(got["resampled"], ref["resampled"])
+        _assert_state_close(L, pf, of)
+        sol, refs = L.forward_trajectory(pf, u, y, epoch=2), of.forward_trajectory(u, y, epoch=2, history=True)
+        assert sol.x.shape == (T, N, 3) and np.allclose(sol.x, refs["x"], rtol=0, atol=1e-10)
+        assert np.allclose(sol.we, refs["we"], rtol=1e-9, atol=1e-300)
+
+
+def test_model_without_input(gpu):       # nu = 0: dynamics(x,u,p,t) = A*x
+    L = gpu
+    s = lg_model(4, 0, 2, seed=5)
+    T, N = 30, 3000
+    from llpf_b200 import workloads as W
+    _, y = W.simulate_lg(s, np.zeros((T, 0)), seed=2)
+    of = s.oracle_filter(N, seed=3)
+    pf = s.particle_filter(N, seed=3, scan_mode="serial")
+    got, ref = L.loglik(pf, None, y, epoch=1, details=True), of.loglik(np.zeros((T, 0)), y, epoch=1)
+    assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+    _assert_state_close(L, pf, of)
+
+
+def test_weight_collapse_is_reported(gpu):
+    """The reference lets NaN propagate silently when every weight underflows (SURVEY §8b error conventions); the C-ABI
+    reports it as LLPF_ERR_NONFINITE instead of returning a NaN log-likelihood."""
+    L = gpu
+    s = lg_model(2, 1, 1, seed=1, r2=1e-12)
+    T, N = 6, 512
+    u = np.zeros((T, 1))
+    y = np.full((T, 1), 1e6)                                   # ~1e24 nats away from every particle
+    pf = s.particle_filter(N, seed=3)
+    with pytest.raises(L.LLPFError) as e:
+        L.loglik(pf, u, y)
+    assert e.value.code == L._abi.ERR_NONFINITE
+
+
+def test_large_filter_properties(gpu):
+    """N = 2^24 (16x the headline size; 1.7 GB of state): the log-likelihood converges to the Kalman filter's, ancestors are
+    sorted and in range, weights are finite."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    N, T = 1 << 24, 12
+    u = np.random.default_rng(1).standard_normal((T, 2))
+    gen = s.oracle_filter(64, seed=1)
+    _, y = gen.simulate(u, 4)
+    pf = s.particle_filter(N, seed=9, resample_threshold=1.0)
+    r = L.loglik(pf, u, y, epoch=1, details=True)
+    kf = O.kalman_loglik(s.oracle_model(), u, y)
+    assert abs(r["ll"] - kf) < 0.02
+    j = L.ancestors(pf)
+    assert j.shape == (N,) and j.min() >= 1 and j.max() <= N and np.all(np.diff(j) >= 0)
+    assert np.isfinite(L.weights(pf)).all()
+
+
+# ---------------------------------------------------------------------------------------------
 # particle smoother (FFBS)  smoothing.jl:104-143  (SURVEY §8f rank 2)
 # ---------------------------------------------------------------------------------------------
 def _traj_mismatch(xb, ref, tol=0.0):
