@@ -1434,18 +1434,18 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   double* const weh = P.we_hist;
   int f_total = 0;
   if constexpr (RESID != 0) {
-   if (res) {   // ResampleResidual  resample.jl:63-117
-    WeSrc rs;
-    rs.w = ws.w; rs.mode = ws.uniform ? 1 : (ws.pend ? 3 : 2);
-    rs.pm = ws.pm; rs.pls = ws.pls; rs.inv_s = ws.inv_s; rs.weu = ws.weu; rs.wu = ws.wu; rs.T = &sh.mt;
-    rs.hist_w = hist_w ? wh + hbase : nullptr;
-    rs.hist_we = hist_w ? weh + hbase : nullptr;
-    double total;
-    resample_residual<int>(P, sh, cx.beg, cx.end, cx.bar_target, rs, nullptr, step_idx, (int)P.N, P.j, P.first,
-                           sc.j_identity, P.first + cx.beg, P.first + cx.end, total);
-    f_total = (int)P.N;
-    sc.bins_total = total;
-   }
+    if (res) {   // ResampleResidual  resample.jl:63-117
+      WeSrc rs;
+      rs.w = ws.w; rs.mode = ws.uniform ? 1 : (ws.pend ? 3 : 2);
+      rs.pm = ws.pm; rs.pls = ws.pls; rs.inv_s = ws.inv_s; rs.weu = ws.weu; rs.wu = ws.wu; rs.T = &sh.mt;
+      rs.hist_w = hist_w ? wh + hbase : nullptr;
+      rs.hist_we = hist_w ? weh + hbase : nullptr;
+      double total;
+      resample_residual<int>(P, sh, cx.beg, cx.end, cx.bar_target, rs, nullptr, step_idx, (int)P.N, P.j, P.first,
+                             sc.j_identity, P.first + cx.beg, P.first + cx.end, total);
+      f_total = (int)P.N;
+      sc.bins_total = total;
+    }
   } else if (res) {
     double total;
     f_total = resample_indices<int>(

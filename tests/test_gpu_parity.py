@@ -680,7 +680,7 @@ def test_weight_collapse_is_reported(gpu):
     s = lg_model(2, 1, 1, seed=1, r2=1e-12)
     T, N = 6, 512
     u = np.zeros((T, 1))
-    y = np.full((T, 1), 1e6)                                   # ~1e24 nats away from every particle
+    y = np.full((T, 1), 1e200)                                 # the quadratic form overflows: every log-weight is -Inf
     pf = s.particle_filter(N, seed=3)
     with pytest.raises(L.LLPFError) as e:
         L.loglik(pf, u, y)
