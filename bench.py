@@ -109,6 +109,24 @@ def cpu_baseline(seconds_target=12.0):
             "host_cores_available": os.cpu_count()}
 
 
+def _replica(seconds_target):
+    return cpu_baseline(seconds_target)
+
+
+def cpu_replicas_all_cores(seconds_target=6.0):
+    """Every host core runs its own single-threaded copy of the workload (independent filters, the pattern of the
+    reference's metropolis_threaded, smoothing.jl:335-347): the most the reference's ParticleFilter path — which has no
+    threading of its own (PFtypes.jl:107-139) — can get out of the box.  Aggregate particle-steps/s."""
+    import multiprocessing as mp
+    C = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(C) as pool:
+        rs = pool.map(_replica, [seconds_target] * C)
+    wall = time.perf_counter() - t0
+    return {"value": sum(r["value"] for r in rs), "unit": "particle-steps/s", "cores": C, "kind": "port",
+            "sample": f"{C} independent single-threaded filters, each: {rs[0]['sample']}; wall {wall:.1f} s"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU algorithm for the path (oracle port), rank 0 only."""
     if rank != 0:
@@ -130,6 +148,8 @@ def run_reference(args, rank):
                                "each step = a bounded sample (first ~8 s of time steps) of that trajectory on the CPU port "
                                "of the reference loops; ms_per_step extrapolated to the full T"},
         "cpu_baseline": cb,
+        # one filter cannot use more than one thread in the reference; all cores only help independent filters:
+        "cpu_replicas_all_cores": cpu_replicas_all_cores(),
         "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

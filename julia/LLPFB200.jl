@@ -128,6 +128,17 @@ function forward_trajectory(pf::GPUParticleFilter, u::AbstractVector, y::Abstrac
     LowLevelParticleFilters.ParticleFilteringSolution(pf, u, y, x, w, we, ll[])
 end
 
+"xb, ll = smooth(pf, M, u, y, p)  src/smoothing.jl:104-143 (forward filtering, backward simulation; history stays on the GPU)"
+function LowLevelParticleFilters.smooth(pf::GPUParticleFilter, M::Integer, u::AbstractVector, y::AbstractVector, p=nothing)
+    U, Y = flat(u), flat(y); T = length(y)
+    xb = Matrix{SVector{pf.nx,Float64}}(undef, M, T)       # M x T, column-major == [T][M][nx] doubles
+    ll = Ref{Float64}(0.0); pf.epoch += 1
+    GC.@preserve xb check(ccall((:llpf_smooth, lib), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, UInt64, Ref{Float64}, Ptr{Float64}, Ptr{Cvoid}),
+        pf.h, T, U, Y, M, pf.epoch, ll, pointer(reinterpret(Float64, xb)), C_NULL))
+    xb, ll[]
+end
+
 # ---- accessors (src/PFtypes.jl:296-334, src/resample.jl:1-10, src/filtering.jl:541-568) --------------------
 num_particles(pf::GPUParticleFilter) = pf.N
 function particles(pf::GPUParticleFilter)
