@@ -760,21 +760,6 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.nblocks = (int)nb;
   P.chunk = (int)((f->n + nb - 1) / nb);
   P.chunk = (P.chunk + 1) & ~1;   // even chunk starts: 16-byte aligned particle pairs in the scan
-  P.chunk_b = P.chunk; P.split = P.nblocks;
-  // Two co-resident blocks per SM do not run at the same speed (the older one gets issue priority: 17.7 vs 20.6 us per
-  // sweep at N=2^20): when the grid is exactly two waves, the first wave takes a few per cent more particles.
-  if (!f->wide && nb == 2ll * f->num_sms && f->n >= 64ll * nb) {
-    static const double skew = [] { const char* e = std::getenv("LLPF_WAVE_SKEW"); return e ? std::atof(e) : 0.0; }();
-    if (skew > 0.0 && skew < 0.5) {
-      const long long half = nb / 2;
-      long long ca = (long long)((double)f->n / (double)nb * (1.0 + skew));
-      ca = (ca + 1) & ~1ll;
-      long long rest = f->n - half * ca;
-      long long cb = (rest + half - 1) / half;
-      cb = (cb + 1) & ~1ll;
-      if (cb > 0 && cb <= ca) { P.chunk = (int)ca; P.chunk_b = (int)cb; P.split = (int)half; }
-    }
-  }
   P.key = RngKey{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)f->epoch << 8};
   P.rank = f->rank; P.world = f->world;
   P.fix_scale = FIX_SCALE; P.fix_inv = FIX_INV;
@@ -1393,7 +1378,6 @@ static int standalone_geometry(int device, long long n, EngineP& P, const void* 
   P.nblocks = (int)nb;
   P.chunk = (int)((n + nb - 1) / nb);
   P.chunk = (P.chunk + 1) & ~1;
-  P.chunk_b = P.chunk; P.split = P.nblocks;
   return LLPF_OK;
 }
 

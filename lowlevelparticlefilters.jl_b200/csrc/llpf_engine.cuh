@@ -126,8 +126,7 @@ struct EngineP {
   int scan_mode;          // LLPF_SCAN_*
   int want_xhat;
   int nblocks;            // == gridDim.x
-  int chunk;              // particles per block (blocks below `split`)
-  int chunk_b, split;     // particles per block from `split` on; split == nblocks: one size
+  int chunk;              // particles per block
   int rank, world;
   RngKey key;
   double fix_scale, fix_inv;  // fixed-point scan scale: 2^62 / 2^-62 for normalised weights
@@ -1726,11 +1725,8 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
   cx.bar_target = 0;
   cx.red_seq = 0;
   {
-    // two chunk sizes: blocks below `split` (the first wave: the older block of every SM, which the warp schedulers
-    // favour) take chunk particles, the second wave chunk_b <= chunk, so that both blocks of an SM finish together
-    const int bi = blockIdx.x;
-    long long b = (bi < P.split) ? (long long)bi * P.chunk : (long long)P.split * P.chunk + (long long)(bi - P.split) * P.chunk_b;
-    long long e = b + ((bi < P.split) ? P.chunk : P.chunk_b);
+    long long b = (long long)blockIdx.x * P.chunk;
+    long long e = b + P.chunk;
     if (b > P.n) b = P.n;
     if (e > P.n) e = P.n;
     cx.beg = (int)b; cx.end = (int)e;
