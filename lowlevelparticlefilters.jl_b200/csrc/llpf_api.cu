@@ -913,6 +913,10 @@ struct DevHistory {   // forward history left on the device for a consumer (the 
   double *x = nullptr, *w = nullptr, *we = nullptr;
   void release() { cudaFree(x); cudaFree(w); cudaFree(we); x = w = we = nullptr; }
 };
+struct HistoryGuard {   // frees the history buffers of a run on every exit path unless they were handed over
+  double *&x, *&w, *&we;
+  ~HistoryGuard() { cudaFree(x); cudaFree(w); cudaFree(we); }
+};
 
 static int run_impl(llpf_filter* f, long long T, const double* u_dev, const double* y_dev,
                     int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out,
@@ -952,6 +956,7 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
     push_op(P, OP_PF, Ti, 0);
   }
   double *xh = nullptr, *wh = nullptr, *weh = nullptr;
+  HistoryGuard hist_guard{xh, wh, weh};
   const size_t NT = (size_t)f->N * (size_t)T;
   if (out) {
     P.ll_steps = out->ll_steps ? f->d_ll : nullptr;
@@ -1010,8 +1015,7 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
   }
   if (keep && rc == LLPF_OK) {
     keep->x = xh; keep->w = wh; keep->we = weh;
-  } else {
-    cudaFree(xh); cudaFree(wh); cudaFree(weh);
+    xh = wh = weh = nullptr;   // ownership moved to the caller
   }
   if (rc) return rc;
   if (ll) *ll = f->hsc.ll_total;

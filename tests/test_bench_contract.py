@@ -1,0 +1,39 @@
+"""bench.py contract checks that need no GPU: the reference arm prints one JSON line with the agreed keys, and the
+product arm refuses to run (non-zero exit, no CPU fallback) when no CUDA device is visible."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_json_line(built):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "particle-steps/sec" and line["unit"] == "particle-steps/s"
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["dtype"] == "f64"
+    assert line["value"] > 1e5 and line["steps"] == 1 and line["gpu_launches"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
+    allc = line["cpu_replicas_all_cores"]
+    assert allc["cores"] == os.cpu_count() and allc["value"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_product_arm_fails_loudly_without_a_gpu(built):
+    import ctypes as C
+    import llpf_b200 as L
+    n = C.c_int()
+    if L.load_library().llpf_device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is visible")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert "no CPU fallback" in (out.stdout + out.stderr)
