@@ -94,39 +94,54 @@ k_smooth(const __grid_constant__ SmoothP S, const __grid_constant__ ModelP<NX, 1
       const double ti = (double)(t - 1) * S.Ts;   // :131
       const double* xft = S.xf + (size_t)(t - 1) * N * NX;
       const double* wft = S.wf + (size_t)(t - 1) * N;
-      // wb[n] = wf[n,t] + logpdf(df, xb[m,t+1] - f(xf[n,t],u[t],p,ti))   :135
-      auto wb_of = [&](int n) -> double {
-        double x[NX];
+      // wb[n] = wf[n,t] + logpdf(df, xb[m,t+1] - f(xf[n,t],u[t],p,ti))   :135 — split into the loads and the arithmetic so
+      // that the sweeps can put two particles' loads in flight before either is consumed (the kernel stalled 55 % of
+      // its time on these loads when each row was fetched right before use: profiles/r1_v9_ncu_smooth.md)
+      struct Row { double x[NX]; double w; };
+      auto load_row = [&](int n) -> Row {
+        Row r;
         const double* row = xft + (size_t)n * NX;
         if constexpr (NX % 2 == 0) {
 #pragma unroll
           for (int d = 0; d < NX; d += 2) {
             const double2 v = __ldg(reinterpret_cast<const double2*>(row + d));
-            x[d] = v.x; x[d + 1] = v.y;
+            r.x[d] = v.x; r.x[d + 1] = v.y;
           }
         } else {
 #pragma unroll
-          for (int d = 0; d < NX; ++d) x[d] = __ldg(row + d);
+          for (int d = 0; d < NX; ++d) r.x[d] = __ldg(row + d);
         }
-        dynamics_mean<NX, 1, DYN>(Mo, sh, bu, ti, x);
+        r.w = __ldg(wft + n);
+        return r;
+      };
+      auto wb_eval = [&](Row r) -> double {
+        dynamics_mean<NX, 1, DYN>(Mo, sh, bu, ti, r.x);
         double q = 0.0;
 #pragma unroll
-        for (int r = 0; r < NX; ++r) {
+        for (int rr = 0; rr < NX; ++rr) {
           double l[NX];
-          lds_row<NX>(sh.mL + r * mdl_stride(NX), l);
-          double acc = l[0] * (xbn[0] - x[0]);
+          lds_row<NX>(sh.mL + rr * mdl_stride(NX), l);
+          double acc = l[0] * (xbn[0] - r.x[0]);
 #pragma unroll
-          for (int c = 1; c <= r; ++c) acc = fma(l[c], xbn[c] - x[c], acc);
+          for (int c = 1; c <= rr; ++c) acc = fma(l[c], xbn[c] - r.x[c], acc);
           q = fma(acc, acc, q);
         }
-        return __ldg(wft + n) + fma(-0.5, q, S.c0);
+        return r.w + fma(-0.5, q, S.c0);
       };
+      auto wb_of = [&](int n) -> double { return wb_eval(load_row(n)); };
       // ---- level 1: per-warp (max, sum exp) over contiguous ranges ------------------------------------------
       const int b1 = min(N, warp * per1), e1 = min(N, b1 + per1);
       Online<1> acc;
       acc.init();
       const double dummy[1] = {0.0};
-      for (int n = b1 + lane; n < e1; n += 32) acc.add(wb_of(n), dummy, false, sh.mt);
+      for (int n = b1 + lane; n < e1; n += 64) {   // two particles per iteration: both rows in flight, two chains
+        const bool two = (n + 32 < e1);
+        const Row ra = load_row(n);
+        const Row rb = load_row(two ? n + 32 : n);
+        const double wa = wb_eval(ra), wbv = wb_eval(rb);
+        acc.add(wa, dummy, false, sh.mt);
+        if (two) acc.add(wbv, dummy, false, sh.mt);
+      }
       double wm = acc.m;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) wm = fmax(wm, __shfl_xor_sync(0xffffffffu, wm, o));
@@ -161,7 +176,14 @@ k_smooth(const __grid_constant__ SmoothP S, const __grid_constant__ ModelP<NX, 1
       const int per2 = ((((re - rb) + SM_WARPS - 1) / SM_WARPS) + 31) & ~31;
       const int b2 = min(re, rb + warp * per2), e2 = min(re, b2 + per2);
       double s2 = 0.0;
-      for (int n = b2 + lane; n < e2; n += 32) s2 += exp_nonpos(wb_of(n) - gm, sh.mt);
+      for (int n = b2 + lane; n < e2; n += 64) {
+        const bool two = (n + 32 < e2);
+        const Row ra = load_row(n);
+        const Row rb = load_row(two ? n + 32 : n);
+        const double ea = exp_nonpos(wb_eval(ra) - gm, sh.mt), eb = exp_nonpos(wb_eval(rb) - gm, sh.mt);
+        s2 += ea;
+        if (two) s2 += eb;
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       __syncthreads();                                     // everyone has consumed ss.ws of level 1
