@@ -55,6 +55,12 @@ def test_gpu_reproduces_golden_trajectories(gpu, name):
     assert np.allclose(L.weights(pf), GOLD[f"{name}/w_final"], rtol=0, atol=1e-4 if wide else 1e-9)
     assert np.array_equal(L.ancestors(pf), GOLD[f"{name}/j_final"])
     if not wide:
+        # the whole N x T history (x, w, we of ParticleFilteringSolution) against the oracle, every step
+        mk, filt, okw, N, T, _ = G.cases()[name]
+        ref = mk().oracle_filter(N, filter=filt, **okw).forward_trajectory(u, y, epoch=3, history=True)
+        assert np.allclose(sol.x, ref["x"], rtol=0, atol=xt)
+        assert np.allclose(sol.w, ref["w"], rtol=0, atol=1e-9)
+        assert np.allclose(sol.we, ref["we"], rtol=1e-8, atol=1e-300)
         assert np.allclose(sol.x[0], GOLD[f"{name}/x_hist_first"], rtol=0, atol=xt)
         assert np.allclose(sol.x[-1], GOLD[f"{name}/x_hist_last"], rtol=0, atol=xt)
         assert np.allclose(sol.we[-1], GOLD[f"{name}/we_hist_last"], rtol=1e-8, atol=1e-300)
