@@ -563,6 +563,48 @@ def test_pf_and_apf_loglik_vs_kalman_on_device(gpu):   # test/runtests.jl:412-44
     assert np.max(np.abs(llkf - llpf)) < 20 and np.max(np.abs(llkf - llapf)) < 20
 
 
+def test_reference_end_to_end_block_on_device(gpu):
+    """The assertions of the reference's "End to end" testset (test/runtests.jl:245-333) on the device path: same model,
+    N=1000, T=200, M=100; shapes, weighted mean / quantile / covariance consistency, smoothing error bounds for the
+    ParticleFilter and the AuxiliaryParticleFilter."""
+    L = gpu
+    A, B, C_ = ref_model_2state()
+    n, N, T, M = 2, 1000, 200, 100
+    rng = np.random.default_rng(0)
+    mu0 = rng.standard_normal(n)
+    args = (N, L.LinearDynamics(A, B), L.LinearMeasurement(C_), L.MvNormal(0.1 ** 2 * np.eye(n)), L.MvNormal(np.eye(1)),
+            L.MvNormal(mu0, 4.0 * np.eye(n)))
+    pf, pfa = L.ParticleFilter(*args, seed=1), L.AuxiliaryParticleFilter(*args, seed=1)
+    assert not L.shouldresample(pf) and not L.shouldresample(pfa)                 # :273-274
+    u = rng.standard_normal((T, 1))                                                # du = mvnormal(m, 1)
+    om = O.ModelArrays(2, 1, 1, C_, 0.1 ** 2 * np.eye(n), np.eye(1), mu0, 4.0 * np.eye(n), A=A, B=B)
+    xs, y = O.OracleFilter(om, 10, seed=1).simulate(u, 7)                          # x,u,y = simulate(pf,T,du)  :279
+    sol = L.forward_trajectory(pf, u, y)
+    assert sol.x.shape == (T, N, n) and sol.w.shape == (T, N) and sol.we.shape == (T, N) and len(sol.t) == T
+    WM = L.mean_trajectory(sol.x, sol.we)                                          # weighted_mean(sol.x, sol.we)  :288
+    assert WM.shape == (T, n) and np.array_equal(WM, L.mean_trajectory(sol))       # :289-290
+    assert np.allclose(WM[0], (sol.x[0] * sol.we[0][:, None]).sum(axis=0))         # :291
+    assert np.allclose(WM, sol.extra["xhat"], rtol=0, atol=1e-9)                   # the fused device reduction agrees
+    WQ1, WQ9 = L.weighted_quantile(sol, 0.1), L.weighted_quantile(sol, 0.9)        # :293-297
+    assert np.all(WM < WQ9) and np.all(WM > WQ1)
+    Cw = L.weighted_cov(sol)                                                       # :299-305
+    d = sol.x[1] - WM[1]
+    C2 = (d * sol.we[1][:, None]).T @ d
+    assert np.allclose(C2 * N / (N - 1), Cw[1])
+    xpf, _ = L.mean_trajectory(pf, u, y)                                           # :311
+    assert xpf.shape == (T, n)
+    xb, ll = L.smooth(pf, M, u, y)                                                 # :313-317
+    assert xb.shape == (T, M, n) and np.isfinite(ll)
+    xbm = L.smoothed_mean(xb)
+    assert np.mean((xs.T - xbm) ** 2) < 5
+    xba, _ = L.smooth(pfa, M, u, y)                                                # :319-321
+    assert np.mean((xs.T - L.smoothed_mean(xba)) ** 2) < 5
+    assert all(np.trace(Cm) < 2 for Cm in L.smoothed_cov(xba))                     # :327-328
+    assert L.smoothed_trajs(xba).shape == (n, M, T)                                # :330
+    # particle smoothing is at least as good as filtering here (the reference keeps this one as @test_skip, :346)
+    assert np.mean((xs - xb.mean(axis=1)) ** 2) < 1.2 * np.mean((xs - WM) ** 2)
+
+
 # ---------------------------------------------------------------------------------------------
 # Float32 particles, wide models (BASELINE config 5; llpf_wide.cuh)
 # ---------------------------------------------------------------------------------------------
