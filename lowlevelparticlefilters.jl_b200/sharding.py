@@ -78,3 +78,62 @@ def sharded_systematic(we_local, u01, N, rank, world, allgather, alltoall, j_pre
     for s, a in recv:
         j[s] = a                                   # untouched (stale) slots keep their previous value
     return j, bins, f_total
+
+
+# ---------------------------------------------------------------------------------------------
+# Packed particle exchange (design for the next engine version; host mirror + gloo tests only)
+# ---------------------------------------------------------------------------------------------
+# Today the kernels route offspring INDICES to the slot owners and every slot then gathers its ancestor's state from
+# whichever rank holds it (fine-grained peer loads).  With degenerate weights most ancestors are remote and a few heavy
+# particles are read by every rank: NVLink latency and same-address contention make those steps 2x slower on 8 GPUs
+# (DESIGN.md section 9).  The bandwidth-optimal alternative uses what the source side already knows: particle b owns the
+# slot range [F(lo_b), F(hi_b)), which is monotone in b, so for every destination rank d the particles with at least one
+# slot on d can be PACKED by the source into one dense buffer (state + first local slot + count).  The destination reads
+# one contiguous buffer per source (bulk copy) and expands the runs locally: every needed particle crosses NVLink exactly
+# once per destination rank, however many slots it owns there.
+def pack_for_destinations(x_local, we_local, u01, N, rank, world, allgather):
+    """Source side.  Returns, per destination rank d, (states [m_d, nx], first_slot_local [m_d], count [m_d]) for this
+    rank's particles that own slots on d, plus (bins_local, f_total)."""
+    first, n = shard_range(N, rank, world)
+    f = to_fixed(we_local)
+    loc = np.cumsum(f, dtype=np.uint64)
+    tots = [int(t) for t in allgather(int(loc[-1]))]
+    base, gtot = sum(tots[:rank]), sum(tots)
+    inv = 2.0 ** -FIX_BITS
+    hi = (np.uint64(base) + loc).astype(np.float64) * inv
+    lo = np.concatenate([[float(base) * inv], hi[:-1]])
+    total = float(gtot) * inv
+    r = u01 * total / N
+    fa, fc = first_slot_ge(lo, r, N), first_slot_ge(hi, r, N)      # slots [fa, fc) of every local particle
+    f_total = int(first_slot_ge(np.array([total]), r, N)[0])
+    packs = []
+    for d in range(world):
+        s0, s1 = d * n, (d + 1) * n
+        a, c = np.maximum(fa, s0), np.minimum(fc, s1)               # intersection with d's slot range
+        keep = c > a                                                # on the device: flags -> block scan -> pack index
+        packs.append((np.asarray(x_local)[keep], (a[keep] - s0).astype(np.int64), (c[keep] - a[keep]).astype(np.int64)))
+    return packs, hi, f_total
+
+
+def expand_packs(recv, n, nx, x_prev_local=None):
+    """Destination side: write every received particle into the run of local slots it owns.  Slots no pack covers are the
+    reference's untouched entries (resample.jl:26-34): they keep the particle of the identity ancestor (x_prev_local)."""
+    out = np.zeros((n, nx)) if x_prev_local is None else np.array(x_prev_local, dtype=np.float64).copy()
+    covered = np.zeros(n, dtype=bool)
+    moved = 0
+    for states, first_slot, count in recv:
+        moved += len(count)
+        for st, a, c in zip(states, first_slot, count):
+            out[a:a + c] = st
+            covered[a:a + c] = True
+    return out, covered, moved
+
+
+def sharded_resample_packed(x_local, we_local, u01, N, rank, world, allgather, alltoall):
+    """x_new_local[i] = x[j[i]] for this rank's slots without ever materialising remote gathers: pack -> exchange -> expand.
+    Returns (x_new_local, covered mask, number of particle states received)."""
+    first, n = shard_range(N, rank, world)
+    packs, _, _ = pack_for_destinations(x_local, we_local, u01, N, rank, world, allgather)
+    recv = alltoall(packs)
+    return expand_packs(recv, n, np.asarray(x_local).shape[1], x_prev_local=x_local)
+
