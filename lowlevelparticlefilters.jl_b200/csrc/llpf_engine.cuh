@@ -30,9 +30,7 @@
 // evaluates s_i in the reference's arithmetic) — the same partition as the reference's two-pointer
 // walk (resample.jl:26-34), with no dependent memory chain.
 #pragma once
-#include <cuda_runtime.h>
-#include <float.h>
-#include <stdint.h>
+#include "llpf_rtc_compat.h"
 
 #include "llpf_rng.cuh"
 

@@ -11,8 +11,7 @@
 // polynomial coefficients in constant memory (DFMA takes c[bank][offset] operands directly).
 // Accuracy: <= ~1.5 ulp (validated on the device against the CPU oracle's libm, tests/test_gpu_parity.py).
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "llpf_rtc_compat.h"
 
 namespace llpf {
 

@@ -13,8 +13,7 @@
 //   uniform53: u = (((r0 << 32) | r1) >> 11) * 2^-53 in [0,1)   (granularity of Julia's rand())
 //   normal pair: Box-Muller in f64: rad = sqrt(-2 log u1); (z0,z1) = rad * (cospi(2 u2), sinpi(2 u2))
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "llpf_rtc_compat.h"
 
 #include "llpf_math.cuh"
 
