@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 150 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "reference_end_to_end" 2>&1 | tail -15
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 60 python -m pytest tests/test_golden.py -m gpu -q 2>&1 | tail -2
