@@ -118,10 +118,17 @@ def cpu_replicas_all_cores(seconds_target=6.0):
     reference's metropolis_threaded, smoothing.jl:335-347): the most the reference's ParticleFilter path — which has no
     threading of its own (PFtypes.jl:107-139) — can get out of the box.  Aggregate particle-steps/s."""
     import multiprocessing as mp
-    C = os.cpu_count() or 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    C = max(1, min(avail, 32))          # each replica holds a 2^20-particle filter (~150 MB): bound the footprint
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(C) as pool:
-        rs = pool.map(_replica, [seconds_target] * C)
+    try:
+        with mp.get_context("fork").Pool(C) as pool:
+            rs = pool.map(_replica, [seconds_target] * C)
+    except Exception as e:  # noqa: BLE001  (the aggregate is extra information: never fail the arm over it)
+        return {"value": None, "unit": "particle-steps/s", "cores": C, "kind": "port", "sample": f"failed: {e}"}
     wall = time.perf_counter() - t0
     return {"value": sum(r["value"] for r in rs), "unit": "particle-steps/s", "cores": C, "kind": "port",
             "sample": f"{C} independent single-threaded filters, each: {rs[0]['sample']}; wall {wall:.1f} s"}

@@ -23,7 +23,7 @@ def test_reference_arm_json_line(built):
     assert line["e2e"] == {"value": line["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
     allc = line["cpu_replicas_all_cores"]
-    assert allc["cores"] == os.cpu_count() and allc["value"] > 0
+    assert 1 <= allc["cores"] <= 32 and allc["value"] > 0
     assert "workload" in line["config"] and "model" not in line["config"]
 
 
