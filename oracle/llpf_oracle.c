@@ -332,6 +332,12 @@ typedef struct orc_pf {
   /* scratch */
   double* lambda;      /* APF: the reference aliases s.we; kept separately addressable here */
   int64_t resample_count;
+  /* user closures (the reference's `dynamics(x,u,p,t)` / `measurement_likelihood(x,u,y,p,t)` are arbitrary Julia
+     functions, PFtypes.jl:128,232): optional C callbacks replacing the descriptor model — test-side only, so that
+     device-compiled user functions can be checked against the same function evaluated on the host */
+  void (*user_dynamics)(const double* x, const double* u, double t, double* out, void* ctx);
+  double (*user_loglik)(const double* x, const double* u, const double* y, double t, void* ctx);
+  void* user_ctx;
   /* Float32-particle mode (llpf_config.particle_dtype == LLPF_PARTICLE_F32): see the f32 section below */
   int f32;
   float *Af, *Bf, *L1f, *L0f, *mu0f, *Gf;   /* row-major f32 copies; Gf = (float)(inv(chol(R2)) * C) */
@@ -528,6 +534,15 @@ int orc_create(const llpf_config* cfg, const llpf_model* m, orc_pf** out) {
   return LLPF_OK;
 }
 int orc_set_model(orc_pf* f, const llpf_model* m) { return set_model(f, m); }
+/* replace the dynamics mean and / or the measurement log-likelihood by caller-supplied functions (NULL keeps the
+   descriptor's); Float64 particles only */
+int orc_set_user_functions(orc_pf* f,
+                           void (*dyn)(const double*, const double*, double, double*, void*),
+                           double (*loglik)(const double*, const double*, const double*, double, void*), void* ctx) {
+  if (f->f32) return LLPF_ERR_UNSUPPORTED;
+  f->user_dynamics = dyn; f->user_loglik = loglik; f->user_ctx = ctx;
+  return LLPF_OK;
+}
 
 /* rand(rng, d) = mu + L*z   utils.jl:260-262 ; Distributions MvNormal: mu + unwhiten(z) */
 static void sample_mvn(const double* mu, const double* L, int n, const double* z, double* out) {
@@ -616,6 +631,7 @@ double orc_rk4_constant_rhs(double c, double x0, double Ts, int supersample) {
 
 /* dynamics(x,u,p,t) without noise: LG `A*x .+ B*u` (example_lineargaussian.jl:27) or rk4(quadtank) */
 static void dynamics_mean(const orc_pf* f, const double* x, const double* u, double t, double* out) {
+  if (f->user_dynamics) { f->user_dynamics(x, u, t, out, f->user_ctx); return; }
   if (f->dynamics == LLPF_DYN_QUADTANK_RK4) {
     rk4_quadtank(f, x, u, t, out);
     return;
@@ -657,6 +673,10 @@ static void measurement_equation(const orc_pf* f, const double* u, const double*
   (void)u; (void)t;
   if (any_nan(y, f->ny)) return;
   if (f->f32) { measurement_equation_f32(f, y, w); return; }
+  if (f->user_loglik) {      /* w[i] += g(x[i],u,y,p,t)   PFtypes.jl:232 */
+    for (int64_t i = 0; i < f->N; ++i) w[i] += f->user_loglik(f->x + (size_t)i * f->nx, u, y, t, f->user_ctx);
+    return;
+  }
   double g[64], r[64];
   for (int64_t i = 0; i < f->N; ++i) {
     matvec(f->C, f->ny, f->nx, f->x + (size_t)i * f->nx, g);

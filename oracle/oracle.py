@@ -93,6 +93,8 @@ def lib():
         L.orc_resample_stratified.restype = None
         L.orc_resample_residual.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, dp]
         L.orc_resample_residual.restype = C.c_int64
+        L.orc_set_user_functions.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_set_user_functions.restype = C.c_int
         L.orc_smooth.argtypes = [H, C.c_int64, C.c_int64, dp, dp, dp, dp, C.c_uint64, dp]
         L.orc_smooth.restype = C.c_int
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -362,6 +364,31 @@ class OracleFilter:
                               out["resampled"].ctypes.data_as(i32p))
         out["ll"] = ll
         return out
+
+    def set_user_functions(self, dynamics=None, loglik=None):
+        """dynamics(x, u, t) -> x_next (no noise) and / or loglik(x, u, y, t) -> float as Python callables replacing the
+        descriptor model (the reference takes arbitrary closures, PFtypes.jl:128,232).  Slow (one Python call per
+        particle): for parity tests of user-supplied device functions at small N."""
+        nx, nu, ny = self.nx, self.nu, self.ny
+        DYN = C.CFUNCTYPE(None, dp, dp, C.c_double, dp, C.c_void_p)
+        LIK = C.CFUNCTYPE(C.c_double, dp, dp, dp, C.c_double, C.c_void_p)
+
+        def _arr(p, n):
+            return np.ctypeslib.as_array(p, shape=(n,)) if n else np.zeros(0)
+
+        def dyn_cb(xp, up, t, outp, _ctx):
+            out = np.asarray(dynamics(_arr(xp, nx).copy(), _arr(up, nu).copy(), t), dtype=np.float64)
+            _arr(outp, nx)[:] = out
+
+        def lik_cb(xp, up, yp, t, _ctx):
+            return float(loglik(_arr(xp, nx).copy(), _arr(up, nu).copy(), _arr(yp, ny).copy(), t))
+
+        self._cb_dyn = DYN(dyn_cb) if dynamics is not None else None      # keep the thunks alive
+        self._cb_lik = LIK(lik_cb) if loglik is not None else None
+        rc = lib().orc_set_user_functions(self.h, C.cast(self._cb_dyn, C.c_void_p) if self._cb_dyn else None,
+                                          C.cast(self._cb_lik, C.c_void_p) if self._cb_lik else None, None)
+        if rc:
+            raise RuntimeError(f"orc_set_user_functions failed: {rc}")
 
     def smooth(self, M, u, xf, wf, wef, epoch=0):
         """smooth(pf, xf, wf, wef, ll, M, u, y)  smoothing.jl:116-143 -> xb [T][M][nx]"""

@@ -439,3 +439,28 @@ def test_smoother_improves_on_filter_mean():   # the (disabled) expectation at t
     err_f = np.mean((xf_mean - xs) ** 2)
     err_s = np.mean((xb.mean(axis=1) - xs) ** 2)
     assert err_s < 1.1 * err_f
+
+
+# ---- user closures (PFtypes.jl:128,232): callbacks must reproduce the descriptor model they restate ------------------
+def test_user_function_callbacks_reproduce_descriptor_model():
+    s = lg_model(nx=3, nu=2, ny=2, seed=4)
+    N, T = 200, 15
+    u = np.random.default_rng(2).standard_normal((T, 2))
+    ref = s.oracle_filter(N, seed=6)
+    _, y = ref.simulate(u, 3)
+    a = ref.loglik(u, y, epoch=1)
+    L2 = np.linalg.cholesky(s.R2)
+    c0 = -(2 * np.log(2 * np.pi) + 2 * np.log(np.diag(L2)).sum()) / 2
+    of = s.oracle_filter(N, seed=6)
+    of.set_user_functions(dynamics=lambda x, uu, t: s.A @ x + s.B @ uu,
+                          loglik=lambda x, uu, yy, t: c0 - 0.5 * np.sum(np.linalg.solve(L2, yy - s.C @ x) ** 2))
+    b = of.loglik(u, y, epoch=1)
+    assert abs(a["ll"] - b["ll"]) <= 1e-10 * abs(a["ll"])
+    assert np.array_equal(a["resampled"], b["resampled"])
+    assert np.allclose(ref.particles, of.particles, rtol=0, atol=1e-10)
+    # a genuinely nonlinear model runs too (no descriptor could express it)
+    of2 = s.oracle_filter(N, seed=6)
+    of2.set_user_functions(dynamics=lambda x, uu, t: np.tanh(s.A @ x) + s.B @ uu + 0.01 * t)
+    c = of2.loglik(u, y, epoch=1)
+    assert np.isfinite(c["ll"]) and c["ll"] != a["ll"]
+
