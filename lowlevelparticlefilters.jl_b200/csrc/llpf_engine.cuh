@@ -34,6 +34,25 @@
 
 #include "llpf_rng.cuh"
 
+// ------------------------------------------------------------------------------------------------
+// user-defined models (DYN == LLPF_DYN_USER = 2): the reference takes arbitrary closures `dynamics(x,u,p,t)` and
+// `measurement_likelihood(x,u,y,p,t)` (src/PFtypes.jl:128,232).  Closures cannot cross a C-ABI, device source can: a
+// translation unit that defines these two templates (or specialisations) and instantiates k_engine<NX,NY,2,RESID> gets a
+// filter with those functions inlined into the sweep — compiled at run time with NVRTC (scripts/nvrtc_probe.py shows the
+// compile path; the run-time loader is not wired into the C-ABI yet).  u, y: the raw vectors of the step; p: the
+// parameter vector `p` of the filter; additive dynamics noise N(0,R1) is still drawn by the engine.
+// Everything below that serves DYN == 2 is compiled only with -DLLPF_USER_MODEL, so that the kernels of the shipped library
+// are byte-for-byte what was measured (the extra kernel-parameter / shared-memory fields alone perturb register allocation).
+// ------------------------------------------------------------------------------------------------
+#ifdef LLPF_USER_MODEL
+namespace llpf_user {
+template <int NX>
+__device__ void dynamics(double (&x)[NX], const double* u, const double* p, double t);
+template <int NX>
+__device__ double loglik(const double (&x)[NX], const double* u, const double* y, const double* p, double t);
+}  // namespace llpf_user
+#endif
+
 namespace llpf {
 
 #ifndef LLPF_MIN_BLOCKS
@@ -140,6 +159,9 @@ struct EngineP {
   int* heavy;
   int* peer_heavy[MAX_WORLD];
   u64* tots2;             // [MAX_BLOCKS] second per-block total (residual resampling: the integer offspring counts)
+#ifdef LLPF_USER_MODEL
+  const double* user_p;   // DYN == 2: the filter's parameter vector `p` (device memory), handed to the user functions
+#endif
 };
 constexpr int MBOX_DOUBLES = 16;  // broadcast-buffer stride per rank ([1..] payload)
 constexpr int MBOX_WORDS = 32;    // mailbox slot: 2 tagged 8-byte words per payload double
@@ -274,6 +296,13 @@ struct Shared {
   double peer_vals[MAX_WORLD * (3 + MAX_NX)];   // reduce_stats: the ranks' statistics (sharded filters)
   u64 offs[MAX_BLOCKS + 1];     // exclusive block offsets of the fixed-point scan
   alignas(16) MathTab mt;       // log / exp tables + polynomial coefficients of llpf_math.cuh
+#ifdef LLPF_USER_MODEL
+  // DYN == 2 (user-defined model): the raw vectors of the pass
+  double u_prop[MAX_NU];        // u of the step being propagated
+  double u_weigh[MAX_NU];       // u of the step being weighed
+  double y_raw[8];
+  const double* user_p;
+#endif
 };
 
 // All-gather of NV doubles per rank.  Every block of every rank calls it with identical `mine` (the
@@ -1144,6 +1173,11 @@ __device__ __forceinline__ void quadtank_rhs(const ModelP<NX, NY>& M, const doub
 template <int NX, int NY, int DYN>
 __device__ __forceinline__ void dynamics_mean(const ModelP<NX, NY>& M, const Shared& sh, const double (&bu)[NX], double t,
                                               double (&x)[NX]) {
+#ifdef LLPF_USER_MODEL
+  if constexpr (DYN == 2) {
+    llpf_user::dynamics<NX>(x, sh.u_prop, sh.user_p, t);
+  } else
+#endif
   if (DYN == 0) {
     double xn[NX];
 #pragma unroll
@@ -1228,6 +1262,16 @@ __device__ __forceinline__ double meas_loglik(const ModelP<NX, NY>& M, const Sha
   return fma(-0.5, q, M.c0);
 }
 
+// w[i] += logpdf(dg, y - g(x))  (PFtypes.jl:116)  or the user's measurement_likelihood(x,u,y,p,t)  (PFtypes.jl:232)
+template <int NX, int NY, int DYN>
+__device__ __forceinline__ double weigh_loglik(const ModelP<NX, NY>& M, const Shared& sh, const double (&yt)[NY],
+                                               const double (&x)[NX], double t) {
+#ifdef LLPF_USER_MODEL
+  if constexpr (DYN == 2) return llpf_user::loglik<NX>(x, sh.u_weigh, sh.y_raw, sh.user_p, t);
+#endif
+  return meas_loglik<NX, NY>(M, sh, yt, x);
+}
+
 template <int NX, int NY>
 __device__ __forceinline__ void model_to_shared(const ModelP<NX, NY>& M, Shared& sh) {
   constexpr int S = mdl_stride(NX);
@@ -1307,7 +1351,21 @@ template <int NX, int NY, int DYN>
 __device__ __forceinline__ void stage_step(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh, int k_u, int k_y,
                                            double (&bu)[NX], double (&yt)[NY], bool& skip) {
   __syncthreads();
+#ifdef LLPF_USER_MODEL
+  if constexpr (DYN == 2) {   // user-defined model: the raw vectors of the pass (u of both steps, y of the weighed one)
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + MAX_NU) {
+      const int c = threadIdx.x - 64;
+      sh.u_prop[c] = (k_u > 0 && c < M.nu) ? __ldg(P.u + (size_t)(k_u - 1) * M.nu + c) : 0.0;
+      sh.u_weigh[c] = (k_y > 0 && c < M.nu) ? __ldg(P.u + (size_t)(k_y - 1) * M.nu + c) : 0.0;
+      if (c < NY) sh.y_raw[c] = (k_y > 0) ? __ldg(P.y + (size_t)(k_y - 1) * NY + c) : 0.0;
+    }
+  }
+#endif
+#ifdef LLPF_USER_MODEL
+  if (k_u > 0 && threadIdx.x < NX && DYN != 2) {
+#else
   if (k_u > 0 && threadIdx.x < NX) {
+#endif
     const double* u = P.u + (size_t)(k_u - 1) * M.nu;
     double acc = 0.0;
     if (DYN == 0) {
@@ -1543,7 +1601,11 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
       }
       if (weigh_) {
         if (hist_x_) store_hist_x<NX>(P, k_weigh, gi, x);
+#ifdef LLPF_USER_MODEL
+        if (!skip_) wv += weigh_loglik<NX, NY, DYN>(M, sh, yt, x, step_time(P, k_weigh));
+#else
         if (!skip_) wv += meas_loglik<NX, NY>(M, sh, yt, x);
+#endif
         __stcg(P.w + i, wv);
         acc.add(wv, x, with_x_, sh.mt);
       }
@@ -1586,6 +1648,12 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   double bu[NX], yt[NY];
   bool skip;
   stage_step<NX, NY, DYN>(P, M, sh, k, k_y1, bu, yt, skip);
+#ifdef LLPF_USER_MODEL
+  if constexpr (DYN == 2) {   // measurement_equation!(pf, u, y1, p, t, λ) gets the u of THIS step (filtering.jl:202)
+    if (threadIdx.x < MAX_NU) sh.u_weigh[threadIdx.x] = sh.u_prop[threadIdx.x];
+    __syncthreads();
+  }
+#endif
   const bool adv = (P.filter == 3);
   const double tprop = step_time(P, k);
   const double* cur = P.x[sc.cur];
@@ -1606,7 +1674,11 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
     }
     dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);                 // :199 no noise
     if (!adv) store_x<NX>(oth, P.ld, i, x);
+#ifdef LLPF_USER_MODEL
+    const double lam = skip ? 0.0 : weigh_loglik<NX, NY, DYN>(M, sh, yt, x, tprop);   // same t as the propagation (:202)
+#else
     const double lam = skip ? 0.0 : meas_loglik<NX, NY>(M, sh, yt, x);  // :200-202
+#endif
     __stcg(P.lam + i, lam);
     const double v = wn + lam;                                    // :203
     __stcg(P.w + i, v);
@@ -1717,6 +1789,11 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
   __shared__ Shared sh;
   math_tab_load(sh.mt);
   model_to_shared<NX, NY>(M, sh);
+#ifdef LLPF_USER_MODEL
+  if constexpr (DYN == 2) {
+    if (threadIdx.x == 0) sh.user_p = P.user_p;
+  }
+#endif
   __syncthreads();
   Scalars sc = *P.sc;   // every block carries an identical copy in registers; block 0 writes it back
   Ctx cx;

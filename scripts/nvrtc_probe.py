@@ -16,8 +16,31 @@ template __global__ void k_engine<4, 2, 0, 0>(const __grid_constant__ EngineP, c
 '''
 
 
-def compile_engine():
-    err, prog = nvrtc.nvrtcCreateProgram(SRC, b"user_engine.cu", 0, [], [])
+# a model no descriptor can express: x+ = [x0 + p0 sin(x1) + u0, p1 x1 + 0.1 cos(t)], y = x0^2 + e, e ~ N(0, p2)
+USER_SRC = b'''
+#define LLPF_USER_MODEL
+#include "llpf_engine.cuh"
+namespace llpf_user {
+template <>
+__device__ void dynamics<2>(double (&x)[2], const double* u, const double* p, double t) {
+  const double x0 = x[0] + p[0] * sin(x[1]) + u[0];
+  const double x1 = p[1] * x[1] + 0.1 * cos(t);
+  x[0] = x0; x[1] = x1;
+}
+template <>
+__device__ double loglik<2>(const double (&x)[2], const double* u, const double* y, const double* p, double t) {
+  const double r = y[0] - x[0] * x[0];
+  return -0.5 * r * r / p[2] - 0.5 * log(6.283185307179586 * p[2]);
+}
+}  // namespace llpf_user
+namespace llpf {
+template __global__ void k_engine<2, 1, 2, 0>(const __grid_constant__ EngineP, const __grid_constant__ ModelP<2, 1>);
+}
+'''
+
+
+def compile_engine(src=None):
+    err, prog = nvrtc.nvrtcCreateProgram(SRC if src is None else src, b"user_engine.cu", 0, [], [])
     opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-default-device", b"-lineinfo",
             ("-I" + CSRC).encode(), b"-I/usr/local/cuda/include"]
     t0 = time.time()
@@ -31,8 +54,11 @@ def compile_engine():
 
 
 if __name__ == "__main__":
-    rc, dt, log, nb = compile_engine()
-    print(f"nvrtc rc={rc} in {dt:.1f} s, cubin {nb} bytes")
-    if log:
-        print(log[:4000])
-    sys.exit(0 if rc == 0 and nb > 0 else 1)
+    ok = True
+    for name, src in (("k_engine<4,2,0,0>", None), ("k_engine<2,1,2,0> + user model", USER_SRC)):
+        rc, dt, log, nb = compile_engine(src)
+        print(f"{name}: nvrtc rc={rc} in {dt:.1f} s, cubin {nb} bytes")
+        if log:
+            print(log[:4000])
+        ok = ok and rc == 0 and nb > 0
+    sys.exit(0 if ok else 1)
