@@ -145,6 +145,79 @@ def test_resample_systematic_matches_python_restatement(N, M):
         assert np.array_equal(j, jp)
 
 
+# ---- independent re-derivations of resample.jl:38-61 (stratified) and :63-117 (residual) in plain Python floats ------
+def _py_stratified(we, us, M=None, j0=None):
+    N = len(we)
+    M = N if M is None else M
+    bins = [0.0] * N
+    bins[0] = float(we[0])
+    for i in range(1, N):
+        bins[i] = bins[i - 1] + float(we[i])
+    j = [0] * M if j0 is None else list(j0)
+    bo = 0
+    for i in range(M):
+        s = ((i + float(us[i])) / M) * bins[-1]        # ((i-1) + rand())/M * bins[end], i 1-based in the reference
+        for b in range(bo, N):
+            if s < bins[b]:
+                j[i] = b + 1
+                bo = b
+                break
+    return np.array(j), np.array(bins)
+
+
+def _py_residual(we, us, M=None, j0=None):
+    N = len(we)
+    M = N if M is None else M
+    wsum = 0.0
+    for i in range(N):
+        wsum += float(we[i])
+    inv_wsum = 1 / wsum
+    j = [0] * M if j0 is None else list(j0)
+    bins = [0.0] * N
+    num = 0
+    for i in range(N):
+        nw = float(we[i]) * inv_wsum * M
+        cnt = int(np.floor(nw))
+        bins[i] = nw - cnt
+        for _ in range(cnt):
+            j[num] = i + 1
+            num += 1
+    if num == M:
+        return np.array(j), np.array(bins)
+    rsum = 0.0
+    for i in range(N):
+        rsum += bins[i]
+    inv_rsum = 1 / rsum
+    for i in range(N):
+        bins[i] *= inv_rsum
+    for i in range(1, N):
+        bins[i] += bins[i - 1]
+    k = 0
+    for m in range(num, M):
+        u = float(us[k]); k += 1
+        for i in range(N):
+            if u < bins[i]:
+                j[m] = i + 1
+                break
+    return np.array(j), np.array(bins)
+
+
+@pytest.mark.parametrize("N,M", [(5, 5), (10, 10), (300, 300), (100, 37), (64, 200)])
+def test_resample_stratified_and_residual_match_python_restatements(N, M):
+    rng = np.random.default_rng(3 * N + M)
+    for rep in range(4):
+        _, _, we = O.logsumexp(rng.standard_normal(N) * (1 + rep))
+        us = rng.random(M)
+        j0 = np.full(M, -3, dtype=np.int64)
+        j, b = O.resample_stratified(we, us, M, j0=j0)
+        jp, bp = _py_stratified(we, us, M, j0=j0)
+        assert np.array_equal(b, bp) and np.array_equal(j, jp)
+        j, b = O.resample_residual(we, us, M, j0=j0, return_bins=True)
+        jp, bp = _py_residual(we, us, M, j0=j0)
+        assert np.array_equal(b, bp) and np.array_equal(j, jp)
+        assert np.all(np.sort(j[j > 0]) >= 1) and j.max() <= N
+
+
 def test_resample_stale_entries_keep_previous_value():
     # Q3: weights that sum to less than the last threshold leave trailing j untouched
     we = np.array([0.25, 0.25, 0.25, 0.2])       # bins[end] = 0.95
