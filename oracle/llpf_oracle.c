@@ -236,22 +236,139 @@ static void cumsum_serial(const double* we, double* bins, int64_t N) {
   for (int64_t i = 1; i < N; ++i) bins[i] = bins[i - 1] + we[i];
 }
 
+/* ---- Julia Base's Float64 range `start:step:stop` (base/twiceprecision.jl) ----------------------------------
+ * resample.jl:24 builds  s = r:(1/M):(bins[N]+r)  and compares s[i] with bins (:28).  Base is not under the
+ * reference tree; the functions below restate the published algorithm of Julia 1.6 - 1.11 one to one
+ * (rat, (:)(start,step,stop), floatrange, steprangelen_hp, TwicePrecision{Float64}((n,d)[,nb]), twiceprecision,
+ * truncbits, nbitslen, add12, mul12, canonicalize2, TwicePrecision division, unsafe_getindex).  An independent
+ * Python restatement lives in oracle/julia_range.py; tests/test_julia_range.py compares the two bit for bit.
+ *   fallback path (start / stop not exact small rationals: the case for a 53-bit rand()):
+ *       s[i] = fl(r + fl((i-1) * fl(1/M)))        (product rounded, then one add; no FMA)
+ *   rational path (rand() == 0, dyadic test inputs, ~1e-3 of random draws at N = 10, ~1e-8 at N = 2^20):
+ *       s[i] = double-double evaluation of (start_n + (i-1) step_n)/den  (can differ in the last bit)        */
+typedef struct { double ref_hi, ref_lo, step_hi, step_lo; int64_t len, offset; int rational; } orc_range;
+
+static void jl_rat(double x, int64_t* num, int64_t* den) {
+  double y = x;
+  int64_t a = 1, d = 1, b = 0, c = 0;
+  const double m = 16777216.0;                     /* maxintfloat(narrow(Float64)) = maxintfloat(Float32) */
+  while (fabs(y) <= m) {
+    const int64_t f = (int64_t)y;                  /* trunc(Int, y) */
+    y -= (double)f;
+    const int64_t a2 = f * a + c, b2 = f * b + d;
+    c = a; a = a2; d = b; b = b2;
+    if (!((llabs(a) > llabs(b) ? llabs(a) : llabs(b)) <= (int64_t)m)) { *num = c; *den = d; return; }
+    if ((double)a / (double)b == x) break;
+    y = 1.0 / y;                                   /* inv(0.0) = Inf ends the loop */
+  }
+  *num = a; *den = b;
+}
+static int jl_isbetween(double a, double x, double b) { return (a <= x && x <= b) || (b <= x && x <= a); }
+static void jl_canonicalize2(double big, double little, double* h, double* l) {
+  *h = big + little;
+  *l = (big - *h) + little;
+}
+static void jl_add12(double x, double y, double* h, double* l) {
+  if (fabs(y) > fabs(x)) { const double t = x; x = y; y = t; }
+  jl_canonicalize2(x, y, h, l);
+}
+static void jl_tp_div(double xhi, double xlo, double yhi, double ylo, double* h, double* l) {
+  const double hi = xhi / yhi;
+  const double uh = hi * yhi;
+  const double ul = fma(hi, yhi, -uh);             /* mul12: exact product error */
+  const double lo = ((((xhi - uh) - ul) + xlo) - hi * ylo) / yhi;
+  jl_canonicalize2(hi, lo, h, l);
+}
+static double jl_truncbits(double x, int nb) {
+  uint64_t u; memcpy(&u, &x, 8);
+  u &= (nb >= 64) ? 0ull : (~0ull << nb);
+  memcpy(&x, &u, 8);
+  return x;
+}
+static int jl_nbitslen(int64_t len, int64_t offset) {
+  if (len < 2) return 0;
+  const int64_t a = offset - 1, b = len - offset;
+  const int nb = (int)ceil(log2((double)(a > b ? a : b))) + 1;
+  return nb < 27 ? nb : 27;                        /* min(cld(precision(Float64), 2), ...) */
+}
+static void jl_tp_ratio(int64_t n, int64_t d, int nb, double* h, double* l) {
+  jl_tp_div((double)n, 0.0, (double)d, 0.0, h, l); /* |n|, |d| <= 2^53: exact conversions */
+  if (nb >= 0) { const double h2 = jl_truncbits(*h, nb); *l = (*h - h2) + *l; *h = h2; }
+}
+static int64_t jl_gcd(int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return llabs(a); }
+
+void orc_julia_range(double start, double step, double stop, orc_range* R) {
+  int64_t step_n, step_d, start_n, start_d, stop_n, stop_d;
+  jl_rat(step, &step_n, &step_d);
+  if (step_d != 0 && (double)step_n / (double)step_d == step) {
+    jl_rat(start, &start_n, &start_d);
+    jl_rat(stop, &stop_n, &stop_d);
+    if (start_d != 0 && stop_d != 0 && (double)start_n / (double)start_d == start &&
+        (double)stop_n / (double)stop_d == stop) {
+      const int64_t den = start_d / jl_gcd(start_d, step_d) * step_d;     /* lcm_unchecked; both <= 2^24 */
+      const double m = 9007199254740992.0;                                /* maxintfloat(Float64) */
+      if (den != 0 && fabs(start * (double)den) <= m && fabs(step * (double)den) <= m &&
+          den % start_d == 0 && den % step_d == 0) {
+        start_n = (int64_t)nearbyint(start * (double)den);
+        step_n = (int64_t)nearbyint(step * (double)den);
+        const __int128 q = ((__int128)den * stop_n) / stop_d;
+        int64_t len = (int64_t)((q - start_n) / step_n) + 1;
+        if (len < 0) len = 0;
+        if (jl_isbetween(start, start + (double)(len - 1) * step, stop + step / 2) &&
+            !jl_isbetween(start, start + (double)len * step, stop)) {
+          R->rational = 1; R->len = len;
+          if (len < 2 || step_n == 0) {
+            R->offset = 1;
+            jl_tp_ratio(start_n, den, -1, &R->ref_hi, &R->ref_lo);
+            jl_tp_ratio(step_n, den, 0, &R->step_hi, &R->step_lo);
+            return;
+          }
+          int64_t imin = (int64_t)nearbyint(-(double)start_n / (double)step_n + 1);
+          if (imin < 1) imin = 1;
+          if (imin > len) imin = len;
+          const int64_t ref_n = start_n + (imin - 1) * step_n;
+          R->offset = imin;
+          jl_tp_ratio(ref_n, den, -1, &R->ref_hi, &R->ref_lo);
+          jl_tp_ratio(step_n, den, jl_nbitslen(len, imin), &R->step_hi, &R->step_lo);
+          return;
+        }
+      }
+    }
+  }
+  const double lf = (stop - start) / step;
+  int64_t len;
+  if (lf < 0) len = 0;
+  else if (lf == 0) len = 1;
+  else {
+    len = (int64_t)nearbyint(lf) + 1;
+    const double stop2 = start + (double)(len - 1) * step;
+    len -= (start < stop && stop < stop2) + (start > stop && stop > stop2);
+  }
+  R->rational = 0; R->len = len; R->offset = 1;
+  R->ref_hi = start; R->ref_lo = 0.0; R->step_hi = step; R->step_lo = 0.0;
+}
+/* unsafe_getindex(r::StepRangeLen{Float64,TwicePrecision,TwicePrecision}, i), i 1-based, no bounds check
+   (resample.jl:27-28 index under @inbounds) */
+double orc_julia_range_getindex(const orc_range* R, int64_t i) {
+  const double u = (double)(i - R->offset);
+  const double shift_hi = u * R->step_hi, shift_lo = u * R->step_lo;
+  double x_hi, x_lo;
+  jl_add12(R->ref_hi, shift_hi, &x_hi, &x_lo);
+  return x_hi + (x_lo + (shift_lo + R->ref_lo));
+}
+
 /* resample(ResampleSystematic, we, j, bins, M)  resample.jl:17-36, with rand() (:23) given as u01.
- * s = r:(1/M):(bins[N]+r) is a Float64 StepRangeLen built by Julia Base's fallback path
- * (base/twiceprecision.jl, steprangelen_hp with nb=0), whose getindex evaluates
- *     s[i] = fl(r + fl((i-1) * fl(1/M)))          (product rounded, then one add; no FMA).
- * (Base is not under the reference tree; formula restated from base/twiceprecision.jl
- *  unsafe_getindex: u=i-1; shift_hi=u*step.hi; add12(ref.hi,shift_hi); lo parts are zero.)
- * j is 1-based.  Entries for which no bin satisfies s[i] < bins[b] keep their previous value. */
+ * s = r:(1/M):(bins[N]+r) is Julia Base's Float64 range (above).  j is 1-based.  Entries for which no bin
+ * satisfies s[i] < bins[b] keep their previous value. */
 void orc_resample_systematic(const double* we, int64_t N, double u01, int64_t M, int64_t* j,
                              double* bins) {
   cumsum_serial(we, bins, N);
   const double r = u01 * bins[N - 1] / (double)N;
-  const double step = 1.0 / (double)M;
+  orc_range s;
+  orc_julia_range(r, 1.0 / (double)M, bins[N - 1] + r, &s);
   int64_t bo = 0;
   for (int64_t i = 0; i < M; ++i) {
-    volatile double prod = (double)i * step; /* volatile: forbid contraction with the add */
-    const double si = r + prod;
+    const double si = orc_julia_range_getindex(&s, i + 1);
     for (int64_t b = bo; b < N; ++b) {
       if (si < bins[b]) {
         j[i] = b + 1;

@@ -25,6 +25,12 @@ ip = C.POINTER(C.c_int64)
 i32p = C.POINTER(C.c_int32)
 
 
+class JuliaRange(C.Structure):
+    """orc_range of llpf_oracle.c: Julia's StepRangeLen{Float64,TwicePrecision,TwicePrecision}"""
+    _fields_ = [("ref_hi", C.c_double), ("ref_lo", C.c_double), ("step_hi", C.c_double), ("step_lo", C.c_double),
+                ("len", C.c_int64), ("offset", C.c_int64), ("rational", C.c_int)]
+
+
 def build(force=False):
     src = os.path.join(_HERE, "llpf_oracle.c")
     if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
@@ -89,6 +95,10 @@ def lib():
         L.orc_effective_particles.restype = C.c_double
         L.orc_resample_systematic.argtypes = [dp, C.c_int64, C.c_double, C.c_int64, ip, dp]
         L.orc_resample_systematic.restype = None
+        L.orc_julia_range.argtypes = [C.c_double, C.c_double, C.c_double, C.POINTER(JuliaRange)]
+        L.orc_julia_range.restype = None
+        L.orc_julia_range_getindex.argtypes = [C.POINTER(JuliaRange), C.c_int64]
+        L.orc_julia_range_getindex.restype = C.c_double
         L.orc_resample_stratified.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, dp]
         L.orc_resample_stratified.restype = None
         L.orc_resample_residual.argtypes = [dp, C.c_int64, dp, C.c_int64, ip, dp]
@@ -162,6 +172,13 @@ def expnormalize(w, inplace=True):
 def effective_particles(we):
     we = _f64(we)
     return lib().orc_effective_particles(_p(we), we.size)
+
+
+def julia_range(start, step, stop):
+    """Julia Base `start:step:stop` (Float64) as restated in llpf_oracle.c; returns (JuliaRange, getindex)."""
+    R = JuliaRange()
+    lib().orc_julia_range(float(start), float(step), float(stop), C.byref(R))
+    return R, (lambda i: lib().orc_julia_range_getindex(C.byref(R), int(i)))
 
 
 def resample_systematic(we, u01, M=None, j0=None):
