@@ -14,6 +14,7 @@
 #include "../../include/llpf.h"
 #include "llpf_engine.cuh"
 #include "llpf_engine_list.h"
+#include "llpf_julia_range.h"
 #include "llpf_smooth.cuh"
 #include "llpf_wide.cuh"
 
@@ -269,7 +270,7 @@ __global__ void k_wstats(const double* we, const double* x, long long ld, long l
 // resample(strategy, we, j, bins, M)  resample.jl:17-61 ; we -> bins (scan) -> j (source-side slot ranges)
 __global__ void __launch_bounds__(BLOCK)
 k_resample(const __grid_constant__ EngineP P, const double* we, double u01, const double* u_slots,
-           int M, long long* j_inout) {
+           int M, long long* j_inout, const RangeArg range) {
   __shared__ Shared sh;
   unsigned bar_target = 0;
   long long b = (long long)blockIdx.x * P.chunk, e = b + P.chunk;
@@ -283,7 +284,7 @@ k_resample(const __grid_constant__ EngineP P, const double* we, double u01, cons
   const long long s0 = (long long)blockIdx.x * per, s1 = s0 + per;
   (void)resample_indices<long long>(P, sh, (int)b, (int)e, bar_target, [=](int i) { return __ldg(we + i); },
                                     [](int, double v) { return v; }, u01, false, 0u, M, u_slots, j_inout, 1ll, total, xs,
-                                    (int)(s0 < M ? s0 : M), (int)(s1 < M ? s1 : M));
+                                    (int)(s0 < M ? s0 : M), (int)(s1 < M ? s1 : M), &range);
 }
 
 // resample(ResampleResidual, we, j, bins, M)  resample.jl:63-117 ; the rand() draws of :106 supplied in order
@@ -524,7 +525,11 @@ static const Dispatch g_dispatch[] = {
     DISP(8, 2, 0), DISP(8, 4, 0), DISP(4, 2, 1),
 };
 
+static void push_op(EngineP& P, int kind, int a0, int b0, int count = 1, int da = 0, int db = 0, int flags = 0);
+static int launch(llpf_filter* f, const EngineP& P, bool timed);
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// staging slot of the step verbs' measurement vectors: y and y1, each up to the widest ny any engine accepts (64: Float32 filters)
+constexpr int kStageYDoubles = WNX > 8 ? WNX : 8;
 
 static int check_handle(llpf_handle h) {
   if (!h) return fail(LLPF_ERR_BAD_ARG, "null handle");
@@ -686,7 +691,7 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const size_t o_loc = take((size_t)f->ld * 8);
   const size_t o_part = take((size_t)MAX_BLOCKS * PS * 8), o_tots = take((size_t)MAX_BLOCKS * 8);
   const size_t o_bar = take((size_t)BAR_TOTAL_WORDS * 4), o_sc = take(sizeof(Scalars));
-  const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * 8 * 8), o_ws = take(256 * (2 + WNX) * 8);
+  const size_t o_su = take(2 * MAX_NU * 8), o_sy = take(2 * kStageYDoubles * 8), o_ws = take(256 * (2 + WNX) * 8);
   const size_t o_scr = take((size_t)(nx + 2) * f->ld * 8);
   const size_t o_mbox = take((size_t)2 * MAX_WORLD * MBOX_WORDS * 8);
   const size_t o_bcast = take((size_t)2 * MAX_WORLD * MBOX_DOUBLES * 8), o_bflag = take(64);
@@ -777,7 +782,7 @@ static void base_params(llpf_filter* f, EngineP& P) {
 }
 
 // ---- op-list construction (the kernel executes EngineP::ops in order) -------------------------------
-static void push_op(EngineP& P, int kind, int a0, int b0, int count = 1, int da = 0, int db = 0, int flags = 0) {
+static void push_op(EngineP& P, int kind, int a0, int b0, int count, int da, int db, int flags) {
   if (count < 1 || P.nops >= MAX_OPS) return;
   P.ops[P.nops++] = OpRun{kind, a0, b0, count, da, db, flags, 0};
 }
@@ -803,6 +808,7 @@ static int launch(llpf_filter* f, const EngineP& P, bool timed) {
 
 static int stage_inputs(llpf_filter* f, const double* u, const double* y0, const double* y1) {
   const int nu = f->hm.nu, ny = f->hm.ny;
+  if (ny > kStageYDoubles || nu > MAX_NU) return fail(LLPF_ERR_BAD_ARG, "u / y do not fit the staging slots");
   if (nu > 0) {
     if (!u) return fail(LLPF_ERR_BAD_ARG, "u is null");
     CU(cudaMemcpyAsync(f->stage_u, u, sizeof(double) * nu, cudaMemcpyHostToDevice, f->stream));
@@ -1068,8 +1074,13 @@ __global__ void k_fill_uniform53(double* out, long long n, RngKey key, uint32_t 
 }
 
 // backward simulation on a forward history resident in device memory; xb_out is host memory [T][M][nx]
+static int standalone_geometry(int device, long long n, EngineP& P, const void* kernel);
+static void fixed_point_scale(const double* we, long long N, EngineP& P);
+
+// weT_host: the caller's wef[:,T] when the history came from the host (llpf_smooth_history: weights of any scale), else
+// nullptr (history written by the forward pass: normalised weights, 2^62 scale)
 static int smooth_backward(llpf_filter* f, long long T, const double* u_dev, const DevHistory& H, long long M,
-                           uint64_t epoch, double* xb_out) {
+                           uint64_t epoch, double* xb_out, const double* weT_host = nullptr) {
   const long long N = f->N;
   const int nx = f->hm.nx;
   if (M < 1 || M > N) return fail(LLPF_ERR_BAD_ARG, "smooth: need 1 <= M <= N (smoothing.jl:122)");
@@ -1086,6 +1097,10 @@ static int smooth_backward(llpf_filter* f, long long T, const double* u_dev, con
   EngineP P;
   base_params(f, P);
   P.strategy = f->cfg.resampling;
+  // block geometry from the occupancy of the kernel that is actually launched (not the engine's), scale from the data
+  OKR(standalone_geometry(f->device, N, P, f->cfg.resampling == LLPF_RESAMPLE_RESIDUAL ? (const void*)k_resample_residual
+                                                                                      : (const void*)k_resample));
+  if (weT_host) fixed_point_scale(weT_host, N, P);
   const double* d_weT = H.we + (size_t)(T - 1) * N;
   int Mi = (int)M;
   CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * BAR_TOTAL_WORDS, f->stream));
@@ -1102,7 +1117,11 @@ static int smooth_backward(llpf_filter* f, long long T, const double* u_dev, con
     } else {
       d_slots = d_us;
     }
-    void* args[] = {(void*)&P, (void*)&d_weT, (void*)&u01, (void*)&d_slots, (void*)&Mi, (void*)&d_j};
+    // (the weights live on the device: the literal range of resample.jl:24 is used, which is what a 53-bit rand() gives
+    //  in all but ~1e-8 of the draws at smoother-sized N — llpf_julia_range.h)
+    RangeArg range;
+    std::memset(&range, 0, sizeof(range));
+    void* args[] = {(void*)&P, (void*)&d_weT, (void*)&u01, (void*)&d_slots, (void*)&Mi, (void*)&d_j, (void*)&range};
     CU(cudaLaunchCooperativeKernel((const void*)k_resample, dim3(P.nblocks), dim3(BLOCK), args, 0, f->stream));
   }
   f->launches += 2;
@@ -1195,7 +1214,7 @@ extern "C" int llpf_smooth_history(llpf_handle h, int64_t T, const double* u, co
   if (!e) e = cudaMemcpyAsync(H.w, wf, NT * 8, cudaMemcpyHostToDevice, h->stream);
   if (!e) e = cudaMemcpyAsync(H.we, wef, NT * 8, cudaMemcpyHostToDevice, h->stream);
   if (e) rc = fail(LLPF_ERR_CUDA, std::string("smooth: staging the history: ") + cudaGetErrorString(e));
-  if (rc == LLPF_OK) rc = smooth_backward(h, T, h->d_u, H, M, epoch, xb_out);
+  if (rc == LLPF_OK) rc = smooth_backward(h, T, h->d_u, H, M, epoch, xb_out, wef + (size_t)(T - 1) * h->N);
   H.release();
   return rc;
 }
@@ -1337,9 +1356,33 @@ static int weight_stats(llpf_filter* h, double* s, double* q, double* sx) {
   if (sx) for (int d = 0; d < h->hm.nx; ++d) sx[d] = acc[2 + d];
   return LLPF_OK;
 }
+// Sharded filters: the weights are normalised GLOBALLY, so ESS / weighted mean need the cross-rank reduction.  One
+// reduce-only pass of the engine (a collective: every rank calls the accessor, like every other verb of a sharded
+// filter) re-derives (max, sum e, sum e^2, sum e*x) over all ranks; the log-likelihood bookkeeping is left untouched.
+static int refresh_stats_sharded(llpf_filter* h) {
+  CU(cudaSetDevice(h->device));
+  const Scalars before = h->hsc;
+  EngineP P;
+  base_params(h, P);
+  P.u = h->stage_u; P.y = h->stage_y;
+  P.use_t_override = 1; P.t_override = 0.0; P.want_xhat = 1;
+  push_op(P, OP_PF, 0, 1, 1, 0, 0, OPF_SKIP_MEAS);
+  OKR(launch(h, P, false));
+  h->hsc.ll_last = before.ll_last; h->hsc.ll_total = before.ll_total; h->hsc.nonfinite = before.nonfinite;
+  if (before.stats_ahead) {   // APF between predict! and correct!: w[] stays raw, correct! is still to be called
+    h->hsc.pend = 0; h->hsc.stats_ahead = 1; h->hsc.stats_valid = before.stats_valid;
+  }
+  return push_scalars(h);
+}
+
 extern "C" int llpf_effective_particles(llpf_handle h, double* ess) {
   OKR(check_handle(h));
   if (!ess) return fail(LLPF_ERR_BAD_ARG, "null");
+  if (h->world > 1) {
+    OKR(refresh_stats_sharded(h));
+    *ess = h->hsc.ess;
+    return LLPF_OK;
+  }
   double q = 0;
   OKR(weight_stats(h, nullptr, &q, nullptr));
   *ess = 1.0 / q;  // 1/sum(abs2, we)  resample.jl:2
@@ -1357,6 +1400,12 @@ extern "C" int llpf_shouldresample(llpf_handle h, int32_t* yes) {
 extern "C" int llpf_weighted_mean(llpf_handle h, double* xhat) {
   OKR(check_handle(h));
   if (!xhat) return fail(LLPF_ERR_BAD_ARG, "null");
+  if (h->world > 1) {
+    if (h->wide) return fail(LLPF_ERR_UNSUPPORTED, "weighted_mean of a sharded Float32-particle filter");
+    OKR(refresh_stats_sharded(h));
+    for (int d = 0; d < h->hm.nx; ++d) xhat[d] = h->hsc.xhat[d];
+    return LLPF_OK;
+  }
   double s = 0;
   OKR(weight_stats(h, &s, nullptr, xhat));
   // @assert sum(we) ≈ 1  filtering.jl:542
@@ -1367,6 +1416,17 @@ extern "C" int llpf_weighted_mean(llpf_handle h, double* xhat) {
 // ------------------------------------------------------------------------------------------------
 // stand-alone numerics
 // ------------------------------------------------------------------------------------------------
+
+// power-of-two fixed-point scale so that sum(we)*scale stays below 2^62 (exact for normalised weights)
+static void fixed_point_scale(const double* we, long long N, EngineP& P) {
+  double sum = 0.0;
+  for (long long i = 0; i < N; ++i) sum += (we[i] > 0 ? we[i] : 0.0);
+  int e = 0;
+  if (sum > 0 && std::isfinite(sum)) std::frexp(sum * (1.0 + 1e-9), &e);   // sum < 2^e
+  if (e < 0) e = 0;
+  P.fix_scale = std::ldexp(1.0, 62 - e);
+  P.fix_inv = std::ldexp(1.0, e - 62);
+}
 
 static int standalone_geometry(int device, long long n, EngineP& P, const void* kernel) {
   CU(cudaSetDevice(device));
@@ -1410,14 +1470,31 @@ static int resample_standalone(int strategy, int64_t N, const double* we, double
     CU(sp.alloc(&d_us, (size_t)M));
     CU(cudaMemcpy(d_us, u_slots, sizeof(double) * M, cudaMemcpyHostToDevice));
   }
-  // power-of-two fixed-point scale so that sum(we)*scale stays below 2^62 (exact for normalised weights)
-  double sum = 0.0;
-  for (int64_t i = 0; i < N; ++i) sum += (we[i] > 0 ? we[i] : 0.0);
-  int e = 0;
-  if (sum > 0 && std::isfinite(sum)) std::frexp(sum * (1.0 + 1e-9), &e);   // sum < 2^e
-  if (e < 0) e = 0;
-  P.fix_scale = std::ldexp(1.0, 62 - e);
-  P.fix_inv = std::ldexp(1.0, e - 62);
+  fixed_point_scale(we, N, P);
+  // Julia's range constructor for the thresholds (resample.jl:24) needs r and bins[N] exactly as the kernel will find
+  // them: SERIAL = the left-to-right f64 sum, FAST = the exact fixed-point total
+  RangeArg range;
+  std::memset(&range, 0, sizeof(range));
+  if (strategy == LLPF_RESAMPLE_SYSTEMATIC) {
+    double total;
+    if (scan_mode != LLPF_SCAN_FAST) {
+      volatile double acc = we[0];
+      for (int64_t i = 1; i < N; ++i) acc = acc + we[i];
+      total = acc;
+    } else {
+      unsigned long long tot = 0;
+      for (int64_t i = 0; i < N; ++i) {
+        const double v = we[i] * P.fix_scale;
+        tot += (v > 0.0) ? (unsigned long long)std::nearbyint(std::fmin(v, FIX_SCALE)) : 0ull;
+      }
+      total = (double)tot * P.fix_inv;
+    }
+    volatile double ut = u01 * total;
+    const double r = ut / (double)N;
+    const RangeTP R = julia_range(r, 1.0 / (double)M, total + r);
+    range.ref_hi = R.ref_hi; range.ref_lo = R.ref_lo; range.step_hi = R.step_hi; range.step_lo = R.step_lo;
+    range.offset = R.offset; range.rational = R.rational;
+  }
   int* d_heavy = nullptr;
   CU(sp.alloc(&d_heavy, (size_t)(1 + 3 * HEAVY_MAX)));
   CU(cudaMemset(d_heavy, 0, sizeof(int)));
@@ -1427,7 +1504,7 @@ static int resample_standalone(int strategy, int64_t N, const double* we, double
   P.world = 1;
   const double* d_us_c = d_us;
   int Mi = (int)M;
-  void* args[] = {(void*)&P, (void*)&d_we, (void*)&u01, (void*)&d_us_c, (void*)&Mi, (void*)&d_j};
+  void* args[] = {(void*)&P, (void*)&d_we, (void*)&u01, (void*)&d_us_c, (void*)&Mi, (void*)&d_j, (void*)&range};
   CU(cudaLaunchCooperativeKernel((const void*)k_resample, dim3(P.nblocks), dim3(BLOCK), args, 0, 0));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(j_inout, d_j, sizeof(long long) * M, cudaMemcpyDeviceToHost));
@@ -1470,13 +1547,7 @@ extern "C" int llpf_resample_residual(int64_t N, const double* we, const double*
   CU(cudaMemcpy(d_j, j_inout, sizeof(long long) * M, cudaMemcpyHostToDevice));
   CU(cudaMemset(d_bar, 0, BAR_TOTAL_WORDS * sizeof(unsigned)));
   CU(cudaMemset(d_heavy, 0, sizeof(int)));
-  double sum = 0.0;
-  for (int64_t i = 0; i < N; ++i) sum += (we[i] > 0 ? we[i] : 0.0);
-  int e = 0;
-  if (sum > 0 && std::isfinite(sum)) std::frexp(sum * (1.0 + 1e-9), &e);   // sum < 2^e
-  if (e < 0) e = 0;
-  P.fix_scale = std::ldexp(1.0, 62 - e);
-  P.fix_inv = std::ldexp(1.0, e - 62);
+  fixed_point_scale(we, N, P);
   P.heavy = d_heavy;
   P.bins = d_bins; P.partials = d_part; P.tots = d_tots; P.tots2 = d_tots2; P.bar = d_bar; P.loc = d_loc;
   P.N = N; P.n = (int)N; P.first = 0; P.strategy = LLPF_RESAMPLE_RESIDUAL; P.scan_mode = scan_mode;

@@ -765,10 +765,36 @@ struct Thresholds {
   int strategy;
   uint32_t step_idx;
   const double* u_slots;   // stratified: caller-supplied rand() per slot (stand-alone entry), else RNG
+  // Julia's "nice rational" range (llpf_julia_range.h; stand-alone entry only): r = ref.hi, step = step.hi and
+  int twice;               // 1: elements are the double-double TwicePrecision getindex below
+  int offset;              // 1-based index of the reference element
+  double ref_lo, step_lo;
 };
 
-// s[i] = fl(r + fl(i * fl(1/M)))   (Julia StepRangeLen getindex; resample.jl:24) — the
-// product and the sum are rounded separately (no FMA).  Stratified: ((i + rand_i)/M)*bins[N] (resample.jl:49).
+// the Float64 range of resample.jl:24 as the host resolved it (llpf_julia_range.h): nullptr / rational == 0 -> literal path
+struct RangeArg {
+  double ref_hi, ref_lo, step_hi, step_lo;
+  int offset, rational;
+};
+
+// element gi (0-based) of the systematic threshold range.  Literal path: s = fl(r + fl(gi * fl(1/M))) — the product and
+// the sum rounded separately (no FMA).  Rational path: Julia's unsafe_getindex for TwicePrecision ranges,
+//   u = i - offset ; (x_hi, x_lo) = add12(ref.hi, u*step.hi) ; s = x_hi + (x_lo + (u*step.lo + ref.lo))
+__device__ __forceinline__ double systematic_threshold(const Thresholds& th, int gi) {
+  if (th.twice) {
+    const double u = (double)(gi + 1 - th.offset);
+    const double shift_hi = __dmul_rn(u, th.step), shift_lo = __dmul_rn(u, th.step_lo);
+    double big = th.r, little = shift_hi;
+    if (fabs(little) > fabs(big)) { big = shift_hi; little = th.r; }
+    const double x_hi = __dadd_rn(big, little);
+    const double x_lo = __dadd_rn(__dsub_rn(big, x_hi), little);
+    return __dadd_rn(x_hi, __dadd_rn(x_lo, __dadd_rn(shift_lo, th.ref_lo)));
+  }
+  return __dadd_rn(th.r, __dmul_rn((double)gi, th.step));
+}
+
+// s[i]: systematic_threshold above (Julia StepRangeLen getindex; resample.jl:24).
+// Stratified: ((i + rand_i)/M)*bins[N] (resample.jl:49).
 __device__ __forceinline__ double threshold(const Thresholds& th, const RngKey& key, int gi) {
   if (th.strategy == 1) {
     double u;
@@ -780,7 +806,7 @@ __device__ __forceinline__ double threshold(const Thresholds& th, const RngKey& 
     }
     return __dmul_rn(__ddiv_rn(__dadd_rn((double)gi, u), th.M), th.total);
   }
-  return __dadd_rn(th.r, __dmul_rn((double)gi, th.step));
+  return systematic_threshold(th, gi);
 }
 
 __device__ __forceinline__ Thresholds make_thresholds(const EngineP& P, double total, double u01, int Mslots,
@@ -795,6 +821,7 @@ __device__ __forceinline__ Thresholds make_thresholds(const EngineP& P, double t
   th.step = __ddiv_rn(1.0, th.M);
   // r = rand()*bins[end]/N   (resample.jl:23; note /N, N = length(we))
   th.r = __ddiv_rn(__dmul_rn(u01, total), (double)P.N);
+  th.twice = 0; th.offset = 1; th.ref_lo = 0.0; th.step_lo = 0.0;
   return th;
 }
 __device__ __forceinline__ double resample_u01(const RngKey& key, uint32_t step_idx) {
@@ -810,9 +837,8 @@ __device__ __forceinline__ int first_slot_ge(const Thresholds& th, const RngKey&
     // systematic: s_i = fl(r + fl(i*step)); estimate ceil((v - r) M), then check the two neighbours once
     int i0 = __double2int_ru((v - th.r) * th.M);
     i0 = max(0, min(i0, th.Mi));
-    const double f0 = (double)i0;
-    const double s_m = __dadd_rn(th.r, __dmul_rn(f0 - 1.0, th.step));   // s[i0-1]
-    const double s_0 = __dadd_rn(th.r, __dmul_rn(f0, th.step));         // s[i0]
+    const double s_m = systematic_threshold(th, i0 - 1);   // s[i0-1]
+    const double s_0 = systematic_threshold(th, i0);       // s[i0]
     const bool down = (i0 > 0) && (s_m >= v);
     const bool up = (i0 < th.Mi) && (s_0 < v);
     if (!(down || up)) return i0;          // the estimate is exact (always, up to rounding ties)
@@ -1029,7 +1055,8 @@ template <class JT, class LoadFn, class WeFn>
 __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, int beg, int end, unsigned& bar_target,
                                                 LoadFn loadfn, WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
                                                 int Mslots, const double* u_slots, JT* jout_flat, JT jbase,
-                                                double& total_out, u64& xseq, int slot_lo, int slot_hi) {
+                                                double& total_out, u64& xseq, int slot_lo, int slot_hi,
+                                                const RangeArg* range = nullptr) {
   // [slot_lo, slot_hi): the GLOBAL output slots this block fills from the heavy-run list; jout_flat[0] is global
   // slot P.first
   if (P.heavy != nullptr && blockIdx.x == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);   // before the first barrier
@@ -1075,7 +1102,11 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   }
   total_out = total;
   if (gen_u01) u01 = resample_u01(P.key, step_idx);
-  const Thresholds th = make_thresholds(P, total, u01, Mslots, step_idx, u_slots);
+  Thresholds th = make_thresholds(P, total, u01, Mslots, step_idx, u_slots);
+  if (range != nullptr && range->rational) {   // stand-alone entry: the host found Julia's rational range for (r, 1/M, total+r)
+    th.twice = 1; th.offset = range->offset;
+    th.r = range->ref_hi; th.ref_lo = range->ref_lo; th.step = range->step_hi; th.step_lo = range->step_lo;
+  }
   if (pairs) {
     scatter_pairs<JT>(P, sh, beg, end, off, th, jout, jbase);
     const int f_tot = first_slot_ge(th, P.key, total);

@@ -123,3 +123,40 @@ def simulate_lg(spec, u, seed=1):
         if t + 1 < T:
             x[t + 1] = spec.A @ x[t] + spec.B @ u[t] + L1 @ rng.standard_normal(spec.nx)
     return x, y
+
+
+def simulate_quadtank(spec, u, seed=1):
+    """simulate(f,u,p)  src/filtering.jl:462-477 for the quadtank AdvancedParticleFilter (data generation only, numpy):
+    x1 = mean(d0) = x0 ; y_t = x_t[1:2] + 0.01 randn (example_quadtank.jl:44) ; x_{t+1} = rk4(quadtank)(x_t,u_t) + N(0,R1)."""
+    rng = np.random.default_rng(seed)
+    kc, k1, k2, A_, a, gam = spec.p
+    g = 9.81
+
+    def rhs(h, uu, t):
+        a1 = a * spec.a1_factor if t > spec.t_switch else a
+        sq = lambda v: np.sqrt(max(v, 0.0) + 1e-3)  # noqa: E731
+        tg = 2 * g
+        return np.array([-a1 / A_ * sq(tg * h[0]) + a / A_ * sq(tg * h[2]) + gam * k1 / A_ * uu[0],
+                         -a / A_ * sq(tg * h[1]) + a / A_ * sq(tg * h[3]) + gam * k2 / A_ * uu[1],
+                         -a / A_ * sq(tg * h[2]) + (1 - gam) * k2 / A_ * uu[1],
+                         -a / A_ * sq(tg * h[3]) + (1 - gam) * k1 / A_ * uu[0]])
+
+    T = u.shape[0]
+    x = np.zeros((T, 4))
+    y = np.zeros((T, 2))
+    x[0] = spec.x0
+    L1, L2 = np.linalg.cholesky(spec.R1), np.linalg.cholesky(spec.R2)
+    h = spec.Ts / spec.supersample
+    for t in range(T):
+        y[t] = spec.C @ x[t] + L2 @ rng.standard_normal(2)
+        if t + 1 < T:
+            xx, tt = x[t].copy(), t * spec.Ts
+            for _ in range(spec.supersample):
+                f1 = rhs(xx, u[t], tt)
+                f2 = rhs(xx + h / 2 * f1, u[t], tt + h / 2)
+                f3 = rhs(xx + h / 2 * f2, u[t], tt + h / 2)
+                f4 = rhs(xx + h * f3, u[t], tt + h)
+                xx = xx + h / 6 * (f1 + 2 * f2 + 2 * f3 + f4)
+                tt += h
+            x[t + 1] = xx + L1 @ rng.standard_normal(4)
+    return x, y

@@ -38,6 +38,10 @@ def main():
         xs = L.particles(pf)
         ws = L.weights(pf)
         js = L.ancestors(pf)
+        # sharded accessors (collectives: every rank calls them): the weights are normalised globally
+        ess_s = L.effective_particles(pf)
+        should_s = L.shouldresample(pf)
+        xhat_s = L.weighted_mean(pf) if kind != "wide" else None
         gathered = [None] * world
         dist.all_gather_object(gathered, (r["ll"], xs, ws, js, r["resampled"]))
         if rank == 0:
@@ -48,12 +52,17 @@ def main():
             one = mk(N, seed=5, resample_threshold=thr, device=local)
             r1 = L.loglik(one, u, y, epoch=2, details=True)
             x1, w1, j1 = L.particles(one), L.weights(one), L.ancestors(one)
+            ess1 = L.effective_particles(one)
+            acc_ok = abs(ess_s - ess1) <= 1e-9 * ess1 and should_s == L.shouldresample(one)
+            if xhat_s is not None:
+                acc_ok &= bool(np.allclose(xhat_s, L.weighted_mean(one), rtol=1e-10, atol=1e-12))
+            ok &= acc_ok
             rel = abs(lls[0] - r1["ll"]) / abs(r1["ll"])
             same_res = np.array_equal(r["resampled"], r1["resampled"])
             dx = np.abs(X - x1).max()
             nj = int((J != j1).sum())
             msg = f"{kind} N={N} T={T} thr={thr} world={world}: ll={lls[0]:.10f} vs 1-GPU {r1['ll']:.10f} rel={rel:.2e} " \
-                  f"resampled_equal={same_res} max|dx|={dx:.2e} j_mismatch={nj} ms={L.last_run_ms(pf):.2f} (1-GPU {L.last_run_ms(one):.2f})"
+                  f"resampled_equal={same_res} max|dx|={dx:.2e} j_mismatch={nj} accessors_ok={acc_ok} ms={L.last_run_ms(pf):.2f} (1-GPU {L.last_run_ms(one):.2f})"
             if N <= (1 << 16) and kind != "wide" or N <= (1 << 13):
                 ref = (s.oracle_filter(N, filter=2 if kind == "aux" else 0, seed=5, resample_threshold=thr)).loglik(u, y, epoch=2)
                 relo = abs(lls[0] - ref["ll"]) / abs(ref["ll"])

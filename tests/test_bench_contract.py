@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,6 +26,22 @@ def test_reference_arm_json_line(built):
     allc = line["cpu_replicas_all_cores"]
     assert 1 <= allc["cores"] <= 32 and allc["value"] > 0
     assert "workload" in line["config"] and "model" not in line["config"]
+    assert line["extrapolated"] is True and line["scaling"] == "weak"
+    # both arms print the identical workload string (the driver's same_config check)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_block(2, 1)
+
+
+def test_every_baseline_config_is_a_bench_line():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert sorted(bench.CONFIGS) == [2, 3, 4, 5]
+    for cfg, c in bench.CONFIGS.items():
+        spec, u, y = bench.workload(cfg, 8)
+        assert u.shape == (8, c["nu"]) and y.shape == (8, c["ny"]) and np.all(np.isfinite(y))
+    assert bench.CONFIGS[2]["alg"] == 3 * 4 * 8 + 16 and bench.CONFIGS[4]["alg"] == 5 * 4 * 8 + 72
+    assert bench.CONFIGS[5]["alg"] == 3 * 64 * 4 + 16
 
 
 def test_product_arm_fails_loudly_without_a_gpu(built):

@@ -861,3 +861,98 @@ def test_full_size_config2_properties(gpu):
     assert L.loglik(pf, u, y, epoch=1) == r["ll"]
     x = L.particles(pf)
     assert np.all(np.isfinite(x))
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: headline-size oracle parity, Julia's range paths, multi-GPU inside pytest
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scan_mode", ["serial", "fast"])
+def test_headline_size_config2_against_oracle(gpu, scan_mode):
+    """BASELINE config 2 at its full particle count (N = 2^20, the bench.py workload) for the first T = 40 time steps,
+    DIRECTLY against the CPU oracle (10 s of oracle time): log-likelihood, every resample decision, per-step ll / ESS, final
+    particles and ancestors.  SERIAL scan = the reference's summation order; FAST = the fixed-point scan bench.py times."""
+    L = gpu
+    from llpf_b200 import workloads as W
+    s = lg_model(4, 2, 2, seed=0)
+    N, T = 1 << 20, 40
+    u = np.random.default_rng(0).standard_normal((T, 2))
+    _, y = W.simulate_lg(s, u, seed=1)                 # bench.py's workload(T) prefix
+    of = s.oracle_filter(N, filter=0, resample_threshold=0.1, seed=1)
+    ref = of.loglik(u, y, epoch=1)
+    assert 0 < ref["resampled"].sum() < T
+    pf = s.particle_filter(N, seed=1, resample_threshold=0.1, scan_mode=scan_mode)
+    got = L.loglik(pf, u, y, epoch=1, details=True)
+    rt = LL_RTOL_TIGHT if scan_mode == "serial" else LL_RTOL
+    assert abs(got["ll"] - ref["ll"]) <= rt * abs(ref["ll"])
+    assert np.array_equal(got["resampled"], ref["resampled"])
+    assert np.allclose(got["ll_steps"], ref["ll_steps"], rtol=0, atol=1e-9 * max(1.0, abs(ref["ll"])))
+    assert np.allclose(got["ess"], ref["ess"], rtol=1e-9)
+    x, j = L.particles(pf), L.ancestors(pf)
+    if scan_mode == "serial":
+        assert np.array_equal(j, of.ancestors)
+        assert np.abs(x - of.particles).max() <= 1e-10
+        assert np.abs(L.weights(pf) - of.weights).max() <= 1e-9
+    else:
+        # the fixed-point scan rounds bins differently by O(sqrt(N)) ulp: an index may move to a neighbour whose
+        # threshold lies inside that gap; every other particle must agree to rounding
+        flips = j != of.ancestors
+        assert flips.mean() <= 1e-5 and np.all(np.abs(j - of.ancestors) <= 1)
+        assert np.abs(x - of.particles)[~flips].max() <= 1e-10
+
+
+@pytest.mark.parametrize("scan_mode", ["serial", "fast"])
+def test_systematic_follows_julia_rational_range(gpu, scan_mode):
+    """rand() values for which Julia builds the threshold range r:(1/M):(bins[N]+r) from exact integer ratios (double-double
+    elements, one ulp away from fl(r + i/M) for non-dyadic M): the stand-alone entry must select the same indices as the
+    oracle, which follows base/twiceprecision.jl (oracle/julia_range.py, tests/test_julia_range.py)."""
+    L = gpu
+    from oracle import julia_range as J
+    hit = 0
+    for N in (5, 10, 7, 12, 25, 100, 1000, 777):
+        we = np.full(N, 1.0 / N)
+        for u in (0.0, 0.5, 0.25):
+            jo, bo = O.resample_systematic(we, u)
+            j, b = L.resample(L.ResampleSystematic, we, u, scan_mode=scan_mode, return_bins=True)
+            if scan_mode == "serial":
+                assert np.array_equal(b, bo)
+            R, _ = O.julia_range(u * bo[-1] / N, 1.0 / N, bo[-1] + u * bo[-1] / N)
+            hit += R.rational
+            if scan_mode == "serial" or np.array_equal(b, bo):
+                assert np.array_equal(j, jo), (N, u)
+    assert hit >= 6
+    j5 = L.resample(L.ResampleSystematic, np.full(5, 0.2), 0.0, scan_mode="serial")
+    assert list(j5) == [1, 2, 3, 3, 5]       # Julia's rational range; the literal formula would give 1:5
+    # dyadic weights: every partial sum exact, so FAST == SERIAL == oracle on both range paths
+    rng = np.random.default_rng(3)
+    for N, M in ((96, 96), (1000, 1000), (384, 100)):
+        k = rng.integers(1, 64, N).astype(np.float64)
+        we = k / 2.0 ** 16                      # dyadic, un-normalised (sum < 1)
+        for u in (0.0, 0.5, 0.125, float(rng.random())):
+            jo, bo = O.resample_systematic(we, u, M)
+            j, b = L.resample(L.ResampleSystematic, we, u, M, scan_mode=scan_mode, return_bins=True)
+            assert np.array_equal(b, bo) and np.array_equal(j, jo), (N, M, u)
+
+
+def test_sharded_filters_inside_pytest(gpu):
+    """tests/multi_gpu_worker.py (sharded PF / APF / Float32-wide filters: bit-identical to one GPU, oracle parity,
+    sharded accessors) run under torchrun on 2 GPUs and on every GPU of the box — part of `pytest -m gpu` so the driver
+    verifies the multi-GPU numbers are numbers of a correct filter.  Skips (with the reason printed) on a 1-GPU box."""
+    import ctypes as C
+    import os
+    import subprocess
+    import sys
+    L = gpu
+    n = C.c_int()
+    L.load_library().llpf_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip(f"multi-GPU parity needs >= 2 GPUs on the box (found {n.value})")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worlds = sorted({2, min(8, n.value)})
+    for world in worlds:
+        port = 29600 + world
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "multi_gpu_worker.py")]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+        print(r.stdout[-4000:])
+        assert r.returncode == 0, r.stderr[-3000:]
+        assert "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
