@@ -365,7 +365,8 @@ struct llpf_filter {
   // sharding (one process per GPU): IPC-mapped peer arenas
   int rank = 0, world = 1;
   bool connected = false;
-  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0, o_heavy = 0, o_tots2 = 0;
+  size_t o_x0 = 0, o_x1 = 0, o_j = 0, o_mbox = 0, o_heavy = 0, o_tots2 = 0, o_pack = 0, o_pack_cnt = 0;
+  int pack_stride = 0, pack_state_bytes = 0;
   char* peer_base[MAX_WORLD] = {nullptr};
   // per-run buffers (grow-only)
   double *d_u = nullptr, *d_y = nullptr, *d_ll = nullptr, *d_ess = nullptr, *d_xhat = nullptr;
@@ -697,6 +698,14 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   const size_t o_bcast = take((size_t)2 * MAX_WORLD * MBOX_DOUBLES * 8), o_bflag = take(64);
   const size_t o_heavy = take((size_t)(1 + 3 * HEAVY_MAX) * 4);
   f->o_tots2 = take((size_t)MAX_BLOCKS * 8);
+  f->o_pack_cnt = take((size_t)MAX_WORLD * 4);
+  if (world > 1) {
+    // packed particle exchange of sharded resampling: one region per source rank, one entry per local particle at most
+    // (a particle contributes at most one entry per destination); entry = state padded to 16 B + int4 meta
+    f->pack_state_bytes = wide ? WNX * 4 : (int)align_up((size_t)nx * 8, 16);
+    f->pack_stride = wide ? WNX * 4 + 32 : f->pack_state_bytes + 16;   // wide rows stay 32-byte aligned (ld.v8.f32)
+    f->o_pack = take((size_t)world * (size_t)f->n * (size_t)f->pack_stride);
+  }
   f->o_x0 = o_x0; f->o_x1 = o_x1; f->o_j = o_j; f->o_mbox = o_mbox; f->o_heavy = o_heavy;
   f->arena_bytes = off;
   CUF(cudaMalloc(&f->arena, f->arena_bytes));
@@ -771,6 +780,10 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.bcast = f->bcast; P.bcast_flag = f->bcast_flag;
   P.heavy = (int*)(f->arena + f->o_heavy);
   P.tots2 = (u64*)(f->arena + f->o_tots2);
+  P.nx = f->hm.nx; P.wide = f->wide ? 1 : 0;
+  P.pack_cnt = (int*)(f->arena + f->o_pack_cnt);
+  P.pack_cap = f->n; P.pack_stride = f->pack_stride; P.pack_state_bytes = f->pack_state_bytes;
+  P.pack_in = f->world > 1 ? f->arena + f->o_pack : nullptr;
   for (int r = 0; r < f->world; ++r) {
     char* base = f->peer_base[r];
     P.peer_x[r][0] = base ? (double*)(base + f->o_x0) : nullptr;
@@ -778,6 +791,7 @@ static void base_params(llpf_filter* f, EngineP& P) {
     P.peer_j[r] = base ? (int*)(base + f->o_j) : nullptr;
     P.peer_mbox[r] = base ? (double*)(base + f->o_mbox) : nullptr;
     P.peer_heavy[r] = base ? (int*)(base + f->o_heavy) : nullptr;
+    P.peer_pack[r] = (base && f->world > 1) ? base + f->o_pack : nullptr;
   }
 }
 
@@ -1594,7 +1608,7 @@ struct ShardBlob {
   unsigned long long magic;
   int rank, world, nx, pad;
   long long n, ld;
-  unsigned long long arena_bytes, o_x0, o_x1, o_j, o_mbox;
+  unsigned long long arena_bytes, o_x0, o_x1, o_j, o_mbox, o_pack;
   cudaIpcMemHandle_t mem;
 };
 static const unsigned long long kBlobMagic = 0x4c4c504642323030ull;  // "LLPFB200"
@@ -1612,7 +1626,7 @@ extern "C" int llpf_shard_export(llpf_handle h, void* blob) {
   std::memset(&b, 0, sizeof(b));
   b.magic = kBlobMagic; b.rank = h->rank; b.world = h->world; b.nx = h->hm.nx;
   b.n = h->n; b.ld = h->ld; b.arena_bytes = h->arena_bytes;
-  b.o_x0 = h->o_x0; b.o_x1 = h->o_x1; b.o_j = h->o_j; b.o_mbox = h->o_mbox;
+  b.o_x0 = h->o_x0; b.o_x1 = h->o_x1; b.o_j = h->o_j; b.o_mbox = h->o_mbox; b.o_pack = h->o_pack;
   CU(cudaIpcGetMemHandle(&b.mem, h->arena));
   std::memcpy(blob, &b, sizeof(b));
   return LLPF_OK;
@@ -1626,7 +1640,8 @@ extern "C" int llpf_shard_connect(llpf_handle h, const void* blobs) {
   for (int r = 0; r < h->world; ++r) {
     const ShardBlob& b = B[r];
     if (b.magic != kBlobMagic || b.rank != r || b.world != h->world || b.nx != h->hm.nx || b.n != h->n ||
-        b.ld != h->ld || b.arena_bytes != h->arena_bytes || b.o_x0 != h->o_x0 || b.o_j != h->o_j || b.o_mbox != h->o_mbox)
+        b.ld != h->ld || b.arena_bytes != h->arena_bytes || b.o_x0 != h->o_x0 || b.o_j != h->o_j || b.o_mbox != h->o_mbox ||
+        b.o_pack != h->o_pack)
       return fail(LLPF_ERR_BAD_ARG, "shard blob mismatch (all ranks must create identical filters, blobs ordered by rank)");
   }
   for (int r = 0; r < h->world; ++r) {

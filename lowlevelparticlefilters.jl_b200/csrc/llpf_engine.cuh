@@ -159,6 +159,19 @@ struct EngineP {
   int* heavy;
   int* peer_heavy[MAX_WORLD];
   u64* tots2;             // [MAX_BLOCKS] second per-block total (residual resampling: the integer offspring counts)
+  // ---- packed particle exchange of sharded resampling (world > 1) ----
+  // A particle whose offspring run reaches into another rank's slots is SHIPPED there once per destination as a packed
+  // entry {state, global id, first slot, count}: posted stores into the destination's pack_in (region of the sending
+  // rank), indices from a local counter.  After the cross-GPU barrier (which carries the counts) the destination expands
+  // the runs into its own j (as negative entry codes) and the gathering sweep reads the state from LOCAL memory.
+  char* pack_in;                  // local: [world][pack_cap] entries of pack_stride bytes
+  char* peer_pack[MAX_WORLD];     // the same area of every rank
+  int* pack_cnt;                  // local: [MAX_WORLD] entries pushed to each destination in the current resample
+  long long pack_cap;             // entries per (source, destination) region (= local particle count: one entry per particle at most)
+  int pack_stride;                // bytes per entry: state padded to 16 B (f64 SoA particles: nx doubles; wide: 64 floats) + 16 B meta
+  int pack_state_bytes;           // offset of the meta int4 {gid, first global slot, count, 0}
+  int nx;                         // state dimension (f64 engines)
+  int wide;                       // 1: Float32 AoS rows of 64 (llpf_wide.cuh), 0: f64 SoA
 #ifdef LLPF_USER_MODEL
   const double* user_p;   // DYN == 2: the filter's parameter vector `p` (device memory), handed to the user functions
 #endif
@@ -861,25 +874,14 @@ __device__ __forceinline__ int first_slot_ge(const Thresholds& th, const RngKey&
   return i0;
 }
 
-// Destination of a global output slot: single GPU -> j + slot ; sharded -> the owner rank's j array.
+// Destination of a global output slot: j[0] is global slot `base` (sharded filters: the rank's first slot; runs are
+// clipped to the rank's own slots before they get here, the rest travels as packed entries — push_remote_parts).
 template <class T>
 struct SlotRouter {
-  T* j;                 // world == 1 (or stand-alone): flat array
-  T* const* peer;       // world > 1: per-rank arrays
-  int n;                // slots per rank
-  int world;
-  int rank;
+  T* j;
+  int base;
   int* heavy;           // grid-wide list for very long runs (nullptr: write everything directly)
-  mutable int remote;   // set once this thread has stored into another rank's array
-  __device__ __forceinline__ T* at(int slot) const {
-    if (world <= 1) return j + slot;
-    // almost every slot belongs to this rank: no division on that path (it cost the sharded scatter ~6 us per step)
-    const int ls = slot - rank * n;
-    if ((unsigned)ls < (unsigned)n) return peer[rank] + ls;
-    const int r = slot / n;
-    remote = 1;
-    return peer[r] + (slot - r * n);
-  }
+  __device__ __forceinline__ T* at(int slot) const { return j + (slot - base); }
 };
 
 // write `id` into slots [lo, lo+cnt): runs of up to 4 by predicated stores of the owning lane, longer
@@ -896,7 +898,6 @@ __device__ __forceinline__ void scatter_runs(const SlotRouter<T>& R, int lo, int
       __stcg(R.heavy + 1 + 3 * idx, lo);
       __stcg(R.heavy + 2 + 3 * idx, cnt);
       __stcg(R.heavy + 3 + 3 * idx, (int)id);
-      if (R.world > 1) R.remote = 1;   // peers read this list: make it visible system-wide before the barrier
       cnt = 0;
     }
   }
@@ -915,6 +916,80 @@ __device__ __forceinline__ void scatter_runs(const SlotRouter<T>& R, int lo, int
     const T id_s = __shfl_sync(0xffffffffu, id, src);
     for (int s = lane; s < c; s += 32) __stcg(R.at(lo_s + s), id_s);
   }
+}
+
+// ---- packed particle exchange (sharded filters) ---------------------------------------------------------------------
+// Source side.  Must be called by all 32 lanes.  The part of local particle `li`'s offspring run [lo, lo+cnt) (GLOBAL
+// slots) that lies in another rank's slot range is shipped to that rank as ONE packed entry {state, gid, first slot,
+// count} — posted stores into the destination's pack_in, region of this rank, index from a local counter (one atomic per
+// group of lanes with the same destination).  Returns the run clipped to this rank's own slots in (lo, cnt).
+__device__ __forceinline__ void push_remote_parts(const EngineP& P, int pack_buf, int& lo, int& cnt, int gid, int li,
+                                                  int& pushed) {
+  const int own_lo = P.first, own_hi = P.first + P.n;
+  const int hi = lo + cnt;
+  const bool rem = (cnt > 0) && (lo < own_lo || hi > own_hi);
+  if (!__any_sync(0xffffffffu, rem)) return;
+  const int lane = threadIdx.x & 31;
+  int d = rem ? lo / P.n : 0;
+  const int d_last = rem ? (hi - 1) / P.n : -1;
+  for (;;) {
+    if (d == P.rank) ++d;   // the own part stays with the caller
+    const bool act = rem && d <= d_last;
+    if (!__any_sync(0xffffffffu, act)) break;
+    const unsigned grp = __match_any_sync(0xffffffffu, act ? d : (MAX_WORLD + lane));
+    if (act) {
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(P.pack_cnt + d, __popc(grp));
+      base = __shfl_sync(grp, base, leader);
+      const int idx = base + __popc(grp & ((1u << lane) - 1u));
+      const int first = max(lo, d * P.n);
+      const int c = min(hi, (d + 1) * P.n) - first;
+      char* e = P.peer_pack[d] + ((size_t)P.rank * (size_t)P.pack_cap + (size_t)idx) * (size_t)P.pack_stride;
+      if (P.wide) {
+        const float4* src = reinterpret_cast<const float4*>(P.x[pack_buf]) + (size_t)li * 16;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) __stcg(reinterpret_cast<float4*>(e) + k, __ldcg(src + k));
+      } else {
+        const double* xs = P.x[pack_buf];
+        for (int k = 0; k < P.nx; ++k) __stcg(reinterpret_cast<double*>(e) + k, __ldcg(xs + (size_t)k * P.ld + li));
+      }
+      __stcg(reinterpret_cast<int4*>(e + P.pack_state_bytes), make_int4(gid, first, c, 0));
+      pushed = 1;
+      ++d;
+    }
+  }
+  const int nlo = max(lo, own_lo), nhi = min(hi, own_hi);
+  lo = nlo;
+  cnt = max(nhi - nlo, 0);
+}
+
+// Cross-GPU barrier that closes the scatter of a sharded resample; it carries, per destination, the number of packed
+// entries this rank pushed there.  Call right after the local grid barrier (every pushing thread executed
+// __threadfence_system() before arriving at it, so the entries are performed before block 0 posts the count).
+// incoming[r] = entries rank r pushed into MY pack_in (0 for r == rank).
+__device__ __forceinline__ void peer_exchange_counts(const EngineP& P, Shared& sh, u64& xseq, int (&incoming)[MAX_WORLD]) {
+  xseq += 1;
+  const int par = (int)(xseq & 1ull);
+  const u64 tag = (xseq & 0xffffffffull) << 32;
+  if (blockIdx.x == 0 && (int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+    const int r = threadIdx.x;
+    const unsigned c = (unsigned)__ldcg(P.pack_cnt + r);
+    u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
+    st_relaxed_sys_u64(out, tag | (u64)c);
+  }
+  uint32_t* words = reinterpret_cast<uint32_t*>(sh.peer_vals);
+  __syncthreads();                                               // earlier readers of sh.peer_vals are done
+  if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+    const u64* in = reinterpret_cast<const u64*>(P.peer_mbox[P.rank]) + ((size_t)par * MAX_WORLD + threadIdx.x) * MBOX_WORDS;
+    u64 v;
+    do { v = ld_relaxed_sys_u64(in); } while ((v & 0xffffffff00000000ull) != tag);
+    words[threadIdx.x] = (uint32_t)v;
+    __threadfence_system();                                      // acquire side: the entries behind the count are read next
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < MAX_WORLD; ++r) incoming[r] = (r < P.world && r != P.rank) ? (int)words[r] : 0;
 }
 
 // ---- FAST path, two adjacent particles per lane (16-byte loads/stores, half the shuffles per particle) ----
@@ -979,7 +1054,8 @@ __device__ __forceinline__ void scan_stage1_pairs(const EngineP& P, Shared& sh, 
 
 template <class JT>
 __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int beg, int end, u64 off,
-                                              const Thresholds& th, const SlotRouter<JT>& jout, JT jbase) {
+                                              const Thresholds& th, const SlotRouter<JT>& jout, JT jbase, int pack_buf,
+                                              int& pushed) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
   // F at every (row, warp) segment start: lane 0 of a segment needs it for its first particle
@@ -1019,33 +1095,74 @@ __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int 
     int fA = __shfl_up_sync(0xffffffffu, fC, 1);       // F(lo) of my first particle = F(hi) of the previous lane's second
     if (lane == 0) fA = sh.wtf[k * NWARP + warp];
     if (i >= end) { fA = 0; fB = 0; fC = 0; }
-    scatter_runs<JT>(jout, fA, fB - fA, jbase + (JT)i);
-    scatter_runs<JT>(jout, fB, fC - fB, jbase + (JT)(i + 1));
+    int l0 = fA, c0 = fB - fA, l1 = fB, c1 = fC - fB;
+    if (P.world > 1) {   // offspring in other ranks' slots travel as packed entries; the own part is scattered below
+      push_remote_parts(P, pack_buf, l0, c0, (int)jbase + i, i, pushed);
+      push_remote_parts(P, pack_buf, l1, c1, (int)jbase + i + 1, i + 1, pushed);
+    }
+    scatter_runs<JT>(jout, l0, c0, jbase + (JT)i);
+    scatter_runs<JT>(jout, l1, c1, jbase + (JT)(i + 1));
   }
 }
 
 // After the barrier(s) that close the scatter: fill the queued heavy runs into the slots [slot_lo, slot_hi) this
 // block is responsible for (the engine: exactly the slots its sweep reads next).  jout[s - slot_base] = id.
+// The list is local: runs that reach into other ranks were clipped at the source and shipped as packed entries.
 template <class JT>
-__device__ __forceinline__ void fill_heavy_runs(const EngineP& P, JT* jout, int slot_base, int slot_lo, int slot_hi,
-                                                const double (&counts)[MAX_WORLD][1]) {
-  // counts[r] = length of rank r's list (travelled with the cross-GPU barrier; single GPU: counts[0] is the local one)
-  bool any = false;
-  for (int r = 0; r < P.world; ++r) any = any || (counts[r][0] > 0.0);
-  if (!any) return;   // block-uniform
-  for (int r = 0; r < P.world; ++r) {
-    const int* list = (P.world > 1) ? P.peer_heavy[r] : P.heavy;
-    if (list == nullptr) continue;
-    int n = (int)counts[r][0];
-    if (n > HEAVY_MAX) n = HEAVY_MAX;
-    for (int e = 0; e < n; ++e) {
-      const int lo = __ldcg(list + 1 + 3 * e), c = __ldcg(list + 2 + 3 * e);
-      const JT id = (JT)__ldcg(list + 3 + 3 * e);
-      const int a = max(lo, slot_lo), b = min(lo + c, slot_hi);
-      for (int sl = a + threadIdx.x; sl < b; sl += BLOCK) __stcg(jout + (sl - slot_base), id);
-    }
+__device__ __forceinline__ void fill_heavy_runs(const EngineP& P, JT* jout, int slot_base, int slot_lo, int slot_hi, int n) {
+  if (n <= 0) return;   // block-uniform
+  if (n > HEAVY_MAX) n = HEAVY_MAX;
+  for (int e = 0; e < n; ++e) {
+    const int lo = __ldcg(P.heavy + 1 + 3 * e), c = __ldcg(P.heavy + 2 + 3 * e);
+    const JT id = (JT)__ldcg(P.heavy + 3 + 3 * e);
+    const int a = max(lo, slot_lo), b = min(lo + c, slot_hi);
+    for (int sl = a + threadIdx.x; sl < b; sl += BLOCK) __stcg(jout + (sl - slot_base), id);
   }
   __syncthreads();
+}
+
+// Destination side of the packed exchange: every block takes a strided share of the entries each source pushed here
+// and writes the runs into the LOCAL j as negative entry codes -(1 + flat entry index); very long runs go through the
+// local heavy-run list like any other.  The gathering sweep turns the codes back into global ancestor ids.
+template <class JT>
+__device__ __forceinline__ void expand_packs(const EngineP& P, JT* jout_flat, const int (&incoming)[MAX_WORLD]) {
+  SlotRouter<JT> R;
+  R.j = jout_flat; R.base = P.first; R.heavy = P.heavy;
+  for (int s = 0; s < P.world; ++s) {
+    const int ns = incoming[s];
+    const char* meta = P.pack_in + (size_t)s * (size_t)P.pack_cap * (size_t)P.pack_stride + P.pack_state_bytes;
+    for (int base = blockIdx.x * BLOCK; base < ns; base += P.nblocks * BLOCK) {   // block-uniform trip count
+      const int idx = base + threadIdx.x;
+      int first = 0, c = 0;
+      if (idx < ns) {
+        const int4 m = __ldcg(reinterpret_cast<const int4*>(meta + (size_t)idx * (size_t)P.pack_stride));
+        first = m.y; c = m.z;
+      }
+      scatter_runs<JT>(R, first, c, (JT)(-1 - (s * (int)P.pack_cap + idx)));
+    }
+  }
+}
+
+// Closes the scatter: local grid barrier; sharded filters then exchange the packed-entry counts (the cross-GPU barrier)
+// and expand what arrived; finally the heavy-run list is filled into the block's own slots.
+template <class JT>
+__device__ __forceinline__ void finish_scatter(const EngineP& P, Shared& sh, unsigned& bar_target, u64& xseq,
+                                               JT* jout_flat, int slot_lo, int slot_hi, int pushed) {
+  if (pushed) __threadfence_system();   // my packed entries are performed system-wide before I arrive
+  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  if (P.world > 1) {
+    int incoming[MAX_WORLD];
+    peer_exchange_counts(P, sh, xseq, incoming);
+    int tot = 0;
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) tot += incoming[r];
+    if (tot > 0) {   // identical in every block of the rank
+      expand_packs<JT>(P, jout_flat, incoming);
+      grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+    }
+  }
+  const int hn = (P.heavy != nullptr) ? __ldcg(P.heavy) : 0;
+  fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi, hn);
 }
 
 // The whole resample: scan(we) -> bins (global) -> per-source slot ranges -> j (global, id = jbase + i).
@@ -1056,18 +1173,16 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
                                                 LoadFn loadfn, WeFn wefn, double u01, bool gen_u01, uint32_t step_idx,
                                                 int Mslots, const double* u_slots, JT* jout_flat, JT jbase,
                                                 double& total_out, u64& xseq, int slot_lo, int slot_hi,
-                                                const RangeArg* range = nullptr) {
+                                                const RangeArg* range = nullptr, int pack_buf = 0) {
   // [slot_lo, slot_hi): the GLOBAL output slots this block fills from the heavy-run list; jout_flat[0] is global
   // slot P.first
   if (P.heavy != nullptr && blockIdx.x == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);   // before the first barrier
+  if (P.world > 1 && blockIdx.x == 0 && (int)threadIdx.x < P.world) __stcg(P.pack_cnt + threadIdx.x, 0);
   SlotRouter<JT> jout;
   jout.heavy = P.heavy;
   jout.j = jout_flat;
-  jout.peer = reinterpret_cast<JT* const*>(P.peer_j);   // only dereferenced when world > 1 (JT == int there)
-  jout.n = P.n;
-  jout.world = P.world;
-  jout.rank = P.rank;
-  jout.remote = 0;
+  jout.base = P.first;
+  int pushed = 0;
   const int rows2 = (end - beg + 2 * BLOCK - 1) / (2 * BLOCK);
   const bool pairs = (P.scan_mode == 0) && (rows2 <= MAX_ROWS) && ((beg & 1) == 0);
   bool tabled = false;
@@ -1108,15 +1223,10 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     th.r = range->ref_hi; th.ref_lo = range->ref_lo; th.step = range->step_hi; th.step_lo = range->step_lo;
   }
   if (pairs) {
-    scatter_pairs<JT>(P, sh, beg, end, off, th, jout, jbase);
+    scatter_pairs<JT>(P, sh, beg, end, off, th, jout, jbase, pack_buf, pushed);
     const int f_tot = first_slot_ge(th, P.key, total);
     LLPF_TS(P, sh, 3);
-    if (jout.remote) __threadfence_system();   // my peer stores are performed system-wide before I arrive
-    grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-    double hcnt[MAX_WORLD][1];
-    hcnt[0][0] = (P.heavy != nullptr) ? (double)__ldcg(P.heavy) : 0.0;
-    if (P.world > 1) peer_barrier(P, sh, xseq, hcnt[0][0], hcnt);    // every rank's offspring indices have landed in my j
-    fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi, hcnt);
+    finish_scatter<JT>(P, sh, bar_target, xseq, jout_flat, slot_lo, slot_hi, pushed);
     LLPF_TS(P, sh, 4);
     return f_tot;
   }
@@ -1163,16 +1273,12 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
       const int f_hi = (hi > lo) ? first_slot_ge(th, P.key, hi) : f_lo;
       cnt = f_hi - f_lo;
     }
+    if (P.world > 1) push_remote_parts(P, pack_buf, f_lo, cnt, (int)jbase + i, i, pushed);
     scatter_runs<JT>(jout, f_lo, cnt, jbase + (JT)i);
   }
   const int f_total = first_slot_ge(th, P.key, total);
   LLPF_TS(P, sh, 3);
-  if (jout.remote) __threadfence_system();
-  grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
-  double hcnt[MAX_WORLD][1];
-  hcnt[0][0] = (P.heavy != nullptr) ? (double)__ldcg(P.heavy) : 0.0;
-  if (P.world > 1) peer_barrier(P, sh, xseq, hcnt[0][0], hcnt);
-  fill_heavy_runs<JT>(P, jout_flat, P.first, slot_lo, slot_hi, hcnt);
+  finish_scatter<JT>(P, sh, bar_target, xseq, jout_flat, slot_lo, slot_hi, pushed);
   LLPF_TS(P, sh, 4);
   return f_total;
 }
@@ -1434,15 +1540,28 @@ __device__ __forceinline__ void stage_step(const EngineP& P, const ModelP<NX, NY
   skip = (k_y > 0) ? (sh.skip != 0) : false;
 }
 
-// particle `a` (GLOBAL index) from buffer `buf_id` of whichever rank owns it
+// ancestor `a` of local slot `slot` from buffer `buf_id`: a >= 0 is a GLOBAL particle index (local on sharded filters
+// except for the reference's "untouched" stale entries, resample.jl:26-34), a < 0 the code of a packed entry that
+// another rank shipped here (expand_packs); the code is replaced by the entry's global id in state.j.
 template <int NX>
-__device__ __forceinline__ void gather_x(const EngineP& P, int buf_id, int a, double (&x)[NX]) {
+__device__ __forceinline__ void gather_x(const EngineP& P, int buf_id, int a, int slot, double (&x)[NX]) {
   const double* buf;
   int li;
   if (P.world > 1) {
+    if (a < 0) {
+      const char* e = P.pack_in + (size_t)(-1 - a) * (size_t)P.pack_stride;
+#pragma unroll
+      for (int d = 0; d + 1 < NX; d += 2) {
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(e) + (d >> 1));
+        x[d] = v.x; x[d + 1] = v.y;
+      }
+      if (NX & 1) x[NX - 1] = __ldcg(reinterpret_cast<const double*>(e) + (NX - 1));
+      __stcg(P.j + slot, __ldcg(reinterpret_cast<const int*>(e + P.pack_state_bytes)));
+      return;
+    }
     li = a - P.first;
     buf = P.x[buf_id];
-    if ((unsigned)li >= (unsigned)P.n) {   // an ancestor on another GPU (rare: only near the shard edges)
+    if ((unsigned)li >= (unsigned)P.n) {   // a stale entry whose particle lives on another GPU (rare)
       const int r = a / P.n;
       li = a - r * P.n;
       buf = P.peer_x[r][buf_id];
@@ -1546,7 +1665,8 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
           }
           return we;
         },
-        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
+        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end,
+        nullptr, sc.cur);
     sc.bins_total = total;
     LLPF_TSB(P, sh, P.dbg_T, 3);
   }
@@ -1587,7 +1707,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
           if (jid) a_n1 = P.first + i0;
           __stcg(P.j + i0, a_n1);
         }
-        gather_x<NX>(P, sc.cur, a_n1, xn);
+        gather_x<NX>(P, sc.cur, a_n1, i0, xn);
       }
       if (i0 + BLOCK < cx.end) a_n2 = __ldcg(P.j + i0 + BLOCK);
     }
@@ -1605,7 +1725,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
             if (jid) a = P.first + in;
             __stcg(P.j + in, a);
           }
-          gather_x<NX>(P, sc.cur, a, xn);
+          gather_x<NX>(P, sc.cur, a, in, xn);
           if (in + BLOCK < cx.end) a_n2 = __ldcg(P.j + in + BLOCK);
         }
       } else {
@@ -1735,7 +1855,8 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
     f_total = resample_indices<int>(
         P, sh, cx.beg, cx.end, cx.bar_target, [=](int i) { return __ldcg(wraw + i); },
         [=](int, double wr) { return exp_nonpos(wr - m1, *mtp) * inv1; }, 0.0, true,
-        step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
+        step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end,
+        nullptr, adv ? sc.cur : (sc.cur ^ 1));   // sweep B gathers xbar (other buffer) / AdvancedPF: xprev
   }
   sc.bins_total = total;
   const bool with_x = (P.want_xhat != 0);
@@ -1754,13 +1875,13 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
     double x[NX];
     double wnew;
     if (adv) {
-      gather_x<NX>(P, sc.cur, a, x);                             // :230 propagate again from xprev[j]
+      gather_x<NX>(P, sc.cur, a, i, x);                          // :230 propagate again from xprev[j]
       dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
       add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);
       store_x<NX>(oth, P.ld, i, x);
       wnew = cx.lw1N;                                            // :228 reset_weights!
     } else {
-      gather_x<NX>(P, sc.cur ^ 1, a, x);                         // :207 permute_with_buffer!
+      gather_x<NX>(P, sc.cur ^ 1, a, i, x);                      // :207 permute_with_buffer!
       add_dynamics_noise<NX, NY>(M, P.key, step_idx, gi, x, sh);     // :208 add_noise!
       store_x<NX>(P.x[sc.cur], P.ld, i, x);
       wnew = __ldcg(P.lam + i) - lN;                             // :210-213

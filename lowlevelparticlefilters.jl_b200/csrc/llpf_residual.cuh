@@ -184,11 +184,7 @@ __device__ __noinline__ void resample_residual(const EngineP& P, Shared& sh, int
   SlotRouter<JT> jout;
   jout.heavy = P.heavy;
   jout.j = jout_flat;
-  jout.peer = nullptr;
-  jout.n = P.n;
-  jout.world = 1;
-  jout.rank = 0;
-  jout.remote = 0;
+  jout.base = P.first;
   const double rden = (double)rtot_all;
   for (int base = beg; base < end; base += BLOCK) {   // uniform trip count: warp collectives inside
     const int i = base + threadIdx.x;

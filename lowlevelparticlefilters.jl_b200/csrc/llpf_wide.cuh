@@ -156,7 +156,8 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
         P, sh, cx.beg, cx.end, cx.bar_target,
         [=](int i) { return wst.uniform ? 0.0 : __ldcg(wst.w + i); },
         [=](int, double wr) { return wst.expweight_raw(wr); },
-        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end);
+        0.0, true, step_idx, (int)P.N, nullptr, P.j, P.first, total, sc.xseq, P.first + cx.beg, P.first + cx.end,
+        nullptr, sc.cur);
     sc.bins_total = total;
   }
   const int cur = sc.cur;
@@ -181,7 +182,14 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
     if (!res && !wst.uniform) wraw = __ldcg(P.w + i);
     u64 acc[WNX / 2];
     if (k_prop > 0) {
-      const float* xin = wide_row(P, cur, a);
+      const float* xin;
+      if (P.world > 1 && a < 0) {   // an ancestor another rank shipped here as a packed entry (expand_packs)
+        const char* e = P.pack_in + (size_t)(-1 - a) * (size_t)P.pack_stride;
+        xin = reinterpret_cast<const float*>(e);
+        __stcg(P.j + i, __ldcg(reinterpret_cast<const int*>(e + P.pack_state_bytes)));   // state.j keeps global ids
+      } else {
+        xin = wide_row(P, cur, a);
+      }
 #pragma unroll
       for (int k = 0; k < WNX / 2; ++k) acc[k] = 0ull;
       // x' = A x : column form, x streamed 8 values (one 32-byte sector) at a time
