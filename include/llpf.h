@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LLPF_VERSION 103
+#define LLPF_VERSION 200
 
 /* ---- status codes -------------------------------------------------------------------- */
 enum {
@@ -79,7 +79,10 @@ enum {
 /* ---- dynamics descriptors --------------------------------------------------------------- */
 enum {
   LLPF_DYN_LINEAR = 0,        /* x+ = A x + B u                 examples/example_lineargaussian.jl:27 */
-  LLPF_DYN_QUADTANK_RK4 = 1   /* quadruple-tank ODE, RK4        examples/example_quadtank.jl:91-106, src/utils.jl:220-237 */
+  LLPF_DYN_QUADTANK_RK4 = 1,  /* quadruple-tank ODE, RK4        examples/example_quadtank.jl:91-106, src/utils.jl:220-237 */
+  LLPF_DYN_USER = 2           /* dynamics / measurement log-likelihood given as CUDA device source (llpf_create_user):
+                                 the reference's arbitrary closures `dynamics(x,u,p,t)` (PFtypes.jl:128,255) and
+                                 `measurement_likelihood(x,u,y,p,t)` (PFtypes.jl:232)                                   */
 };
 
 /* time convention of the trajectory drivers:
@@ -167,6 +170,24 @@ int llpf_device_count(int* count);
 
 /* replace model matrices / parameters (`p` overridden per call, filtering.jl:140,164) */
 int llpf_set_model(llpf_handle h, const llpf_model* model);
+
+/* User-defined models: the reference takes arbitrary Julia closures for `dynamics` and `measurement_likelihood`
+   (PFtypes.jl:122-139, :226-239, :242-289).  Closures cannot cross a C-ABI; device source can.  `cuda_source` must define
+       namespace llpf_user {
+         template <> __device__ void   dynamics<NX>(double (&x)[NX], const double* u, const double* p, double t);   // x <- f(x,u,p,t), no noise
+         template <> __device__ double loglik<NX>(const double (&x)[NX], const double* u, const double* y, const double* p, double t);
+       }
+   for NX == model->nx.  It is compiled at run time (NVRTC, sm_100a) together with the engine, so both functions are
+   inlined into the fused sweep of k_engine<nx, ny, LLPF_DYN_USER>; every filter kind, resampling strategy, the step
+   verbs, the trajectory drivers and sharding work as for the descriptor models.  Any 1 <= nx, ny <= 8.
+   `model`: nx, nu, ny, R1 (the additive dynamics noise N(0,R1) is drawn by the engine, PFtypes.jl:135), mu0, Sigma0 are
+   used; model->dynamics must be LLPF_DYN_USER; A, B, C, R2 may be NULL.  p[np]: the parameter vector `p` handed to both
+   functions (copied to the device; llpf_set_user_params replaces it, e.g. between PMMH proposals, without recompiling).
+   Compile errors: LLPF_ERR_BAD_ARG with the NVRTC log in llpf_last_error().  Needs libnvrtc.so.12 at run time
+   (searched in the loader path, $LLPF_NVRTC_PATH, /usr/local/cuda/lib64).                                             */
+int llpf_create_user(const llpf_config* cfg, const llpf_model* model, const char* cuda_source,
+                     const double* p, int32_t np, llpf_handle* out);
+int llpf_set_user_params(llpf_handle h, const double* p, int32_t np);
 
 /* reset!(pf)  filtering.jl:4-14 : x=xprev ~ initial_density, w=-log N, we=1/N, t=1.
    `epoch` selects the RNG sub-stream (successive reset! calls in the reference advance pf.rng). */

@@ -7,13 +7,14 @@ nothing here falls back to a CPU implementation.
 from . import _abi  # noqa: F401
 from ._abi import LLPFError, load_library  # noqa: F401
 from .filters import (  # noqa: F401
-    AbstractParticleFilter, AdvancedParticleFilter, AuxiliaryParticleFilter, GaussianLikelihood,
+    AbstractParticleFilter, AdvancedParticleFilter, AuxiliaryParticleFilter, CudaDynamics, CudaLikelihood, CudaMeasurement,
+    GaussianLikelihood,
     LinearDynamics, LinearMeasurement, MvNormal, ParticleFilter, ParticleFilteringSolution, QuadtankRK4,
     ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, connect_shards, correct,
     effective_particles, expweights, forward_trajectory, index, last_run_ms, launch_count, loglik, logsumexp,
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
     shard_blob, shouldresample, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
-    weighted_mean, weights)
+    weighted_mean, weights, xprev)
 from .estimation import (  # noqa: F401
     Normal, Uniform, log_likelihood_fun, metropolis, metropolis_threaded, naive_sampler, set_model, weighted_cov,
     weighted_quantile)

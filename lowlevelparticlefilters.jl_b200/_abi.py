@@ -19,7 +19,7 @@ RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_RESIDUAL = range(3)
 # scan mode
 SCAN_FAST, SCAN_SERIAL = range(2)
 # dynamics
-DYN_LINEAR, DYN_QUADTANK_RK4 = range(2)
+DYN_LINEAR, DYN_QUADTANK_RK4, DYN_USER = range(3)
 # particle element type
 PARTICLE_F64, PARTICLE_F32 = range(2)
 # time convention
@@ -84,6 +84,8 @@ def load_library(path=None):
         "llpf_destroy": [H],
         "llpf_device_count": [C.POINTER(C.c_int)],
         "llpf_set_model": [H, C.POINTER(Model)],
+        "llpf_create_user": [C.POINTER(Config), C.POINTER(Model), C.c_char_p, dp, C.c_int32, C.POINTER(H)],
+        "llpf_set_user_params": [H, dp, C.c_int32],
         "llpf_reset": [H, C.c_uint64],
         "llpf_correct": [H, dp, dp, C.c_double, dp],
         "llpf_predict": [H, dp, C.c_double],

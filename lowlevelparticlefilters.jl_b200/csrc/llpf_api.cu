@@ -2,12 +2,16 @@
 // sm_100a engine (llpf_engine.cuh).  No torch types, no CPU fallback: without a CUDA device every
 // entry point fails with LLPF_ERR_NO_DEVICE / LLPF_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -98,8 +102,27 @@ static int build_host_model(const llpf_model* m, HostModel& H, bool wide) {
   } else if (nx < 1 || nx > MAX_NX || ny < 1 || ny > 8 || nu < 0 || nu > MAX_NU)
     return fail(LLPF_ERR_UNSUPPORTED, "supported dimensions: 1<=nx<=8, 1<=ny<=8, 0<=nu<=8 (Float64 particles); "
                                       "up to 64 states with particle_dtype = LLPF_PARTICLE_F32");
-  if (!m->C || !m->R1 || !m->R2 || !m->mu0 || !m->Sigma0) return fail(LLPF_ERR_BAD_ARG, "null model matrix");
   H.nx = nx; H.nu = nu; H.ny = ny; H.dyn = m->dynamics;
+  if (m->dynamics == LLPF_DYN_USER) {
+    // dynamics mean and measurement log-likelihood are device functions (llpf_create_user): only the noise and the
+    // initial density come from the descriptor; the whitened measurement matrices of the Gaussian case stay neutral
+    if (wide) return fail(LLPF_ERR_UNSUPPORTED, "user-defined models: Float64 particles only");
+    if (!m->R1 || !m->mu0 || !m->Sigma0) return fail(LLPF_ERR_BAD_ARG, "user-defined model: R1, mu0, Sigma0 are required");
+    H.A.clear(); H.B.clear();
+    H.C.assign((size_t)ny * nx, 0.0);
+    H.mu0.assign(m->mu0, m->mu0 + nx);
+    if (!chol_lower(m->R1, nx, H.L1)) return fail(LLPF_ERR_NOT_POSDEF, "R1 is not positive definite");
+    if (!chol_lower(m->Sigma0, nx, H.L0)) return fail(LLPF_ERR_NOT_POSDEF, "Sigma0 is not positive definite");
+    H.L2.assign((size_t)ny * ny, 0.0); H.W.assign((size_t)ny * ny, 0.0);
+    for (int i = 0; i < ny; ++i) { CMH(H.L2, i, i, ny) = 1.0; CMH(H.W, i, i, ny) = 1.0; }
+    H.G.assign((size_t)ny * nx, 0.0);
+    H.c0 = 0.0;
+    std::memcpy(H.dynp, m->dyn_params, sizeof(H.dynp));
+    H.t_switch = m->t_switch; H.a1_factor = m->a1_factor; H.integ_Ts = m->integ_Ts;
+    H.supersample = m->supersample > 0 ? m->supersample : 1;
+    return LLPF_OK;
+  }
+  if (!m->C || !m->R1 || !m->R2 || !m->mu0 || !m->Sigma0) return fail(LLPF_ERR_BAD_ARG, "null model matrix");
   if (m->dynamics == LLPF_DYN_LINEAR) {
     if (!m->A || (nu > 0 && !m->B)) return fail(LLPF_ERR_BAD_ARG, "linear dynamics need A (and B)");
     H.A.assign(m->A, m->A + (size_t)nx * nx);
@@ -386,6 +409,11 @@ struct llpf_filter {
   float *w_At = nullptr, *w_Lt = nullptr, *w_G = nullptr, *w_B = nullptr, *w_mu0 = nullptr, *w_L0 = nullptr;
   double* w_W = nullptr;
   int w_diagL = 0;
+  // user-defined model (LLPF_DYN_USER): kernel compiled at run time, parameter vector p on the device
+  bool user = false;
+  cudaKernel_t user_kernel = nullptr;
+  double* d_user_p = nullptr;
+  int user_np = 0;
 };
 
 // the k_engine<NX, NY, DYN, RESID> instantiations live in llpf_engine_inst.cu (one translation unit per group of
@@ -512,6 +540,164 @@ static cudaError_t launch_init_wide(llpf_filter* f, uint64_t epoch) {
 
 static int resid_of(const llpf_filter* f) { return f->cfg.resampling == LLPF_RESAMPLE_RESIDUAL ? 1 : 0; }
 
+// ------------------------------------------------------------------------------------------------
+// user-defined models: run-time compilation of k_engine<NX, NY, LLPF_DYN_USER, RESID> with NVRTC
+// ------------------------------------------------------------------------------------------------
+// libnvrtc is opened lazily (dlopen) so that the library itself has no link-time dependency on it.
+namespace {
+struct NvrtcApi {
+  void* lib = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*) = nullptr;
+  nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**) = nullptr;
+  const char* (*GetErrorString)(nvrtcResult) = nullptr;
+};
+NvrtcApi g_nvrtc;
+std::mutex g_nvrtc_mu;
+
+bool nvrtc_open(std::string& why) {
+  if (g_nvrtc.lib) return true;
+  std::vector<std::string> cand;
+  if (const char* e = std::getenv("LLPF_NVRTC_PATH")) cand.push_back(e);
+  cand.push_back("libnvrtc.so.12");
+  cand.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+  cand.push_back("libnvrtc.so");
+  void* lib = nullptr;
+  for (const std::string& c : cand) {
+    lib = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (lib) break;
+  }
+  if (!lib) { why = "libnvrtc.so.12 not found (set LLPF_NVRTC_PATH)"; return false; }
+#define LLPF_SYM(name)                                                        \
+  g_nvrtc.name = reinterpret_cast<decltype(g_nvrtc.name)>(dlsym(lib, "nvrtc" #name)); \
+  if (!g_nvrtc.name) { why = "libnvrtc lacks nvrtc" #name; dlclose(lib); return false; }
+  LLPF_SYM(CreateProgram) LLPF_SYM(DestroyProgram) LLPF_SYM(CompileProgram) LLPF_SYM(GetProgramLogSize)
+  LLPF_SYM(GetProgramLog) LLPF_SYM(GetCUBINSize) LLPF_SYM(GetCUBIN) LLPF_SYM(AddNameExpression)
+  LLPF_SYM(GetLoweredName) LLPF_SYM(GetErrorString)
+#undef LLPF_SYM
+  g_nvrtc.lib = lib;
+  return true;
+}
+
+// directory of this shared library: the engine headers are shipped next to it (csrc/)
+std::string library_dir() {
+  Dl_info info;
+  if (dladdr(reinterpret_cast<const void*>(&llpf_last_error), &info) && info.dli_fname) {
+    std::string pth(info.dli_fname);
+    const size_t k = pth.find_last_of('/');
+    return k == std::string::npos ? std::string(".") : pth.substr(0, k);
+  }
+  return ".";
+}
+
+struct UserKernel { cudaLibrary_t lib; cudaKernel_t kernel; };
+std::map<std::string, UserKernel> g_user_kernels;   // key: device ordinal + instantiation + source
+
+// Compiles `#define LLPF_USER_MODEL / #include "llpf_engine.cuh" / <user source> / explicit instantiation` to an sm_100a
+// cubin and loads it (cudaLibraryLoadData: context-independent, usable from the handle's device).
+int compile_user_kernel(int device, int nx, int ny, int resid, const char* user_src, cudaKernel_t* out) {
+  std::lock_guard<std::mutex> lock(g_nvrtc_mu);
+  char inst[96];
+  std::snprintf(inst, sizeof(inst), "llpf::k_engine<%d, %d, 2, %d>", nx, ny, resid);
+  const std::string key = std::to_string(device) + "|" + inst + "|" + user_src;
+  auto it = g_user_kernels.find(key);
+  if (it != g_user_kernels.end()) { *out = it->second.kernel; return LLPF_OK; }
+  std::string why;
+  if (!nvrtc_open(why)) return fail(LLPF_ERR_UNSUPPORTED, "user-defined model: " + why);
+  std::string src = "#define LLPF_USER_MODEL\n#include \"llpf_engine.cuh\"\n#line 1 \"user_model.cu\"\n";
+  src += user_src;
+  src += "\nnamespace llpf {\ntemplate __global__ void k_engine<" + std::to_string(nx) + ", " + std::to_string(ny) + ", 2, " +
+         std::to_string(resid) + ">(const __grid_constant__ EngineP, const __grid_constant__ ModelP<" + std::to_string(nx) +
+         ", " + std::to_string(ny) + ">);\n}\n";
+  nvrtcProgram prog = nullptr;
+  nvrtcResult rc = g_nvrtc.CreateProgram(&prog, src.c_str(), "llpf_user_engine.cu", 0, nullptr, nullptr);
+  if (rc != NVRTC_SUCCESS) return fail(LLPF_ERR_CUDA, std::string("nvrtcCreateProgram: ") + g_nvrtc.GetErrorString(rc));
+  g_nvrtc.AddNameExpression(prog, inst);
+  const std::string inc = "-I" + library_dir();
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-lineinfo", inc.c_str(),
+                                   "-I/usr/local/cuda/include"};
+  rc = g_nvrtc.CompileProgram(prog, (int)opts.size(), opts.data());
+  if (rc != NVRTC_SUCCESS) {
+    size_t n = 0;
+    g_nvrtc.GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+    if (log.size() > 6000) log.resize(6000);
+    g_nvrtc.DestroyProgram(&prog);
+    return fail(LLPF_ERR_BAD_ARG, std::string("user-defined model does not compile (") + g_nvrtc.GetErrorString(rc) + "):\n" + log);
+  }
+  const char* lowered = nullptr;
+  g_nvrtc.GetLoweredName(prog, inst, &lowered);
+  size_t nb = 0;
+  g_nvrtc.GetCUBINSize(prog, &nb);
+  std::vector<char> cubin(nb);
+  if (nb) g_nvrtc.GetCUBIN(prog, cubin.data());
+  const std::string name = lowered ? lowered : "";
+  g_nvrtc.DestroyProgram(&prog);
+  if (!nb || name.empty()) return fail(LLPF_ERR_CUDA, "NVRTC produced no cubin / no lowered kernel name");
+  UserKernel uk;
+  cudaError_t e = cudaLibraryLoadData(&uk.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e != cudaSuccess) return fail(LLPF_ERR_CUDA, std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e));
+  e = cudaLibraryGetKernel(&uk.kernel, uk.lib, name.c_str());
+  if (e != cudaSuccess) return fail(LLPF_ERR_CUDA, std::string("cudaLibraryGetKernel(") + name + "): " + cudaGetErrorString(e));
+  g_user_kernels[key] = uk;
+  *out = uk.kernel;
+  return LLPF_OK;
+}
+}  // namespace
+
+// the bytes of ModelP<nx, ny> for run-time dimensions (same member order as the template: A, L1, G, W, B, c0, qt[8],
+// t_switch, integ_h, supersample, nu)
+static std::vector<double> pack_modelp_runtime(const HostModel& H) {
+  const int nx = H.nx, ny = H.ny;
+  std::vector<double> v((size_t)2 * nx * nx + (size_t)ny * nx + (size_t)ny * ny + (size_t)nx * MAX_NU + 11 + 1, 0.0);
+  double* A = v.data();
+  double* L1 = A + nx * nx;
+  double* G = L1 + nx * nx;
+  double* W = G + ny * nx;
+  double* B = W + ny * ny;
+  double* tail = B + nx * MAX_NU;
+  for (int r = 0; r < nx; ++r)
+    for (int c = 0; c < nx; ++c) {
+      if (!H.A.empty()) A[r * nx + c] = CMH(H.A, r, c, nx);
+      L1[r * nx + c] = CMH(H.L1, r, c, nx);
+    }
+  for (int a = 0; a < ny; ++a) {
+    for (int c = 0; c < nx; ++c) G[a * nx + c] = CMH(H.G, a, c, ny);
+    for (int c = 0; c < ny; ++c) W[a * ny + c] = CMH(H.W, a, c, ny);
+  }
+  for (int r = 0; r < nx; ++r)
+    for (int c = 0; c < H.nu; ++c)
+      if (!H.B.empty()) B[r * MAX_NU + c] = CMH(H.B, r, c, nx);
+  tail[0] = H.c0;                               // c0 ; qt[8] stays zero
+  tail[9] = H.t_switch;
+  tail[10] = H.integ_Ts / (double)H.supersample;
+  int ints[2] = {H.supersample, H.nu};
+  std::memcpy(tail + 11, ints, sizeof(ints));
+  return v;
+}
+
+// EngineP as the LLPF_USER_MODEL build of the engine sees it: one trailing member more
+struct EnginePUser {
+  EngineP base;
+  const double* user_p;
+};
+
+static cudaError_t launch_engine_user(llpf_filter* f, const EngineP& P) {
+  std::vector<double> M = pack_modelp_runtime(f->hm);
+  EnginePUser PU;
+  PU.base = P;
+  PU.user_p = f->d_user_p;
+  void* args[] = {(void*)&PU, (void*)M.data()};
+  return cudaLaunchCooperativeKernel((const void*)f->user_kernel, dim3(P.nblocks), dim3(BLOCK), args, 0, f->stream);
+}
+
 // host-side half of the dispatch (model packing + init kernel); the device half is llpf_engine_list.h
 struct Dispatch {
   int nx, ny, dyn;
@@ -528,6 +714,9 @@ static const Dispatch g_dispatch[] = {
 
 static void push_op(EngineP& P, int kind, int a0, int b0, int count = 1, int da = 0, int db = 0, int flags = 0);
 static int launch(llpf_filter* f, const EngineP& P, bool timed);
+static const init_fn g_init_by_nx[MAX_NX + 1] = {nullptr, launch_init<1>, launch_init<2>, launch_init<3>, launch_init<4>,
+                                                 launch_init<5>, launch_init<6>, launch_init<7>, launch_init<8>};
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // staging slot of the step verbs' measurement vectors: y and y1, each up to the widest ny any engine accepts (64: Float32 filters)
 constexpr int kStageYDoubles = WNX > 8 ? WNX : 8;
@@ -574,6 +763,7 @@ extern "C" int llpf_destroy(llpf_handle h) {
   cudaFree(h->d_res);
   cudaFree(h->w_At); cudaFree(h->w_Lt); cudaFree(h->w_G); cudaFree(h->w_B); cudaFree(h->w_mu0); cudaFree(h->w_L0);
   cudaFree(h->w_W);
+  cudaFree(h->d_user_p);
   if (h->pin_sc) cudaFreeHost(h->pin_sc);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -599,9 +789,14 @@ extern "C" int llpf_set_model(llpf_handle h, const llpf_model* model) {
 
 extern "C" int llpf_reset(llpf_handle h, uint64_t epoch);
 
-extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf_handle* out) {
+static int create_impl(const llpf_config* cfg, const llpf_model* model, const char* user_src, const double* user_p,
+                       int32_t user_np, llpf_handle* out) {
   if (!cfg || !model || !out) return fail(LLPF_ERR_BAD_ARG, "null argument");
   *out = nullptr;
+  const bool user = user_src != nullptr;
+  if (user != (model->dynamics == LLPF_DYN_USER))
+    return fail(LLPF_ERR_BAD_ARG, "LLPF_DYN_USER models are created with llpf_create_user (and only those)");
+  if (user && (user_np < 0 || (user_np > 0 && !user_p))) return fail(LLPF_ERR_BAD_ARG, "bad parameter vector");
   if (cfg->N < 1 || cfg->N >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "need 1 <= N < 2^31");
   if (cfg->filter < 0 || cfg->filter > 3) return fail(LLPF_ERR_BAD_ARG, "unknown filter kind");
   if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED &&
@@ -633,7 +828,15 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
   int rc = build_host_model(model, f->hm, wide);
   if (rc) { delete f; return rc; }
   const Dispatch* d = nullptr;
-  if (!wide) {
+  f->user = user;
+  if (user) {
+    if (wide) { delete f; return fail(LLPF_ERR_UNSUPPORTED, "user-defined models: Float64 particles only"); }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { delete f; return fail(LLPF_ERR_CUDA, "cudaSetDevice"); }
+    rc = compile_user_kernel(cfg->device, f->hm.nx, f->hm.ny, resid_of(f), user_src, &f->user_kernel);
+    if (rc) { delete f; return rc; }
+    f->launch = launch_engine_user;
+    f->init = g_init_by_nx[f->hm.nx];
+  } else if (!wide) {
     for (const Dispatch& e : g_dispatch)
       if (e.nx == f->hm.nx && e.ny == f->hm.ny && e.dyn == f->hm.dyn) d = &e;
     if (d && !engine_kernel(d->nx, d->ny, d->dyn, resid_of(f))) d = nullptr;
@@ -664,7 +867,12 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
     llpf_destroy(f);
     return fail(LLPF_ERR_UNSUPPORTED, "device lacks cooperative launch");
   }
-  const int occ = wide ? occupancy_engine_wide() : occupancy_engine(d->nx, d->ny, d->dyn, resid_of(f));
+  int occ = 0;
+  if (user) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)f->user_kernel, BLOCK, 0) != cudaSuccess) occ = 0;
+  } else {
+    occ = wide ? occupancy_engine_wide() : occupancy_engine(d->nx, d->ny, d->dyn, resid_of(f));
+  }
   if (occ < 1) {
     llpf_destroy(f);
     return fail(LLPF_ERR_CUDA, "engine kernel does not fit on an SM (is this an sm_100a device?)");
@@ -726,12 +934,38 @@ extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf
     rc = upload_wide_model(f);
     if (rc) { llpf_destroy(f); return rc; }
   }
+  if (user) {
+    f->user_np = user_np;
+    if (cudaMalloc(&f->d_user_p, sizeof(double) * (user_np > 0 ? user_np : 1)) != cudaSuccess ||
+        (user_np > 0 && cudaMemcpy(f->d_user_p, user_p, sizeof(double) * user_np, cudaMemcpyHostToDevice) != cudaSuccess)) {
+      llpf_destroy(f);
+      return fail(LLPF_ERR_CUDA, "allocating the user parameter vector");
+    }
+  }
   rc = llpf_reset(f, 0);
   if (rc) { llpf_destroy(f); return rc; }
   f->hsc.t_index = 0;  // PFstate(...,Ref(0)) PFtypes.jl:70 ; reset! sets 1
   rc = push_scalars(f);
   if (rc) { llpf_destroy(f); return rc; }
   *out = f;
+  return LLPF_OK;
+}
+
+extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf_handle* out) {
+  return create_impl(cfg, model, nullptr, nullptr, 0, out);
+}
+extern "C" int llpf_create_user(const llpf_config* cfg, const llpf_model* model, const char* cuda_source,
+                                const double* p, int32_t np, llpf_handle* out) {
+  if (!cuda_source) return fail(LLPF_ERR_BAD_ARG, "cuda_source is null");
+  return create_impl(cfg, model, cuda_source, p, np, out);
+}
+extern "C" int llpf_set_user_params(llpf_handle h, const double* p, int32_t np) {
+  OKR(check_handle(h));
+  if (!h->user) return fail(LLPF_ERR_BAD_ARG, "not a user-defined model");
+  if (np != h->user_np || (np > 0 && !p)) return fail(LLPF_ERR_BAD_ARG, "parameter vector length differs from the one given at creation");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (np > 0) CU(cudaMemcpy(h->d_user_p, p, sizeof(double) * np, cudaMemcpyHostToDevice));
   return LLPF_OK;
 }
 
@@ -1182,6 +1416,7 @@ static int smooth_backward(llpf_filter* f, long long T, const double* u_dev, con
 }
 
 static int smooth_supported(llpf_filter* f) {
+  if (f->user) return fail(LLPF_ERR_UNSUPPORTED, "smooth: descriptor models only (the backward kernel has no user-function hook yet)");
   if (f->wide) return fail(LLPF_ERR_UNSUPPORTED, "smooth: Float32-particle filters keep no history");
   if (f->world > 1) return fail(LLPF_ERR_UNSUPPORTED, "smooth: single-GPU filters only (the history is not sharded)");
   return LLPF_OK;

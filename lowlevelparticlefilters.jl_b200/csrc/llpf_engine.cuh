@@ -558,36 +558,38 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
       mine[0] = m;
 #pragma unroll
       for (int k = 0; k < 2 + NX; ++k) mine[1 + k] = t[k];
-      if (threadIdx.x < P.world) {
-        const int r = threadIdx.x;
+      // one thread per (peer, word): every store and every poll is a single independent transaction (the first version
+      // had thread r write and then poll rank r's 2*NV words one after the other: ~2*NV dependent L2 round trips)
+      static_assert(MAX_WORLD * NW <= BLOCK, "one thread per (peer, word)");
+      uint32_t* pw = reinterpret_cast<uint32_t*>(sh.peer_vals);   // [world][NW] payload halves
+      if ((int)threadIdx.x < P.world * NW) {
+        const int r = threadIdx.x / NW, wd = threadIdx.x % NW;
+        double val = mine[0];
+#pragma unroll
+        for (int k = 1; k < NV; ++k)
+          if ((wd >> 1) == k) val = mine[k];
+        const u64 bits = (u64)__double_as_longlong(val);
+        const uint32_t half = (wd & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
         if (r != P.rank) {
           u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            const u64 bits = (u64)__double_as_longlong(mine[k]);
-            st_relaxed_sys_u64(out + 2 * k, tag | (bits & 0xffffffffull));
-            st_relaxed_sys_u64(out + 2 * k + 1, tag | (bits >> 32));
-          }
+          st_relaxed_sys_u64(out + wd, tag | (u64)half);
           const u64* in = reinterpret_cast<const u64*>(P.peer_mbox[P.rank]) + ((size_t)par * MAX_WORLD + r) * MBOX_WORDS;
-#pragma unroll
-          for (int k = 0; k < NV; ++k) {
-            u64 lo, hi;
-            do { lo = ld_relaxed_sys_u64(in + 2 * k); } while ((lo & 0xffffffff00000000ull) != tag);
-            do { hi = ld_relaxed_sys_u64(in + 2 * k + 1); } while ((hi & 0xffffffff00000000ull) != tag);
-            sh.peer_vals[r * (3 + MAX_NX) + k] = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
-          }
+          u64 v;
+          do { v = ld_relaxed_sys_u64(in + wd); } while ((v & 0xffffffff00000000ull) != tag);
+          pw[r * NW + wd] = (uint32_t)v;
         } else {
-#pragma unroll
-          for (int k = 0; k < NV; ++k) sh.peer_vals[r * (3 + MAX_NX) + k] = mine[k];
+          pw[r * NW + wd] = half;
         }
       }
       __syncthreads();
-      double gm = sh.peer_vals[0];
-      for (int r = 1; r < P.world; ++r) gm = fmax(gm, sh.peer_vals[r * (3 + MAX_NX)]);
+      double gm = -DBL_MAX;
+      for (int r = 0; r < P.world; ++r) gm = fmax(gm, __hiloint2double((int)pw[r * NW + 1], (int)pw[r * NW]));
 #pragma unroll
       for (int k = 0; k < 2 + NX; ++k) t[k] = 0.0;
       for (int r = 0; r < P.world; ++r) {
-        const double* pv = sh.peer_vals + r * (3 + MAX_NX);
+        double pv[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) pv[k] = __hiloint2double((int)pw[r * NW + 2 * k + 1], (int)pw[r * NW + 2 * k]);
         const double e = exp_nonpos(pv[0] - gm, sh.mt);
         t[0] = fma(pv[1], e, t[0]);
         t[1] = fma(pv[2], e * e, t[1]);
@@ -1150,15 +1152,19 @@ __device__ __forceinline__ void finish_scatter(const EngineP& P, Shared& sh, uns
                                                JT* jout_flat, int slot_lo, int slot_hi, int pushed) {
   if (pushed) __threadfence_system();   // my packed entries are performed system-wide before I arrive
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+  LLPF_TS(P, sh, 10);
   if (P.world > 1) {
     int incoming[MAX_WORLD];
     peer_exchange_counts(P, sh, xseq, incoming);
+    LLPF_TS(P, sh, 11);
     int tot = 0;
 #pragma unroll
     for (int r = 0; r < MAX_WORLD; ++r) tot += incoming[r];
     if (tot > 0) {   // identical in every block of the rank
       expand_packs<JT>(P, jout_flat, incoming);
+      LLPF_TS(P, sh, 12);
       grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
+      LLPF_TS(P, sh, 13);
     }
   }
   const int hn = (P.heavy != nullptr) ? __ldcg(P.heavy) : 0;
@@ -1214,6 +1220,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
     }
     total = (double)gtot * P.fix_inv;
     off = gbase + sh.offs[blockIdx.x];
+    LLPF_TS(P, sh, 14);
   }
   total_out = total;
   if (gen_u01) u01 = resample_u01(P.key, step_idx);

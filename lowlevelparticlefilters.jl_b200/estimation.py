@@ -76,7 +76,10 @@ def log_likelihood_fun(filter_from_parameters, priors, u, y, p=None):
         nargs = len(inspect.signature(filter_from_parameters).parameters)
     except (TypeError, ValueError):
         nargs = 1
-    state = {"pf": None}
+    # the RNG epoch belongs to the likelihood function, not to the filter handle: a filter_from_parameters that builds a
+    # fresh filter per call would otherwise evaluate every θ with the same particle noise (a fixed, biased surface
+    # instead of the reference's fresh unbiased estimate per call — pf.rng runs on across reset!, filtering.jl:6)
+    state = {"pf": None, "epoch": 0}
 
     def ll(theta):
         theta = np.asarray(theta, dtype=np.float64).reshape(-1)
@@ -90,7 +93,8 @@ def log_likelihood_fun(filter_from_parameters, priors, u, y, p=None):
                 state["pf"] = filter_from_parameters(theta)
             else:
                 state["pf"] = filter_from_parameters(theta, state["pf"])
-            return lp + F.loglik(state["pf"], u, y)
+            state["epoch"] += 1
+            return lp + F.loglik(state["pf"], u, y, epoch=state["epoch"] & 0xFFFFFF)
         except (LLPFError, np.linalg.LinAlgError, FloatingPointError):
             return -math.inf     # the reference's `catch` at :280 (e.g. a covariance that is not positive definite)
 
@@ -152,6 +156,8 @@ def metropolis_threaded(burnin, ll, R, theta0, draw=None, *, nthreads=4, seed=No
             rng = np.random.default_rng(kids[k])
             if factory is not None:
                 llk = factory()
+                if hasattr(llk, "state"):      # chains must not share particle-noise streams (per-task RNGs in the reference)
+                    llk.state["epoch"] = (k + 1) << 18
             else:
                 def llk(th):
                     with lock:

@@ -24,7 +24,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _abi
-from ._abi import (DYN_LINEAR, DYN_QUADTANK_RK4, FILTER_ADVANCED, FILTER_AUX, FILTER_AUX_ADVANCED,
+from ._abi import (DYN_LINEAR, DYN_QUADTANK_RK4, DYN_USER, FILTER_ADVANCED, FILTER_AUX, FILTER_AUX_ADVANCED,
                    FILTER_PF, RESAMPLE_STRATIFIED, RESAMPLE_SYSTEMATIC, SCAN_FAST, SCAN_SERIAL,
                    TIME_FORWARD_TRAJECTORY, TIME_LOGLIK, check)
 
@@ -107,6 +107,103 @@ class GaussianLikelihood:
     R2: np.ndarray
 
 
+# ---- user-defined models: the reference's closures, given as CUDA device code (llpf_create_user) ----------------
+@dataclass
+class CudaDynamics:
+    """dynamics(x,u,p,t) (PFtypes.jl:128,255) as the BODY of
+        __device__ void dynamics(double (&x)[NX], const double* u, const double* p, double t)
+    It must overwrite x with f(x,u,p,t) WITHOUT noise: the additive N(0,R1) of `dynamics_density` is drawn by the engine
+    (PFtypes.jl:135).  `nu` = length of u.  Compiled at run time (NVRTC) and inlined into the fused sweep."""
+    body: str
+    nu: int = 0
+
+
+@dataclass
+class CudaLikelihood:
+    """measurement_likelihood(x,u,y,p,t) (PFtypes.jl:232) as the BODY of
+        __device__ double loglik(const double (&x)[NX], const double* u, const double* y, const double* p, double t)
+    returning the log-likelihood of y given x.  `ny` = length of y."""
+    body: str
+    ny: int = 1
+
+
+@dataclass
+class CudaMeasurement:
+    """measurement(x,u,p,t) (PFtypes.jl:116) as the BODY of a function that writes the predicted measurement into
+    `double yh[NY]` (x, u, p, t in scope); the Gaussian `measurement_density` supplies logpdf(dg, y - yh)."""
+    body: str
+
+
+def _lit(v):
+    return float(v).hex()
+
+
+def _linear_dynamics_body(A, B, nx, nu):
+    A = np.atleast_2d(np.asarray(A, dtype=np.float64))
+    lines = [f"double xn[{nx}];"]
+    for r in range(nx):
+        terms = " + ".join(f"{_lit(A[r, c])} * x[{c}]" for c in range(nx))
+        if nu:
+            Bm = np.asarray(B, dtype=np.float64).reshape(nx, nu)
+            terms = f"({terms}) + (" + " + ".join(f"{_lit(Bm[r, c])} * u[{c}]" for c in range(nu)) + ")"
+        lines.append(f"xn[{r}] = {terms};")
+    lines += [f"x[{r}] = xn[{r}];" for r in range(nx)]
+    return "\n".join(lines)
+
+
+def _gaussian_loglik_body(meas_body, R2, ny):
+    """logpdf(N(0,R2), y - yh) = c0 - |L \\ (y - yh)|^2 / 2  (utils.jl:252-257), L = chol(R2) as literals"""
+    R2 = np.atleast_2d(np.asarray(R2, dtype=np.float64))
+    L = np.linalg.cholesky(R2)
+    c0 = -(ny * np.log(2 * np.pi) + 2 * np.sum(np.log(np.diag(L)))) / 2
+    lines = [f"double yh[{ny}];", "{", meas_body, "}", f"double v[{ny}]; double q = 0.0;"]
+    for i in range(ny):
+        acc = f"(y[{i}] - yh[{i}])" + "".join(f" - {_lit(L[i, k])} * v[{k}]" for k in range(i))
+        lines.append(f"v[{i}] = ({acc}) / {_lit(L[i, i])}; q += v[{i}] * v[{i}];")
+    lines.append(f"return {_lit(c0)} - q / 2;")
+    return "\n".join(lines)
+
+
+def _user_source(nx, dyn_body, lik_body):
+    return (f"namespace llpf_user {{\n"
+            f"template <> __device__ void dynamics<{nx}>(double (&x)[{nx}], const double* u, const double* p, double t) {{\n"
+            f"{dyn_body}\n}}\n"
+            f"template <> __device__ double loglik<{nx}>(const double (&x)[{nx}], const double* u, const double* y, "
+            f"const double* p, double t) {{\n{lik_body}\n}}\n}}  // namespace llpf_user\n")
+
+
+class _UserModelBuffers:
+    """Model struct + generated CUDA source of a filter whose dynamics and / or likelihood are device code."""
+
+    def __init__(self, dynamics, likelihood_body, ny, R1, d0):
+        nx = len(d0)
+        if isinstance(dynamics, CudaDynamics):
+            nu, dyn_body = int(dynamics.nu), dynamics.body
+        elif isinstance(dynamics, LinearDynamics):
+            nu = 0 if dynamics.B is None else np.asarray(dynamics.B).reshape(nx, -1).shape[1]
+            dyn_body = _linear_dynamics_body(dynamics.A, dynamics.B, nx, nu)
+        else:
+            raise TypeError("with user-defined device code the dynamics must be CudaDynamics or LinearDynamics")
+        self.source = _user_source(nx, dyn_body, likelihood_body)
+        m = _abi.Model()
+        self.keep = []
+        null = C.cast(None, dp)
+
+        def put(M, shape):
+            a = _colmajor(M, shape)
+            self.keep.append(a)
+            return a.ctypes.data_as(dp)
+
+        m.nx, m.nu, m.ny, m.dynamics = nx, nu, int(ny), DYN_USER
+        m.A = m.B = m.C = m.R2 = null
+        m.R1 = put(R1, (nx, nx))
+        m.mu0 = put(d0.mu, (nx,))
+        m.Sigma0 = put(d0.Sigma, (nx, nx))
+        m.t_switch, m.a1_factor, m.integ_Ts, m.supersample = float("inf"), 1.0, 1.0, 1
+        self.struct = m
+        self.nx, self.nu, self.ny = nx, nu, int(ny)
+
+
 @dataclass
 class ParticleFilteringSolution:  # src/solutions.jl:334-345
     f: object
@@ -172,7 +269,7 @@ class AbstractParticleFilter:
     _filter_code = FILTER_PF
 
     def _create(self, N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device,
-                rank=0, world=1, particle_dtype=np.float64):
+                rank=0, world=1, particle_dtype=np.float64, p=None):
         """N is the GLOBAL particle count; with world > 1 this process owns the contiguous slice
         [rank*N/world, (rank+1)*N/world) and must call connect_shards() before the first step."""
         self._lib = _abi.load_library()
@@ -190,7 +287,15 @@ class AbstractParticleFilter:
         cfg.particle_dtype = _abi.PARTICLE_F32 if self.particle_dtype == np.dtype(np.float32) else _abi.PARTICLE_F64
         self._cfg = cfg
         self._h = C.c_void_p()
-        check(self._lib, self._lib.llpf_create(C.byref(cfg), C.byref(model.struct), C.byref(self._h)))
+        self.p = None
+        if isinstance(model, _UserModelBuffers):
+            pv = np.ascontiguousarray(np.asarray([] if p is None else p, dtype=np.float64).reshape(-1))
+            self.p = pv
+            check(self._lib, self._lib.llpf_create_user(C.byref(cfg), C.byref(model.struct), model.source.encode(),
+                                                        pv.ctypes.data_as(dp) if pv.size else C.cast(None, dp),
+                                                        int(pv.size), C.byref(self._h)))
+        else:
+            check(self._lib, self._lib.llpf_create(C.byref(cfg), C.byref(model.struct), C.byref(self._h)))
         self.N_global = int(N)
         self.rank, self.world = int(rank), max(1, int(world))
         self.N = int(N) // self.world          # local particle count: accessor arrays have this length
@@ -222,6 +327,21 @@ class AbstractParticleFilter:
     def _default_t(self, t):
         return index(self) * self.Ts if t is None else float(t)
 
+    def _use_p(self, p):
+        """Per-call parameter override `p` (filtering.jl:140,164).  User-defined models: the vector handed to the device
+        functions is replaced (no recompilation).  Descriptor models carry their parameters in the matrices: use
+        set_model(pf, ...) — silently ignoring `p` would compute with the wrong parameters, so it raises."""
+        if p is None:
+            return
+        if isinstance(self._model, _UserModelBuffers):
+            pv = np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(-1))
+            check(self._lib, self._lib.llpf_set_user_params(self._h, pv.ctypes.data_as(dp) if pv.size else C.cast(None, dp),
+                                                            int(pv.size)))
+            self.p = pv
+            return
+        raise TypeError("descriptor models have no parameter vector: change the model with set_model(pf, ...) "
+                        "(the reference's `p` override, filtering.jl:140,164, applies to closures)")
+
     def __call__(self, u, y, p=None, t=None):  # (pf::ParticleFilter)(u,y,p,t) filtering.jl:238
         return update(self, u, y, p, t)
 
@@ -232,15 +352,29 @@ class ParticleFilter(AbstractParticleFilter):
     def __init__(self, N, dynamics, measurement, dynamics_density, measurement_density, initial_density, *,
                  resample_threshold=0.1, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
                  scan_mode="fast", device=0, p=None, rank=0, world=1, **_ignored):
-        if not isinstance(measurement, LinearMeasurement):
-            raise TypeError("measurement must be a LinearMeasurement descriptor")
         self.dynamics, self.measurement = dynamics, measurement
         self.dynamics_density, self.measurement_density = dynamics_density, measurement_density
         self.initial_density = initial_density
-        model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
-                              initial_density)
+        ny = len(measurement_density)
+        if isinstance(dynamics, CudaDynamics) or isinstance(measurement, CudaMeasurement):
+            # closures of the reference (PFtypes.jl:116,128) given as device code: w[i] += logpdf(dg, y - g(x[i]))
+            if isinstance(measurement, CudaMeasurement):
+                meas_body = measurement.body
+            elif isinstance(measurement, LinearMeasurement):
+                Cm = np.atleast_2d(np.asarray(measurement.C, dtype=np.float64))
+                meas_body = "\n".join(f"yh[{a}] = " + " + ".join(f"{_lit(Cm[a, c])} * x[{c}]" for c in range(Cm.shape[1])) + ";"
+                                      for a in range(ny))
+            else:
+                raise TypeError("measurement must be a LinearMeasurement or CudaMeasurement descriptor")
+            lik = _gaussian_loglik_body(meas_body, measurement_density.Sigma, ny)
+            model = _UserModelBuffers(dynamics, lik, ny, dynamics_density.Sigma, initial_density)
+        else:
+            if not isinstance(measurement, LinearMeasurement):
+                raise TypeError("measurement must be a LinearMeasurement or CudaMeasurement descriptor")
+            model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
+                                  initial_density)
         self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
-                     particle_dtype=getattr(initial_density, "dtype", np.float64))
+                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p)
 
 
 class AdvancedParticleFilter(AbstractParticleFilter):
@@ -249,15 +383,30 @@ class AdvancedParticleFilter(AbstractParticleFilter):
     def __init__(self, N, dynamics, measurement, measurement_likelihood, dynamics_density, initial_density, *,
                  resample_threshold=0.5, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
                  scan_mode="fast", device=0, p=None, rank=0, world=1, **_ignored):
-        if not isinstance(measurement_likelihood, GaussianLikelihood):
-            raise TypeError("measurement_likelihood must be a GaussianLikelihood descriptor")
         self.dynamics, self.measurement = dynamics, measurement
         self.measurement_likelihood = measurement_likelihood
         self.dynamics_density, self.initial_density = dynamics_density, initial_density
-        model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
-                              measurement_likelihood.R2, initial_density)
+        if isinstance(dynamics, CudaDynamics) or isinstance(measurement_likelihood, CudaLikelihood):
+            # the reference's closures dynamics(x,u,p,t,noise) / measurement_likelihood(x,u,y,p,t) (PFtypes.jl:232,255) as
+            # device code; the noise stays additive Gaussian (dynamics_density), drawn by the engine
+            if isinstance(measurement_likelihood, CudaLikelihood):
+                lik, ny = measurement_likelihood.body, int(measurement_likelihood.ny)
+            elif isinstance(measurement_likelihood, GaussianLikelihood):
+                Cm = np.atleast_2d(np.asarray(measurement_likelihood.C, dtype=np.float64))
+                ny = Cm.shape[0]
+                meas_body = "\n".join(f"yh[{a}] = " + " + ".join(f"{_lit(Cm[a, c])} * x[{c}]" for c in range(Cm.shape[1])) + ";"
+                                      for a in range(ny))
+                lik = _gaussian_loglik_body(meas_body, measurement_likelihood.R2, ny)
+            else:
+                raise TypeError("measurement_likelihood must be a GaussianLikelihood or CudaLikelihood descriptor")
+            model = _UserModelBuffers(dynamics, lik, ny, dynamics_density.Sigma, initial_density)
+        else:
+            if not isinstance(measurement_likelihood, GaussianLikelihood):
+                raise TypeError("measurement_likelihood must be a GaussianLikelihood or CudaLikelihood descriptor")
+            model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
+                                  measurement_likelihood.R2, initial_density)
         self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
-                     particle_dtype=getattr(initial_density, "dtype", np.float64))
+                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p)
 
 
 class AuxiliaryParticleFilter(AbstractParticleFilter):
@@ -274,7 +423,7 @@ class AuxiliaryParticleFilter(AbstractParticleFilter):
                 setattr(self, name, getattr(inner, name))
             self._create(inner.N_global, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
                          inner.seed, cfg.scan_mode, cfg.device, inner.rank, inner.world,
-                         particle_dtype=inner.particle_dtype)
+                         particle_dtype=inner.particle_dtype, p=inner.p)
         else:
             self.__init__(ParticleFilter(*args, **kwargs))
 
@@ -297,6 +446,7 @@ def reset(pf, epoch=None):
 
 def correct(pf, u, y, p=None, t=None):
     """correct!(pf,u,y,p,t) -> (ll, 0)  filtering.jl:164-174"""
+    pf._use_p(p)
     _, up = pf._vec(u, pf.nu, "u")
     ya, yp = pf._vec(y, pf.ny, "y")
     ll = C.c_double()
@@ -306,6 +456,7 @@ def correct(pf, u, y, p=None, t=None):
 
 def predict(pf, u, p=None, t=None, y1=None):
     """predict!(pf,u,p,t) filtering.jl:140-153 ; predict!(pfa,u,y1,p,t) :195-234"""
+    pf._use_p(p)
     _, up = pf._vec(u, pf.nu, "u")
     if isinstance(pf, AuxiliaryParticleFilter):
         if y1 is None:
@@ -318,6 +469,7 @@ def predict(pf, u, p=None, t=None, y1=None):
 
 def update(pf, u, y, p=None, t=None, y1=None):
     """update!(f,u,y,p,t) filtering.jl:181-185 ; update!(pfa,u,y,y1,p,t) :187-191.  Returns (ll, 0)."""
+    pf._use_p(p)
     _, up = pf._vec(u, pf.nu, "u")
     _, yp = pf._vec(y, pf.ny, "y")
     null = C.cast(None, dp)
@@ -389,6 +541,7 @@ def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None):
     history=False skips the N x T x/w/we arrays (they are then None); the per-step ll, ESS,
     resample flags and weighted means are always returned in `sol.extra`."""
     # Float32-particle (wide) filters do not reduce the 64-component weighted mean inside the fused loop
+    pf._use_p(p)
     wide = pf.particle_dtype == np.dtype(np.float32)
     r = _run(pf, u, y, TIME_FORWARD_TRAJECTORY, history, epoch, want_xhat=not wide)
     t = np.arange(r["T"]) * pf.Ts  # range(0, step=Ts, length=T)  solutions.jl:345
@@ -398,6 +551,7 @@ def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None):
 
 def loglik(pf, u, y, p=None, *, epoch=None, details=False):
     """loglik(pf,u,y,p)  smoothing.jl:227-236"""
+    pf._use_p(p)
     r = _run(pf, u, y, TIME_LOGLIK, False, epoch, want_steps=details, want_xhat=False)
     return r if details else r["ll"]
 
@@ -539,9 +693,14 @@ def bins(pf):
     return _get(pf, pf._lib.llpf_get_bins, (pf.N,))
 
 
+def xprev(pf):
+    """state(pf).xprev — at every API boundary xprev == x (copyto!(xprev, x) closes predict!, filtering.jl:151)"""
+    return _get(pf, pf._lib.llpf_get_xprev, (pf.N, pf.nx))
+
+
 def state(pf):
     x = particles(pf)
-    return dict(x=x, xprev=x.copy(), w=weights(pf), we=expweights(pf), j=ancestors(pf), bins=bins(pf), t=index(pf))
+    return dict(x=x, xprev=xprev(pf), w=weights(pf), we=expweights(pf), j=ancestors(pf), bins=bins(pf), t=index(pf))
 
 
 def set_state(pf, x, w, t):

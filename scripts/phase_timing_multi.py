@@ -23,6 +23,9 @@ if rank == 0:
     print(f"world={world} N=2^{log2n}/gpu thr={thr} ms={L.last_run_ms(pf):.3f}")
     for name, m in (("non-res", ~res), ("res", res)):
         if m.sum() == 0: continue
+        if name == "res":
+            print(f"   detail : offsets+totals-xchg {seg(2,14,m):6.2f} | scatter+push {seg(14,3,m):6.2f} | fence+bar {seg(3,10,m):6.2f} | "
+                  f"counts-xchg {seg(10,11,m):6.2f} | expand {seg(11,12,m):6.2f} | bar {seg(12,13,m):6.2f} | heavy-fill {seg(13,4,m):6.2f}")
         print(f" {name:8s}: scan1 {seg(0,1,m):6.2f} | bar {seg(1,2,m):6.2f} | scatter(+totals xchg) {seg(2,3,m):6.2f} | bar+peerbar {seg(3,4,m):6.2f} | main {seg(4,5,m) if name=='res' else seg(0,5,m):6.2f} | "
               f"blk-red {seg(5,6,m):6.2f} | bar {seg(6,7,m):6.2f} | combine {seg(7,9,m):6.2f} | xchg {seg(9,8,m):6.2f} | total {seg(0,8,m):6.2f}")
 dist.destroy_process_group()
