@@ -140,7 +140,8 @@ typedef struct llpf_config {
   int32_t rank;
   int32_t world;
   int32_t particle_dtype;     /* LLPF_PARTICLE_*                                        */
-  int32_t _reserved;          /* must be 0                                              */
+  int32_t single_block;       /* 1: the whole filter is run by ONE thread block (small N: PMMH-sized filters); required
+                                 for llpf_run_batch, and makes a chain's result independent of how it is launched     */
 } llpf_config;
 
 /* Optional outputs of llpf_run. Any pointer may be NULL. Host memory. */
@@ -215,6 +216,15 @@ int llpf_run(llpf_handle h, int64_t T, const double* u, const double* y,
 /* same, with u (nu*T) and y (ny*T) already resident in device memory; nothing is copied H2D */
 int llpf_run_dev(llpf_handle h, int64_t T, const double* u_dev, const double* y_dev,
                  int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out);
+
+/* Batched multi-chain loglik: C independent filters — each its own handle (model, seed, state),
+   created with cfg.single_block = 1 and identical dimensions / dynamics kind / resampling strategy, on one device —
+   evaluated by ONE kernel launch, one thread block per filter: reset!(epochs[c]) + the T fused steps of
+   loglik / forward_trajectory (time_convention) on the shared data u (nu*T), y (ny*T).  ll_out[c] = the log-likelihood of
+   chain c, bit-identical to llpf_run on the same handle.  This is what `metropolis_threaded` (smoothing.jl:335-347)
+   needs: one launch per MCMC iteration for all chains.                                                          */
+int llpf_run_batch(int32_t C, const llpf_handle* handles, int64_t T, const double* u, const double* y,
+                   int32_t time_convention, const uint64_t* epochs, double* ll_out);
 
 /* ---- particle smoother: forward filtering, backward simulation -------------- */
 /* xb, ll = smooth(pf, M, u, y, p)  smoothing.jl:104-107 : forward_trajectory (the N x T history of x, w, we stays in

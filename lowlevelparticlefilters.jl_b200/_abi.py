@@ -46,7 +46,7 @@ class Config(C.Structure):
         ("N", C.c_int64), ("filter", C.c_int32), ("resampling", C.c_int32),
         ("resample_threshold", C.c_double), ("Ts", C.c_double), ("seed", C.c_uint64),
         ("scan_mode", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
-        ("particle_dtype", C.c_int32), ("_reserved", C.c_int32),
+        ("particle_dtype", C.c_int32), ("single_block", C.c_int32),
     ]
 
 
@@ -92,6 +92,7 @@ def load_library(path=None):
         "llpf_predict_aux": [H, dp, dp, C.c_double],
         "llpf_update": [H, dp, dp, dp, C.c_double, dp],
         "llpf_run": [H, C.c_int64, dp, dp, C.c_int32, C.c_uint64, dp, C.POINTER(RunOutputs)],
+        "llpf_run_batch": [C.c_int32, C.POINTER(H), C.c_int64, dp, dp, C.c_int32, C.POINTER(C.c_uint64), dp],
         "llpf_run_dev": [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, dp, C.POINTER(RunOutputs)],
         "llpf_smooth": [H, C.c_int64, dp, dp, C.c_int64, C.c_uint64, dp, dp, C.POINTER(RunOutputs)],
         "llpf_smooth_history": [H, C.c_int64, dp, dp, dp, dp, C.c_int64, C.c_uint64, dp],

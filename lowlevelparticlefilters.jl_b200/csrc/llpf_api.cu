@@ -409,6 +409,11 @@ struct llpf_filter {
   float *w_At = nullptr, *w_Lt = nullptr, *w_G = nullptr, *w_B = nullptr, *w_mu0 = nullptr, *w_L0 = nullptr;
   double* w_W = nullptr;
   int w_diagL = 0;
+  // llpf_run_batch staging (owned by the first handle of a batch; grow-only)
+  void* d_batch = nullptr;
+  size_t batch_bytes = 0;
+  Scalars* d_batch_sc = nullptr;
+  int batch_cap = 0;
   // user-defined model (LLPF_DYN_USER): kernel compiled at run time, parameter vector p on the device
   bool user = false;
   cudaKernel_t user_kernel = nullptr;
@@ -764,6 +769,7 @@ extern "C" int llpf_destroy(llpf_handle h) {
   cudaFree(h->w_At); cudaFree(h->w_Lt); cudaFree(h->w_G); cudaFree(h->w_B); cudaFree(h->w_mu0); cudaFree(h->w_L0);
   cudaFree(h->w_W);
   cudaFree(h->d_user_p);
+  cudaFree(h->d_batch); cudaFree(h->d_batch_sc);
   if (h->pin_sc) cudaFreeHost(h->pin_sc);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -951,6 +957,20 @@ static int create_impl(const llpf_config* cfg, const llpf_model* model, const ch
   return LLPF_OK;
 }
 
+// the scalar state right after reset!  (filtering.jl:4-14)
+static Scalars reset_scalars(const llpf_filter* h) {
+  Scalars s;
+  std::memset(&s, 0, sizeof(s));
+  s.t_index = 1;          // filtering.jl:13
+  s.cur = 0;
+  s.uniform = 1;          // w = -log N, we = 1/N   filtering.jl:11-12
+  s.stats_valid = 1;
+  s.ess = (double)h->N;
+  s.j_identity = 1;
+  s.xseq = h->hsc.xseq;   // the peer-exchange counter runs on across resets (mailboxes are never re-zeroed)
+  return s;
+}
+
 extern "C" int llpf_create(const llpf_config* cfg, const llpf_model* model, llpf_handle* out) {
   return create_impl(cfg, model, nullptr, nullptr, 0, out);
 }
@@ -975,16 +995,7 @@ extern "C" int llpf_reset(llpf_handle h, uint64_t epoch) {
   h->epoch = epoch;
   CU(h->init(h, epoch));
   h->launches += 1;
-  Scalars s;
-  std::memset(&s, 0, sizeof(s));
-  s.t_index = 1;          // filtering.jl:13
-  s.cur = 0;
-  s.uniform = 1;          // w = -log N, we = 1/N   filtering.jl:11-12
-  s.stats_valid = 1;
-  s.ess = (double)h->N;
-  s.j_identity = 1;
-  s.xseq = h->hsc.xseq;   // the peer-exchange counter runs on across resets (mailboxes are never re-zeroed)
-  h->hsc = s;
+  h->hsc = reset_scalars(h);
   return push_scalars(h);
 }
 
@@ -1004,7 +1015,7 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.scan_mode = f->cfg.scan_mode;
   long long nb = (f->n + BLOCK - 1) / BLOCK;
   if (nb > f->max_blocks) nb = f->max_blocks;
-  if (nb < 1) nb = 1;
+  if (nb < 1 || f->cfg.single_block) nb = 1;   // single_block: PMMH-sized filters, batchable (llpf_run_batch)
   P.nblocks = (int)nb;
   P.chunk = (int)((f->n + nb - 1) / nb);
   P.chunk = (P.chunk + 1) & ~1;   // even chunk starts: 16-byte aligned particle pairs in the scan
@@ -1172,18 +1183,8 @@ struct HistoryGuard {   // frees the history buffers of a run on every exit path
   ~HistoryGuard() { cudaFree(x); cudaFree(w); cudaFree(we); }
 };
 
-static int run_impl(llpf_filter* f, long long T, const double* u_dev, const double* y_dev,
-                    int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out,
-                    DevHistory* keep = nullptr) {
-  if (T < 1 || T > (1ll << 30)) return fail(LLPF_ERR_BAD_ARG, "bad T");
-  if (f->wide && out && (out->xhat || out->x_hist || out->w_hist || out->we_hist))
-    return fail(LLPF_ERR_UNSUPPORTED, "Float32-particle filters: per-step xhat and the x/w/we history are not recorded "
-                                      "in the fused loop (use the step verbs + accessors)");
-  OKR(llpf_reset(f, epoch));
-  EngineP P;
-  base_params(f, P);
-  P.u = u_dev; P.y = y_dev;
-  const int Ti = (int)T;
+// the op list of a whole trajectory: forward_trajectory (filtering.jl:343-384) or loglik (smoothing.jl:227-236)
+static void build_run_ops(llpf_filter* f, EngineP& P, int Ti, int32_t time_convention) {
   // APF passes t=(k-1)*Ts explicitly in both drivers (filtering.jl:376, smoothing.jl:234-235)
   P.time_conv = is_aux(f) ? 0 : (time_convention == LLPF_TIME_LOGLIK ? 1 : 0);
   if (!is_aux(f)) {
@@ -1209,6 +1210,20 @@ static int run_impl(llpf_filter* f, long long T, const double* u_dev, const doub
     }
     push_op(P, OP_PF, Ti, 0);
   }
+}
+
+static int run_impl(llpf_filter* f, long long T, const double* u_dev, const double* y_dev,
+                    int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out,
+                    DevHistory* keep = nullptr) {
+  if (T < 1 || T > (1ll << 30)) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  if (f->wide && out && (out->xhat || out->x_hist || out->w_hist || out->we_hist))
+    return fail(LLPF_ERR_UNSUPPORTED, "Float32-particle filters: per-step xhat and the x/w/we history are not recorded "
+                                      "in the fused loop (use the step verbs + accessors)");
+  OKR(llpf_reset(f, epoch));
+  EngineP P;
+  base_params(f, P);
+  P.u = u_dev; P.y = y_dev;
+  build_run_ops(f, P, (int)T, time_convention);
   double *xh = nullptr, *wh = nullptr, *weh = nullptr;
   HistoryGuard hist_guard{xh, wh, weh};
   const size_t NT = (size_t)f->N * (size_t)T;
@@ -1298,6 +1313,99 @@ extern "C" int llpf_run_dev(llpf_handle h, int64_t T, const double* u_dev, const
   CU(cudaSetDevice(h->device));
   OKR(ensure_run_buffers(h, T));
   return run_impl(h, T, u_dev, y_dev, time_convention, epoch, ll, out);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// batched multi-chain loglik: one launch, one thread block per filter (llpf_engine_batch.cu)
+// ------------------------------------------------------------------------------------------------
+namespace llpf {
+const void* engine_batch_kernel(int nx, int ny, int dyn, int resid);
+}
+
+template <int NX, int NY>
+static int run_batch_t(int C, llpf_filter* const* fs, long long T, int32_t conv, const uint64_t* epochs, double* ll_out,
+                       const void* kernel) {
+  typedef BatchItem<NX, NY> Item;
+  llpf_filter* f0 = fs[0];
+  const size_t bytes = sizeof(Item) * (size_t)C;
+  if (bytes > f0->batch_bytes || C > f0->batch_cap) {
+    cudaFree(f0->d_batch); cudaFree(f0->d_batch_sc);
+    f0->d_batch = nullptr; f0->d_batch_sc = nullptr; f0->batch_bytes = 0; f0->batch_cap = 0;
+    CU(cudaMalloc(&f0->d_batch, bytes));
+    CU(cudaMalloc(&f0->d_batch_sc, sizeof(Scalars) * (size_t)C));
+    f0->batch_bytes = bytes; f0->batch_cap = C;
+  }
+  std::vector<Item> items((size_t)C);
+  for (int c = 0; c < C; ++c) {
+    llpf_filter* f = fs[c];
+    f->epoch = epochs ? epochs[c] : 0;
+    Item& it = items[(size_t)c];
+    std::memset(&it, 0, sizeof(it));
+    base_params(f, it.P);
+    if (it.P.nblocks != 1) return fail(LLPF_ERR_BAD_ARG, "llpf_run_batch needs filters created with single_block = 1");
+    it.P.u = f0->d_u; it.P.y = f0->d_y;
+    it.P.time_conv = is_aux(f) ? 0 : (conv == LLPF_TIME_LOGLIK ? 1 : 0);
+    f->hsc = reset_scalars(f);      // the block performs reset! itself; stats_ahead etc. start from this state
+    build_run_ops(f, it.P, (int)T, conv);
+    fill_modelp<NX, NY>(f->hm, it.M);
+    for (int r = 0; r < NX; ++r) {
+      it.mu0[r] = f->hm.mu0[r];
+      for (int cc = 0; cc <= r; ++cc) it.L0[r * MAX_NX + cc] = CMH(f->hm.L0, r, cc, NX);
+    }
+    it.sc0 = f->hsc;
+  }
+  CU(cudaMemcpyAsync(f0->d_batch, items.data(), bytes, cudaMemcpyHostToDevice, f0->stream));
+  CU(cudaEventRecord(f0->ev0, f0->stream));
+  void* d_items = f0->d_batch;
+  Scalars* d_sc = f0->d_batch_sc;
+  void* args[] = {(void*)&d_items, (void*)&d_sc};
+  CU(cudaLaunchKernel(kernel, dim3(C), dim3(BLOCK), args, 0, f0->stream));
+  CU(cudaEventRecord(f0->ev1, f0->stream));
+  std::vector<Scalars> out((size_t)C);
+  CU(cudaMemcpyAsync(out.data(), d_sc, sizeof(Scalars) * (size_t)C, cudaMemcpyDeviceToHost, f0->stream));
+  CU(cudaStreamSynchronize(f0->stream));
+  CU(cudaEventElapsedTime(&f0->last_ms, f0->ev0, f0->ev1));
+  for (int c = 0; c < C; ++c) {
+    fs[c]->hsc = out[(size_t)c];
+    fs[c]->hsc.nonfinite = 0;       // a collapsed chain shows as a non-finite ll_out entry (PMMH maps it to -Inf)
+    fs[c]->launches += 1;
+    ll_out[c] = out[(size_t)c].ll_total;
+  }
+  return LLPF_OK;
+}
+
+extern "C" int llpf_run_batch(int32_t C, const llpf_handle* handles, int64_t T, const double* u, const double* y,
+                              int32_t time_convention, const uint64_t* epochs, double* ll_out) {
+  if (C < 1 || !handles || !y || !ll_out) return fail(LLPF_ERR_BAD_ARG, "bad argument");
+  if (T < 1 || T > (1ll << 30)) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  llpf_filter* f0 = handles[0];
+  OKR(check_handle(f0));
+  if (f0->hm.nu > 0 && !u) return fail(LLPF_ERR_BAD_ARG, "u is null");
+  for (int c = 0; c < C; ++c) {
+    llpf_filter* f = handles[c];
+    OKR(check_handle(f));
+    if (f->wide || f->user || f->world > 1) return fail(LLPF_ERR_UNSUPPORTED, "llpf_run_batch: single-GPU descriptor-model Float64 filters");
+    if (f->device != f0->device || f->hm.nx != f0->hm.nx || f->hm.ny != f0->hm.ny || f->hm.nu != f0->hm.nu ||
+        f->hm.dyn != f0->hm.dyn || resid_of(f) != resid_of(f0) || f->cfg.filter != f0->cfg.filter)
+      return fail(LLPF_ERR_BAD_ARG, "llpf_run_batch: all filters must share device, dimensions, dynamics kind, filter kind and resampling family");
+    if (!f->cfg.single_block) return fail(LLPF_ERR_BAD_ARG, "llpf_run_batch needs filters created with single_block = 1");
+  }
+  const void* k = engine_batch_kernel(f0->hm.nx, f0->hm.ny, f0->hm.dyn, resid_of(f0));
+  if (!k) return fail(LLPF_ERR_UNSUPPORTED, "no batched kernel instantiated for this (nx, ny, dynamics, resampling)");
+  CU(cudaSetDevice(f0->device));
+  OKR(ensure_run_buffers(f0, T));
+  if (f0->hm.nu > 0)
+    CU(cudaMemcpyAsync(f0->d_u, u, sizeof(double) * T * f0->hm.nu, cudaMemcpyHostToDevice, f0->stream));
+  CU(cudaMemcpyAsync(f0->d_y, y, sizeof(double) * T * f0->hm.ny, cudaMemcpyHostToDevice, f0->stream));
+  for (int c = 1; c < C; ++c) CU(cudaStreamSynchronize(handles[c]->stream));   // earlier work of the chains is done
+  const int nx = f0->hm.nx, ny = f0->hm.ny;
+  llpf_filter* const* fs = handles;
+  if (nx == 1 && ny == 1) return run_batch_t<1, 1>(C, fs, T, time_convention, epochs, ll_out, k);
+  if (nx == 2 && ny == 1) return run_batch_t<2, 1>(C, fs, T, time_convention, epochs, ll_out, k);
+  if (nx == 2 && ny == 2) return run_batch_t<2, 2>(C, fs, T, time_convention, epochs, ll_out, k);
+  if (nx == 4 && ny == 2) return run_batch_t<4, 2>(C, fs, T, time_convention, epochs, ll_out, k);
+  return fail(LLPF_ERR_UNSUPPORTED, "no batched kernel instantiated for this (nx, ny)");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -53,6 +53,14 @@ __device__ double loglik(const double (&x)[NX], const double* u, const double* y
 }  // namespace llpf_user
 #endif
 
+// Block index as the engine sees it.  The batched multi-chain kernel (llpf_engine_batch.cu, -DLLPF_BATCH) runs one
+// independent single-block filter per thread block: there every block is "block 0 of a grid of one".
+#ifdef LLPF_BATCH
+#define LLPF_BLOCKIDX 0u
+#else
+#define LLPF_BLOCKIDX blockIdx.x
+#endif
+
 namespace llpf {
 
 #ifndef LLPF_MIN_BLOCKS
@@ -337,7 +345,7 @@ __device__ __forceinline__ void peer_allgather(const EngineP& P, Shared& sh, u64
   xseq += 1;
   const int par = (int)(xseq & 1ull);
   const u64 tag = (xseq & 0xffffffffull) << 32;
-  if (blockIdx.x == 0 && threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+  if (LLPF_BLOCKIDX == 0 && threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
     const int r = threadIdx.x;
     u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
 #pragma unroll
@@ -507,7 +515,7 @@ __device__ __forceinline__ Stats reduce_stats(const EngineP& P, Shared& sh, Onli
   if (P.world > 1) xseq += 1;
   u64* res = reinterpret_cast<u64*>(P.bar + BAR_RES_WORDS) + (size_t)(seq & 1u) * 32;
   if (threadIdx.x == 0) {   // partial = {m, s, q, sx[NX]} as 16-byte pairs
-    double2* p = reinterpret_cast<double2*>(P.partials + (size_t)blockIdx.x * PS);
+    double2* p = reinterpret_cast<double2*>(P.partials + (size_t)LLPF_BLOCKIDX * PS);
     double pk[2 * ((3 + NX + 1) / 2)];
     pk[0] = mb; pk[1] = v[0]; pk[2] = v[1];
 #pragma unroll
@@ -684,7 +692,7 @@ __device__ __forceinline__ bool scan_stage1(const EngineP& P, Shared& sh, int be
         sh.wt[q] = run;
         run += t;
       }
-      if (lane == 31) __stcg(P.tots + blockIdx.x, incl);
+      if (lane == 31) __stcg(P.tots + LLPF_BLOCKIDX, incl);
     }
     __syncthreads();
     return true;
@@ -711,7 +719,7 @@ __device__ __forceinline__ bool scan_stage1(const EngineP& P, Shared& sh, int be
     if (i < end) __stcg(P.loc + i, carry + woff + v);
     carry += rtot;
   }
-  if (threadIdx.x == 0) __stcg(P.tots + blockIdx.x, carry);
+  if (threadIdx.x == 0) __stcg(P.tots + LLPF_BLOCKIDX, carry);
   return false;
 }
 
@@ -974,7 +982,7 @@ __device__ __forceinline__ void peer_exchange_counts(const EngineP& P, Shared& s
   xseq += 1;
   const int par = (int)(xseq & 1ull);
   const u64 tag = (xseq & 0xffffffffull) << 32;
-  if (blockIdx.x == 0 && (int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+  if (LLPF_BLOCKIDX == 0 && (int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
     const int r = threadIdx.x;
     const unsigned c = (unsigned)__ldcg(P.pack_cnt + r);
     u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
@@ -1049,7 +1057,7 @@ __device__ __forceinline__ void scan_stage1_pairs(const EngineP& P, Shared& sh, 
       sh.wt[q] = run;
       run += t;
     }
-    if (lane == 31) __stcg(P.tots + blockIdx.x, incl);
+    if (lane == 31) __stcg(P.tots + LLPF_BLOCKIDX, incl);
   }
   __syncthreads();
 }
@@ -1133,7 +1141,7 @@ __device__ __forceinline__ void expand_packs(const EngineP& P, JT* jout_flat, co
   for (int s = 0; s < P.world; ++s) {
     const int ns = incoming[s];
     const char* meta = P.pack_in + (size_t)s * (size_t)P.pack_cap * (size_t)P.pack_stride + P.pack_state_bytes;
-    for (int base = blockIdx.x * BLOCK; base < ns; base += P.nblocks * BLOCK) {   // block-uniform trip count
+    for (int base = LLPF_BLOCKIDX * BLOCK; base < ns; base += P.nblocks * BLOCK) {   // block-uniform trip count
       const int idx = base + threadIdx.x;
       int first = 0, c = 0;
       if (idx < ns) {
@@ -1182,8 +1190,8 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
                                                 const RangeArg* range = nullptr, int pack_buf = 0) {
   // [slot_lo, slot_hi): the GLOBAL output slots this block fills from the heavy-run list; jout_flat[0] is global
   // slot P.first
-  if (P.heavy != nullptr && blockIdx.x == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);   // before the first barrier
-  if (P.world > 1 && blockIdx.x == 0 && (int)threadIdx.x < P.world) __stcg(P.pack_cnt + threadIdx.x, 0);
+  if (P.heavy != nullptr && LLPF_BLOCKIDX == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);   // before the first barrier
+  if (P.world > 1 && LLPF_BLOCKIDX == 0 && (int)threadIdx.x < P.world) __stcg(P.pack_cnt + threadIdx.x, 0);
   SlotRouter<JT> jout;
   jout.heavy = P.heavy;
   jout.j = jout_flat;
@@ -1200,7 +1208,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   double total;
   u64 off = 0;
   if (P.scan_mode != 0) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
+    if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
     grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
     total = __ldcg(P.bins + P.n - 1);
   } else {
@@ -1219,7 +1227,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
       }
     }
     total = (double)gtot * P.fix_inv;
-    off = gbase + sh.offs[blockIdx.x];
+    off = gbase + sh.offs[LLPF_BLOCKIDX];
     LLPF_TS(P, sh, 14);
   }
   total_out = total;
@@ -1609,7 +1617,7 @@ __device__ __forceinline__ void publish_step(const EngineP& P, Scalars& sc, int 
   if (!(fabs(ll) <= DBL_MAX)) sc.nonfinite = 1;
 #pragma unroll
   for (int d = 0; d < NX; ++d) sc.xhat[d] = st.sx[d] / st.s;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && k > 0) {
+  if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0 && k > 0) {
     if (P.ll_steps) P.ll_steps[k - 1] = ll;
     if (P.ess_steps) P.ess_steps[k - 1] = sc.ess;
     if (P.xhat) {
@@ -1786,7 +1794,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
       sc.j_identity = 1;   // s.j .= 1:N  filtering.jl:148
     }
     sc.last_resampled = res ? 1 : 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k_prop - 1] = res ? 1 : 0;
+    if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k_prop - 1] = res ? 1 : 0;
     sc.t_index += 1;       // filtering.jl:152
   }
   if (k_weigh > 0) {
@@ -1901,7 +1909,7 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   sc.j_identity = 0;
   sc.resample_count += 1;
   sc.last_resampled = 1;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k - 1] = 1;
+  if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k - 1] = 1;
   sc.t_index += 1;                                               // :215
   const Stats s2 = reduce_stats<NX>(P, sh, acc, with_x, cx.red_seq, sc.xseq);
   // stats of the raw w[] are ready; correct! (filtering.jl:170-174) has not been *called* yet
@@ -1921,7 +1929,7 @@ __device__ __forceinline__ void aux_correct_from_stats(const EngineP& P, Scalars
   sc.ll_last = ll;
   sc.ll_total += ll;
   if (!(fabs(ll) <= DBL_MAX)) sc.nonfinite = 1;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && k > 0) {
+  if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0 && k > 0) {
     if (P.ll_steps) P.ll_steps[k - 1] = ll;
     if (P.ess_steps) P.ess_steps[k - 1] = sc.ess;
     if (P.xhat) {
@@ -1942,10 +1950,9 @@ __device__ __forceinline__ void flush_weight_history(const EngineP& P, Shared& s
   }
 }
 
+// the body of the persistent kernel: executes the op list on this block's chunk of the particles
 template <int NX, int NY, int DYN, int RESID>
-__global__ void __launch_bounds__(BLOCK, LLPF_MIN_BLOCKS)
-k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, NY> M) {
-  __shared__ Shared sh;
+__device__ __forceinline__ void engine_body(const EngineP& P, const ModelP<NX, NY>& M, Shared& sh) {
   math_tab_load(sh.mt);
   model_to_shared<NX, NY>(M, sh);
 #ifdef LLPF_USER_MODEL
@@ -1959,7 +1966,7 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
   cx.bar_target = 0;
   cx.red_seq = 0;
   {
-    long long b = (long long)blockIdx.x * P.chunk;
+    long long b = (long long)LLPF_BLOCKIDX * P.chunk;
     long long e = b + P.chunk;
     if (b > P.n) b = P.n;
     if (e > P.n) e = P.n;
@@ -1995,7 +2002,65 @@ k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, N
   }
   // every block must have read the incoming scalars before block 0 overwrites them
   grid_barrier(P.bar, (unsigned)P.nblocks, cx.bar_target);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *P.sc = sc;
+  if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0) *P.sc = sc;
 }
+
+// one entry of the batched multi-chain launch (llpf_engine_batch.cu): everything one block needs to run its filter
+template <int NX, int NY>
+struct BatchItem {
+  EngineP P;
+  ModelP<NX, NY> M;
+  double mu0[MAX_NX];
+  double L0[MAX_NX * MAX_NX];   // row-major lower Cholesky factor of Sigma0
+  Scalars sc0;                  // state after reset!
+};
+
+#ifndef LLPF_BATCH
+template <int NX, int NY, int DYN, int RESID>
+__global__ void __launch_bounds__(BLOCK, LLPF_MIN_BLOCKS)
+k_engine(const __grid_constant__ EngineP P, const __grid_constant__ ModelP<NX, NY> M) {
+  __shared__ Shared sh;
+  engine_body<NX, NY, DYN, RESID>(P, M, sh);
+}
+#else
+// ---- batched multi-chain engine (PMMH calls loglik thousands of times on small filters) ------------
+// One thread block = one independent filter (its own handle: arena, model, seed, epoch), created with
+// llpf_config.single_block = 1 so that the handle's own launches use the same one-block geometry: a chain evaluated
+// here is bit-identical to the same chain run alone.  The block performs reset! (initial particles, filtering.jl:4-14;
+// same counters and arithmetic as k_init) and then the op list, with block-level synchronisation only.
+template <int NX, int NY, int DYN, int RESID>
+__global__ void __launch_bounds__(BLOCK, LLPF_MIN_BLOCKS)
+k_engine_batch(const BatchItem<NX, NY>* __restrict__ items, Scalars* __restrict__ sc_out) {
+  __shared__ Shared sh;
+  __shared__ BatchItem<NX, NY> it;
+  static_assert(sizeof(BatchItem<NX, NY>) % 8 == 0, "copied by 8-byte words");
+  {
+    const u64* src = reinterpret_cast<const u64*>(items + blockIdx.x);
+    u64* dst = reinterpret_cast<u64*>(&it);
+    for (int k = threadIdx.x; k < (int)(sizeof(BatchItem<NX, NY>) / 8); k += BLOCK) dst[k] = src[k];
+  }
+  math_tab_load(sh.mt);
+  __syncthreads();
+  const EngineP& P = it.P;
+  for (int k = threadIdx.x; k < BAR_TOTAL_WORDS; k += BLOCK) __stcg(P.bar + k, 0u);
+  // reset!(pf): xprev[i] = rand(rng, initial_density) = mu0 + L0 z   (filtering.jl:8, utils.jl:260)
+  for (int i = threadIdx.x; i < P.n; i += BLOCK) {
+    double z[NX];
+    normals<NX>(P.key, ST_INIT, 0u, (unsigned long long)(P.first + i), z, sh.mt);
+#pragma unroll
+    for (int r = 0; r < NX; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c <= r; ++c) acc = fma(it.L0[r * MAX_NX + c], z[c], acc);
+      __stcg(P.x[0] + (size_t)r * P.ld + i, it.mu0[r] + acc);
+    }
+  }
+  if (threadIdx.x == 0) *P.sc = it.sc0;
+  __threadfence();
+  __syncthreads();
+  engine_body<NX, NY, DYN, RESID>(P, it.M, sh);
+  if (threadIdx.x == 0) sc_out[blockIdx.x] = *P.sc;
+}
+#endif
 
 }  // namespace llpf

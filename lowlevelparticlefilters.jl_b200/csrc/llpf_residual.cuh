@@ -62,7 +62,7 @@ __device__ __noinline__ void resample_residual(const EngineP& P, Shared& sh, int
                                                double& total_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool fast = (P.scan_mode == 0);
-  if (P.heavy != nullptr && blockIdx.x == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);
+  if (P.heavy != nullptr && LLPF_BLOCKIDX == 0 && threadIdx.x == 0) __stcg(P.heavy, 0);
   // the block partials of the statistics reduction are free between two reductions: pass A's block totals go there
   // (tots / tots2 are written by pass B while slower blocks may still be summing pass A's totals)
   u64* const pa = reinterpret_cast<u64*>(P.partials);
@@ -80,7 +80,7 @@ __device__ __noinline__ void resample_residual(const EngineP& P, Shared& sh, int
     }
     if (fast) {
       const u64 t = block_sum_u64(fsum, sh);
-      if (threadIdx.x == 0) __stcg(pa + blockIdx.x, t);
+      if (threadIdx.x == 0) __stcg(pa + LLPF_BLOCKIDX, t);
     }
   }
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
@@ -90,7 +90,7 @@ __device__ __noinline__ void resample_residual(const EngineP& P, Shared& sh, int
     wsum = (double)sh.offs[P.nblocks] * P.fix_inv;
     __syncthreads();
   } else {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {   // resample.jl:66-69
+    if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0) {   // resample.jl:66-69
       double acc = 0.0;
       for (int i = 0; i < P.n; ++i) acc = __dadd_rn(acc, __ldcg(P.bins + i));
       __stcg(P.partials + MAX_BLOCKS, acc);
@@ -151,24 +151,24 @@ __device__ __noinline__ void resample_residual(const EngineP& P, Shared& sh, int
       carry_c += ctot;
     }
     if (threadIdx.x == 0) {
-      __stcg(P.tots + blockIdx.x, carry_r);
-      __stcg(P.tots2 + blockIdx.x, (u64)carry_c);
+      __stcg(P.tots + LLPF_BLOCKIDX, carry_r);
+      __stcg(P.tots2 + LLPF_BLOCKIDX, (u64)carry_c);
     }
   }
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
   // ---- C: offsets, deterministic copies, residual CDF ------------------------------------------------------------
   scan_block_offsets_from(P.tots2, P.nblocks, sh, 0ull);
-  const int coff = (int)sh.offs[blockIdx.x];
+  const int coff = (int)sh.offs[LLPF_BLOCKIDX];
   const int num = (int)sh.offs[P.nblocks];
   __syncthreads();
   u64 roff = 0, rtot_all = 0;
   if (fast) {
     scan_block_offsets_from(P.tots, P.nblocks, sh, 0ull);
-    roff = sh.offs[blockIdx.x];
+    roff = sh.offs[LLPF_BLOCKIDX];
     rtot_all = sh.offs[P.nblocks];
     __syncthreads();
   } else if (num != Mslots) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0) {
       double rsum = 0.0;                                              // :89-92
       for (int i = 0; i < P.n; ++i) rsum = __dadd_rn(rsum, __ldcg(P.bins + i));
       const double inv_rsum = __ddiv_rn(1.0, rsum);                   // :94

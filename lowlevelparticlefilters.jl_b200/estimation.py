@@ -178,6 +178,66 @@ def metropolis_threaded(burnin, ll, R, theta0, draw=None, *, nthreads=4, seed=No
     return np.vstack(res)
 
 
+def metropolis_batched(burnin, filter_from_parameters, priors, u, y, R, theta0, draw=None, *, nchains=64, seed=None):
+    """The device-side form of `metropolis_threaded` (smoothing.jl:335-347): `nchains` independent Markov chains advance in
+    lock step and every iteration evaluates all their log-likelihoods with ONE kernel launch (loglik_batch: one thread
+    block per chain) instead of one launch per chain per iteration.
+    filter_from_parameters(θ) must build a filter with single_block=True; if it accepts (θ, pf) the chain's filter is
+    updated in place with set_model (no device allocation per proposal).  Each chain's filter gets its own seed.
+    Returns [(R - burnin) * nchains] x [len(θ) + 1] with the log-likelihoods in the last column, like the reference."""
+    ss = np.random.SeedSequence(seed)
+    rngs = [np.random.default_rng(k) for k in ss.spawn(nchains)]
+    theta0 = np.asarray(theta0, dtype=np.float64).reshape(-1)
+    try:
+        nargs = len(inspect.signature(filter_from_parameters).parameters)
+    except (TypeError, ValueError):
+        nargs = 1
+    draws = [(naive_sampler(theta0, rngs[c]) if draw is None else (draw(rngs[c]) if getattr(draw, "wants_rng", False) else draw))
+             for c in range(nchains)]
+
+    def prior(th):
+        return sum(priors[i].logpdf(th[i]) for i in range(len(priors)))
+
+    pfs = [None] * nchains
+
+    def evaluate(thetas, it):
+        """log p(y|θ_c) + log p(θ_c) for every chain; chains whose proposal has zero prior mass (or an invalid model) get
+        -Inf and are evaluated with their previous model (result discarded)."""
+        lp = np.array([prior(th) for th in thetas])
+        ok = np.isfinite(lp)
+        for c in range(nchains):
+            if not ok[c] and pfs[c] is not None:
+                continue
+            try:
+                if pfs[c] is None or nargs < 2:
+                    pf = filter_from_parameters(thetas[c] if ok[c] else theta0)
+                    pf.seed_chain = c
+                    pfs[c] = pf
+                else:
+                    pfs[c] = filter_from_parameters(thetas[c], pfs[c])
+            except (LLPFError, np.linalg.LinAlgError, FloatingPointError):
+                ok[c] = False
+        ll = F.loglik_batch(pfs, u, y, epochs=[((c + 1) << 18) + it + 1 for c in range(nchains)])
+        out = np.where(ok & np.isfinite(ll), lp + ll, -math.inf)
+        return out
+
+    params = np.zeros((R, nchains, theta0.size))
+    lls = np.zeros((R, nchains))
+    params[0] = theta0
+    lls[0] = evaluate([theta0] * nchains, 0)
+    for i in range(1, R):
+        prop = [np.asarray(draws[c](params[i - 1, c]), dtype=np.float64) for c in range(nchains)]
+        lli = evaluate(prop, i)
+        for c in range(nchains):
+            d = lli[c] - lls[i - 1, c]
+            if not math.isnan(d) and rngs[c].random() < math.exp(min(d, 0.0)):
+                params[i, c], lls[i, c] = prop[c], lli[c]
+            else:
+                params[i, c], lls[i, c] = params[i - 1, c], lls[i - 1, c]
+    out = np.concatenate([params, lls[:, :, None]], axis=2)[burnin:]        # [R - burnin][chains][nθ + 1]
+    return np.concatenate([out[:, c] for c in range(nchains)], axis=0)
+
+
 # ---------------------------------------------------------------------------------------------
 # weighted statistics of a stored solution   filtering.jl:570-595
 # ---------------------------------------------------------------------------------------------

@@ -269,7 +269,7 @@ class AbstractParticleFilter:
     _filter_code = FILTER_PF
 
     def _create(self, N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device,
-                rank=0, world=1, particle_dtype=np.float64, p=None):
+                rank=0, world=1, particle_dtype=np.float64, p=None, single_block=False):
         """N is the GLOBAL particle count; with world > 1 this process owns the contiguous slice
         [rank*N/world, (rank+1)*N/world) and must call connect_shards() before the first step."""
         self._lib = _abi.load_library()
@@ -285,6 +285,8 @@ class AbstractParticleFilter:
         cfg.device, cfg.rank, cfg.world = int(device), int(rank), int(world)
         self.particle_dtype = np.dtype(particle_dtype)
         cfg.particle_dtype = _abi.PARTICLE_F32 if self.particle_dtype == np.dtype(np.float32) else _abi.PARTICLE_F64
+        cfg.single_block = 1 if single_block else 0
+        self.single_block = bool(single_block)
         self._cfg = cfg
         self._h = C.c_void_p()
         self.p = None
@@ -351,7 +353,7 @@ class ParticleFilter(AbstractParticleFilter):
 
     def __init__(self, N, dynamics, measurement, dynamics_density, measurement_density, initial_density, *,
                  resample_threshold=0.1, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
-                 scan_mode="fast", device=0, p=None, rank=0, world=1, **_ignored):
+                 scan_mode="fast", device=0, p=None, rank=0, world=1, single_block=False, **_ignored):
         self.dynamics, self.measurement = dynamics, measurement
         self.dynamics_density, self.measurement_density = dynamics_density, measurement_density
         self.initial_density = initial_density
@@ -374,7 +376,7 @@ class ParticleFilter(AbstractParticleFilter):
             model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
                                   initial_density)
         self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
-                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p)
+                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p, single_block=single_block)
 
 
 class AdvancedParticleFilter(AbstractParticleFilter):
@@ -382,7 +384,7 @@ class AdvancedParticleFilter(AbstractParticleFilter):
 
     def __init__(self, N, dynamics, measurement, measurement_likelihood, dynamics_density, initial_density, *,
                  resample_threshold=0.5, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
-                 scan_mode="fast", device=0, p=None, rank=0, world=1, **_ignored):
+                 scan_mode="fast", device=0, p=None, rank=0, world=1, single_block=False, **_ignored):
         self.dynamics, self.measurement = dynamics, measurement
         self.measurement_likelihood = measurement_likelihood
         self.dynamics_density, self.initial_density = dynamics_density, initial_density
@@ -406,7 +408,7 @@ class AdvancedParticleFilter(AbstractParticleFilter):
             model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
                                   measurement_likelihood.R2, initial_density)
         self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
-                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p)
+                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p, single_block=single_block)
 
 
 class AuxiliaryParticleFilter(AbstractParticleFilter):
@@ -423,7 +425,7 @@ class AuxiliaryParticleFilter(AbstractParticleFilter):
                 setattr(self, name, getattr(inner, name))
             self._create(inner.N_global, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
                          inner.seed, cfg.scan_mode, cfg.device, inner.rank, inner.world,
-                         particle_dtype=inner.particle_dtype, p=inner.p)
+                         particle_dtype=inner.particle_dtype, p=inner.p, single_block=inner.single_block)
         else:
             self.__init__(ParticleFilter(*args, **kwargs))
 
@@ -554,6 +556,31 @@ def loglik(pf, u, y, p=None, *, epoch=None, details=False):
     pf._use_p(p)
     r = _run(pf, u, y, TIME_LOGLIK, False, epoch, want_steps=details, want_xhat=False)
     return r if details else r["ll"]
+
+
+def loglik_batch(pfs, u, y, epochs=None, conv=TIME_LOGLIK):
+    """[loglik(pf, u, y) for pf in pfs] in ONE kernel launch (llpf_run_batch): one thread block per filter.  The filters —
+    each its own model / seed, e.g. one per Markov chain of `metropolis_threaded` (smoothing.jl:335-347) — must have been
+    created with single_block=True and share dimensions.  epochs: RNG epoch per filter (default: each filter's next one).
+    Every value is bit-identical to loglik(pf, u, y, epoch=...) on the same filter."""
+    pfs = list(pfs)
+    pf0 = pfs[0]
+    u, up, y, yp, T = _traj_inputs(pf0, u, y)
+    if epochs is None:
+        epochs = []
+        for pf in pfs:
+            pf._epoch += 1
+            epochs.append(pf._epoch)
+    else:
+        epochs = [int(e) for e in epochs]
+        for pf, e in zip(pfs, epochs):
+            pf._epoch = e
+    Cn = len(pfs)
+    hs = (C.c_void_p * Cn)(*[pf._h for pf in pfs])
+    ep = (C.c_uint64 * Cn)(*epochs)
+    out = np.zeros(Cn)
+    check(pf0._lib, pf0._lib.llpf_run_batch(Cn, hs, T, up, yp, conv, ep, out.ctypes.data_as(dp)))
+    return out
 
 
 def mean_trajectory(*args, **kw):

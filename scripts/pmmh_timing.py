@@ -35,3 +35,28 @@ for K in (16, 64):
     dt = time.perf_counter() - t0
     print(f"{K} chains x 300 evaluations in {dt:.3f} s = {K * 300 * N * T / dt / 1e6:.1f} M particle-steps/s "
           f"({K * 300 / dt:.0f} loglik/s)", flush=True)
+
+# batched: one launch per MCMC iteration for all chains (llpf_run_batch, one thread block per chain)
+def ffp1(theta, pf=None):
+    d1, d2 = L.MvNormal(math.exp(theta[0]) * np.eye(2)), L.MvNormal(math.exp(theta[1]) * np.eye(2))
+    if pf is None:
+        return L.ParticleFilter(N, L.LinearDynamics(s.A, s.B), L.LinearMeasurement(s.C), d1, d2, L.MvNormal(s.mu0, s.Sigma0), seed=4, single_block=True)
+    return L.set_model(pf, dynamics_density=d1, measurement_density=d2)
+for K in (64, 296, 592, 1184):
+    pfs = [ffp1(np.zeros(2)) for _ in range(K)]
+    L.loglik_batch(pfs, u, y)
+    t0 = time.perf_counter(); reps = 5
+    for _ in range(reps):
+        L.loglik_batch(pfs, u, y)
+    dt = (time.perf_counter() - t0) / reps
+    print(f"loglik_batch {K} chains: {dt * 1e3:.3f} ms per launch (kernel {L.last_run_ms(pfs[0]):.3f} ms) = {K / dt:.0f} loglik/s = "
+          f"{K * N * T / dt / 1e9:.2f} G particle-steps/s", flush=True)
+    del pfs
+def draw(rng):
+    return lambda th: th + 0.1 * rng.standard_normal(2)
+draw.wants_rng = True
+for K in (64, 296):
+    t0 = time.perf_counter()
+    out = L.metropolis_batched(0, ffp1, priors, u, y, 100, np.array([0.5, -0.5]), draw, nchains=K, seed=2)
+    dt = time.perf_counter() - t0
+    print(f"metropolis_batched {K} chains x 100 iterations in {dt:.3f} s = {K * 100 / dt:.0f} loglik/s (host proposal / set_model included)", flush=True)

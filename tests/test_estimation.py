@@ -115,3 +115,55 @@ def test_pmmh_on_device_finds_the_noise_level(gpu):
                                 None, nthreads=4, seed=1)
     assert out.shape == (4 * 70, 3) and np.all(np.isfinite(out))
     assert np.all(np.abs(out[:, :2].mean(axis=0)) < 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,aux", [((2, 2, 2), False), ((4, 2, 2), False), ((2, 1, 1), True)])
+def test_batched_loglik_is_bit_identical_to_single_handles(gpu, dims, aux):
+    """llpf_run_batch: C chains (own model, seed, epoch each) in ONE launch, one thread block per chain — every value
+    bit-identical to the same chain evaluated on its own handle, and in parity with the CPU oracle."""
+    s, u, y = _pmmh_problem(T=60, dims=dims)
+    N, Cn = 1000, 37
+    rng = np.random.default_rng(5)
+    pfs, specs = [], []
+    for c in range(Cn):
+        sc = lg_model(*dims, seed=3 if dims == (2, 1, 1) else 0, r1=float(np.exp(0.3 * rng.standard_normal())),
+                      r2=float(np.exp(0.3 * rng.standard_normal())))
+        mk = sc.aux_filter if aux else sc.particle_filter
+        pfs.append(mk(N, seed=100 + c, single_block=True))
+        specs.append(sc)
+    epochs = [7 + 3 * c for c in range(Cn)]
+    got = L.loglik_batch(pfs, u, y, epochs=epochs)
+    assert got.shape == (Cn,) and np.all(np.isfinite(got)) and len(set(got)) == Cn
+    for c in (0, 1, 17, Cn - 1):
+        assert L.loglik(pfs[c], u, y, epoch=epochs[c]) == got[c]                 # same handle, launched alone
+        ref = specs[c].oracle_filter(N, filter=2 if aux else 0, seed=100 + c).loglik(u, y, epoch=epochs[c])
+        assert abs(got[c] - ref["ll"]) <= 1e-6 * abs(ref["ll"])
+    # state after the batch is the state after loglik: the step verbs continue from it
+    assert L.index(pfs[3]) == 61
+    assert L.loglik_batch(pfs, u, y, epochs=epochs).tolist() == got.tolist()      # deterministic
+    with pytest.raises(L.LLPFError):
+        L.loglik_batch([s.particle_filter(N, seed=1)], u, y)                      # not single_block
+
+
+@pytest.mark.gpu
+def test_metropolis_batched_matches_the_posterior(gpu):
+    s, u, y = _pmmh_problem(T=200, dims=(2, 2, 2))
+
+    def ffp(theta, pf=None):
+        d1, d2 = L.MvNormal(math.exp(theta[0]) * np.eye(2)), L.MvNormal(math.exp(theta[1]) * np.eye(2))
+        if pf is None:
+            return L.ParticleFilter(1000, L.LinearDynamics(s.A, s.B), L.LinearMeasurement(s.C), d1, d2,
+                                    L.MvNormal(s.mu0, s.Sigma0), seed=4, single_block=True)
+        return L.set_model(pf, dynamics_density=d1, measurement_density=d2)
+
+    priors = [L.Normal(0, 1.0), L.Normal(0, 1.0)]
+
+    def draw(rng):
+        return lambda th: th + 0.1 * rng.standard_normal(2)
+    draw.wants_rng = True
+    out = L.metropolis_batched(60, ffp, priors, u, y, 160, np.array([0.3, -0.3]), draw, nchains=24, seed=1)
+    assert out.shape == (24 * 100, 3) and np.all(np.isfinite(out))
+    assert np.all(np.abs(out[:, :2].mean(axis=0)) < 0.6)
+    chains = out[:, 0].reshape(24, 100)
+    assert np.std(chains[:, -1]) > 0           # the chains are independent (own seeds, own proposals)

@@ -877,7 +877,8 @@ def test_headline_size_config2_against_oracle(gpu, scan_mode):
     resampling is chaotic in that respect: ONE moved ancestor shifts every later bin edge of the next resample by ~1e-6 = one
     threshold spacing, after which the two runs are different (statistically equivalent) realisations.  So FAST is held to:
     identical to the oracle (1e-10) up to the first moved ancestor, never diverging before the first resample, and within
-    Monte-Carlo distance of the oracle and of the closed-form Kalman filter afterwards.  (The per-resample claim — every
+    Monte-Carlo distance of the oracle and of the closed-form Kalman filter afterwards (measured on B200: identical for
+    the first 30 of the 40 steps = 13 resamples, then |ll - ll_oracle| = 5.9e-3).  (The per-resample claim — every
     moved ancestor is a +-1 neighbour inside the rounding gap — is test_systematic_fast_scan_flips_are_rounding_ties.)"""
     L = gpu
     from llpf_b200 import workloads as W
@@ -909,9 +910,10 @@ def test_headline_size_config2_against_oracle(gpu, scan_mode):
     assert k > first_res                                # nothing can differ before an ancestor has been chosen
     assert np.array_equal(got["resampled"][:k], ref["resampled"][:k])
     assert np.allclose(got["ess"][:k], ref["ess"][:k], rtol=1e-9)
-    # afterwards: another realisation of the same estimator (std of ll at N = 2^20, T = 40 is ~ 6e-3)
+    # afterwards: another realisation of the same estimator (std of ll at N = 2^20, T = 40 is ~ 0.1: measured 0.27 at
+    # N = 2^17 over seeds; the two runs share their first k steps, so they stay much closer to each other than to the KF)
     kf = O.kalman_loglik(s.oracle_model(), u, y)
-    assert abs(got["ll"] - ref["ll"]) < 0.05 and abs(got["ll"] - kf) < 0.1
+    assert abs(got["ll"] - ref["ll"]) < 0.1 and abs(got["ll"] - kf) < 0.5
     if k == T:
         assert abs(got["ll"] - ref["ll"]) <= LL_RTOL * abs(ref["ll"])
 
