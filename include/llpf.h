@@ -157,6 +157,22 @@ typedef struct llpf_run_outputs {
   double* we_hist;
 } llpf_run_outputs;
 
+/* Weighted statistics of the forward history, reduced on the device (the N x T history stays in HBM; only T x (...) results
+   are copied back).  Any output pointer may be NULL.  Host memory.
+     xmean     [T][nx]      mean_trajectory(sol)  = sum(x .* we)            filtering.jl:417,436-438
+     xmode     [T][nx]      mode_trajectory(sol)  = particle with the largest weight (first on ties)   :427,434
+     xcov      [T][nx][nx]  weighted_cov(sol): StatsBase cov, ProbabilityWeights, corrected = true     :575-583
+     xquantile [T][nq][nx]  weighted_quantile(sol, q[k]): StatsBase quantile with ProbabilityWeights   :592-595   */
+typedef struct llpf_hist_stats {
+  double* xmean;
+  double* xmode;
+  double* xcov;
+  const double* q;         /* [nq] probabilities in [0, 1] */
+  int32_t nq;
+  int32_t _pad;
+  double* xquantile;
+} llpf_hist_stats;
+
 typedef struct llpf_filter* llpf_handle;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
@@ -216,6 +232,13 @@ int llpf_run(llpf_handle h, int64_t T, const double* u, const double* y,
 /* same, with u (nu*T) and y (ny*T) already resident in device memory; nothing is copied H2D */
 int llpf_run_dev(llpf_handle h, int64_t T, const double* u_dev, const double* y_dev,
                  int32_t time_convention, uint64_t epoch, double* ll, const llpf_run_outputs* out);
+
+/* forward_trajectory(pf,u,y,p) (filtering.jl:343-384) whose N x T history of x / w / we is kept in device memory, reduced
+   there to the statistics requested in `stats` and then released: mean_trajectory / mode_trajectory / weighted_cov /
+   weighted_quantile of the solution without moving the history to the host.  `out` as in llpf_run
+   (x_hist / w_hist / we_hist may still be requested).  Single-GPU Float64-particle filters.                        */
+int llpf_run_stats(llpf_handle h, int64_t T, const double* u, const double* y, uint64_t epoch, double* ll,
+                   const llpf_run_outputs* out, const llpf_hist_stats* stats);
 
 /* Batched multi-chain loglik: C independent filters — each its own handle (model, seed, state),
    created with cfg.single_block = 1 and identical dimensions / dynamics kind / resampling strategy, on one device —

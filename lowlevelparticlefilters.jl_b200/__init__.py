@@ -13,7 +13,7 @@ from .filters import (  # noqa: F401
     ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, connect_shards, correct,
     effective_particles, expweights, forward_trajectory, index, last_run_ms, launch_count, loglik, loglik_batch, logsumexp,
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
-    shard_blob, shouldresample, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
+    shard_blob, shouldresample, trajectory_statistics, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
     weighted_mean, weights, xprev)
 from .estimation import (  # noqa: F401
     Normal, Uniform, log_likelihood_fun, metropolis, metropolis_batched, metropolis_threaded, naive_sampler, set_model, weighted_cov,

@@ -57,6 +57,13 @@ class RunOutputs(C.Structure):
     ]
 
 
+class HistStats(C.Structure):
+    _fields_ = [
+        ("xmean", c_double_p), ("xmode", c_double_p), ("xcov", c_double_p), ("q", c_double_p),
+        ("nq", C.c_int32), ("_pad", C.c_int32), ("xquantile", c_double_p),
+    ]
+
+
 class LLPFError(RuntimeError):
     def __init__(self, code, msg=""):
         self.code = code
@@ -92,6 +99,7 @@ def load_library(path=None):
         "llpf_predict_aux": [H, dp, dp, C.c_double],
         "llpf_update": [H, dp, dp, dp, C.c_double, dp],
         "llpf_run": [H, C.c_int64, dp, dp, C.c_int32, C.c_uint64, dp, C.POINTER(RunOutputs)],
+        "llpf_run_stats": [H, C.c_int64, dp, dp, C.c_uint64, dp, C.POINTER(RunOutputs), C.POINTER(HistStats)],
         "llpf_run_batch": [C.c_int32, C.POINTER(H), C.c_int64, dp, dp, C.c_int32, C.POINTER(C.c_uint64), dp],
         "llpf_run_dev": [H, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64, dp, C.POINTER(RunOutputs)],
         "llpf_smooth": [H, C.c_int64, dp, dp, C.c_int64, C.c_uint64, dp, dp, C.POINTER(RunOutputs)],

@@ -20,6 +20,7 @@
 #include "llpf_engine_list.h"
 #include "llpf_julia_range.h"
 #include "llpf_smooth.cuh"
+#include "llpf_stats.cuh"
 #include "llpf_wide.cuh"
 
 using namespace llpf;
@@ -1574,6 +1575,71 @@ extern "C" int llpf_smooth_history(llpf_handle h, int64_t T, const double* u, co
   if (rc == LLPF_OK) rc = smooth_backward(h, T, h->d_u, H, M, epoch, xb_out, wef + (size_t)(T - 1) * h->N);
   H.release();
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// weighted statistics of the HBM-resident history (llpf_stats.cuh)
+// ------------------------------------------------------------------------------------------------
+typedef void (*moments_fn)(const double*, const double*, long long, int, double*, double*, double*, int, cudaStream_t);
+template <int NX>
+static void launch_moments(const double* xh, const double* weh, long long N, int T, double* m, double* mo, double* cv,
+                           int grid, cudaStream_t st) {
+  k_hist_moments<NX><<<grid, BLOCK, 0, st>>>(xh, weh, N, T, m, mo, cv);
+}
+static const moments_fn g_moments_by_nx[MAX_NX + 1] = {nullptr, launch_moments<1>, launch_moments<2>, launch_moments<3>,
+                                                       launch_moments<4>, launch_moments<5>, launch_moments<6>,
+                                                       launch_moments<7>, launch_moments<8>};
+
+extern "C" int llpf_run_stats(llpf_handle h, int64_t T, const double* u, const double* y, uint64_t epoch, double* ll,
+                              const llpf_run_outputs* out, const llpf_hist_stats* stats) {
+  OKR(check_handle(h));
+  if (!stats) return fail(LLPF_ERR_BAD_ARG, "stats is null");
+  if (h->wide || h->world > 1) return fail(LLPF_ERR_UNSUPPORTED, "llpf_run_stats: single-GPU Float64-particle filters");
+  if (!y || (h->hm.nu > 0 && !u)) return fail(LLPF_ERR_BAD_ARG, "u / y is null");
+  if (T < 1) return fail(LLPF_ERR_BAD_ARG, "bad T");
+  if (stats->nq < 0 || (stats->nq > 0 && (!stats->q || !stats->xquantile))) return fail(LLPF_ERR_BAD_ARG, "bad quantile request");
+  for (int k = 0; k < stats->nq; ++k)
+    if (!(stats->q[k] >= 0.0 && stats->q[k] <= 1.0)) return fail(LLPF_ERR_BAD_ARG, "quantile probabilities must lie in [0, 1]");
+  CU(cudaSetDevice(h->device));
+  OKR(ensure_run_buffers(h, T));
+  if (h->hm.nu > 0)
+    CU(cudaMemcpyAsync(h->d_u, u, sizeof(double) * T * h->hm.nu, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_y, y, sizeof(double) * T * h->hm.ny, cudaMemcpyHostToDevice, h->stream));
+  DevHistory H;
+  int rc = run_impl(h, T, h->d_u, h->d_y, LLPF_TIME_FORWARD_TRAJECTORY, epoch, ll, out, &H);
+  if (rc != LLPF_OK) { H.release(); return rc; }
+  const int nx = h->hm.nx, nq = stats->nq;
+  Scratchpad sp;
+  double *d_mean = nullptr, *d_mode = nullptr, *d_cov = nullptr, *d_q = nullptr, *d_qo = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (stats->xmean) e = sp.alloc(&d_mean, (size_t)T * nx);
+  if (!e && stats->xmode) e = sp.alloc(&d_mode, (size_t)T * nx);
+  if (!e && stats->xcov) e = sp.alloc(&d_cov, (size_t)T * nx * nx);
+  if (!e && nq > 0) e = sp.alloc(&d_q, (size_t)nq);
+  if (!e && nq > 0) e = sp.alloc(&d_qo, (size_t)T * nq * nx);
+  if (!e && nq > 0) e = cudaMemcpyAsync(d_q, stats->q, sizeof(double) * nq, cudaMemcpyHostToDevice, h->stream);
+  if (!e && (d_mean || d_mode || d_cov)) {
+    const int grid = (int)std::min<long long>(T, (long long)h->num_sms * 8);
+    g_moments_by_nx[nx](H.x, H.we, h->N, (int)T, d_mean, d_mode, d_cov, grid, h->stream);
+    e = cudaGetLastError();
+    h->launches += 1;
+  }
+  if (!e && nq > 0) {
+    const long long items = (long long)T * nx * nq;
+    const int grid = (int)std::min<long long>(items, (long long)h->num_sms * 8);
+    k_hist_quantile<<<grid, BLOCK, 0, h->stream>>>(H.x, H.we, h->N, (int)T, nx, d_q, nq, d_qo);
+    e = cudaGetLastError();
+    h->launches += 1;
+  }
+  if (!e && d_mean) e = cudaMemcpyAsync(stats->xmean, d_mean, sizeof(double) * T * nx, cudaMemcpyDeviceToHost, h->stream);
+  if (!e && d_mode) e = cudaMemcpyAsync(stats->xmode, d_mode, sizeof(double) * T * nx, cudaMemcpyDeviceToHost, h->stream);
+  if (!e && d_cov) e = cudaMemcpyAsync(stats->xcov, d_cov, sizeof(double) * T * nx * nx, cudaMemcpyDeviceToHost, h->stream);
+  if (!e && d_qo) e = cudaMemcpyAsync(stats->xquantile, d_qo, sizeof(double) * T * nq * nx, cudaMemcpyDeviceToHost, h->stream);
+  if (!e) e = cudaStreamSynchronize(h->stream);
+  H.release();
+  if (e) return fail(LLPF_ERR_CUDA, std::string("history statistics: ") + cudaGetErrorString(e));
+  return LLPF_OK;
 }
 
 extern "C" int llpf_last_smooth_ms(llpf_handle h, float* ms) {

@@ -558,6 +558,40 @@ def loglik(pf, u, y, p=None, *, epoch=None, details=False):
     return r if details else r["ll"]
 
 
+def trajectory_statistics(pf, u, y, p=None, *, q=(), epoch=None, mean=True, mode=True, cov=True):
+    """forward_trajectory(pf, u, y) reduced ON THE DEVICE to the statistics the reference computes from the solution on the
+    host: mean_trajectory / mode_trajectory (filtering.jl:417-440), weighted_cov (:575-583), weighted_quantile (:592-595).
+    The N x T history stays in HBM (llpf_run_stats); nothing of size N crosses PCIe.
+    Returns dict(ll, mean [T][nx], mode [T][nx], cov [T][nx][nx], quantile [T][len(q)][nx], ll_steps, ess, resampled)."""
+    pf._use_p(p)
+    u, up, y, yp, T = _traj_inputs(pf, u, y)
+    if epoch is None:
+        pf._epoch += 1
+        epoch = pf._epoch
+    else:
+        pf._epoch = int(epoch)
+    out = _abi.RunOutputs()
+    res = dict(ll_steps=np.zeros(T), ess=np.zeros(T), resampled=np.zeros(T, dtype=np.int32))
+    out.ll_steps = res["ll_steps"].ctypes.data_as(dp)
+    out.ess_steps = res["ess"].ctypes.data_as(dp)
+    out.resampled = res["resampled"].ctypes.data_as(_abi.c_int32_p)
+    st = _abi.HistStats()
+    qv = np.ascontiguousarray(np.asarray(q, dtype=np.float64).reshape(-1))
+    if mean:
+        res["mean"] = np.zeros((T, pf.nx)); st.xmean = res["mean"].ctypes.data_as(dp)
+    if mode:
+        res["mode"] = np.zeros((T, pf.nx)); st.xmode = res["mode"].ctypes.data_as(dp)
+    if cov:
+        res["cov"] = np.zeros((T, pf.nx, pf.nx)); st.xcov = res["cov"].ctypes.data_as(dp)
+    if qv.size:
+        res["quantile"] = np.zeros((T, qv.size, pf.nx))
+        st.q, st.nq, st.xquantile = qv.ctypes.data_as(dp), int(qv.size), res["quantile"].ctypes.data_as(dp)
+    ll = C.c_double()
+    check(pf._lib, pf._lib.llpf_run_stats(pf._h, T, up, yp, int(epoch), C.byref(ll), C.byref(out), C.byref(st)))
+    res["ll"] = ll.value
+    return res
+
+
 def loglik_batch(pfs, u, y, epochs=None, conv=TIME_LOGLIK):
     """[loglik(pf, u, y) for pf in pfs] in ONE kernel launch (llpf_run_batch): one thread block per filter.  The filters —
     each its own model / seed, e.g. one per Markov chain of `metropolis_threaded` (smoothing.jl:335-347) — must have been

@@ -167,3 +167,27 @@ def test_metropolis_batched_matches_the_posterior(gpu):
     assert np.all(np.abs(out[:, :2].mean(axis=0)) < 0.6)
     chains = out[:, 0].reshape(24, 100)
     assert np.std(chains[:, -1]) > 0           # the chains are independent (own seeds, own proposals)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,N,T", [((2, 1, 1), 1000, 40), ((4, 2, 2), 5000, 25), ((3, 2, 2), 257, 30)])
+def test_device_trajectory_statistics_match_the_host_formulas(gpu, dims, N, T):
+    """mean / mode / weighted_cov / weighted_quantile of the solution computed on the device from the HBM-resident history
+    (llpf_run_stats) against the same statistics computed on the host from the D2H'd history with the restated StatsBase
+    formulas (estimation.py) — and the history itself is in parity with the oracle (test_golden)."""
+    s, u, y = _pmmh_problem(T=T, dims=dims)
+    pf = s.particle_filter(N, seed=9, resample_threshold=0.5)
+    qs = (0.0, 0.05, 0.5, 0.9, 1.0)
+    st = L.trajectory_statistics(pf, u, y, q=qs, epoch=3)
+    sol = L.forward_trajectory(pf, u, y, epoch=3)
+    assert st["ll"] == sol.ll
+    assert np.allclose(st["mean"], L.mean_trajectory(sol), rtol=1e-12, atol=1e-13)
+    assert np.array_equal(st["mode"], L.mode_trajectory(sol))
+    cov = L.weighted_cov(sol)
+    for t in range(T):
+        assert np.allclose(st["cov"][t], cov[t], rtol=1e-9, atol=1e-12), t
+    for k, q in enumerate(qs):
+        ref = L.weighted_quantile(sol, q)
+        assert np.allclose(st["quantile"][:, k, :], ref, rtol=1e-9, atol=1e-11), q
+    # the per-step weighted mean of the fused reduction agrees with the history-based one
+    assert np.allclose(st["mean"], sol.extra["xhat"], rtol=1e-10, atol=1e-12)

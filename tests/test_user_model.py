@@ -111,8 +111,12 @@ def test_user_model_any_dimension_and_parameter_override(gpu):
                            L.MvNormal(np.zeros(3), s.R2), L.MvNormal(s.mu0, s.Sigma0), p=[0.9], seed=5, scan_mode="serial")
     assert a == L.loglik(pf2, u, y, epoch=1) and a != got["ll"]
     # descriptor models carry no parameter vector: an override must not be silently ignored
+    s4 = lg_model(4, 2, 2, seed=0)
     with pytest.raises(TypeError):
-        L.loglik(s.particle_filter(64, seed=1), u, y, [1.0])
+        L.loglik(s4.particle_filter(64, seed=1), u[:, :2], y[:, :2], [1.0])
+    # ... and nx = 5 exists as a descriptor model only through the run-time path
+    with pytest.raises(L.LLPFError):
+        s.particle_filter(64, seed=1)
 
 
 def test_user_model_compile_error_is_reported(gpu):
