@@ -55,7 +55,11 @@ enum {
 enum {
   LLPF_RESAMPLE_SYSTEMATIC = 0, /* resample.jl:17-36  */
   LLPF_RESAMPLE_STRATIFIED = 1, /* resample.jl:38-61  */
-  LLPF_RESAMPLE_RESIDUAL = 2    /* resample.jl:63-117 (single-GPU filters)           */
+  LLPF_RESAMPLE_RESIDUAL = 2,   /* resample.jl:63-117 (single-GPU filters)           */
+  LLPF_RESAMPLE_METROPOLIS = 3  /* NOT in the reference: Metropolis resampling (Murray, Lee & Jacob 2016), the low-
+                                   synchronisation alternative: no prefix sum, ratios of weights only, biased for a
+                                   finite number of proposals (llpf_config.metropolis_steps).  Single-GPU filters;
+                                   (nx, ny) in {(4,2), (2,1), (2,2)} or any user-defined model.  Statistical tests only. */
 };
 
 /* ---- how the cumulative sum `bins` is formed (resample.jl:19-22) ----------------------- */
@@ -142,6 +146,8 @@ typedef struct llpf_config {
   int32_t particle_dtype;     /* LLPF_PARTICLE_*                                        */
   int32_t single_block;       /* 1: the whole filter is run by ONE thread block (small N: PMMH-sized filters); required
                                  for llpf_run_batch, and makes a chain's result independent of how it is launched     */
+  int32_t metropolis_steps;   /* LLPF_RESAMPLE_METROPOLIS: proposals per output slot (0 = default 32)                  */
+  int32_t _reserved;          /* must be 0                                                                             */
 } llpf_config;
 
 /* Optional outputs of llpf_run. Any pointer may be NULL. Host memory. */
@@ -295,6 +301,10 @@ int llpf_resample_stratified(int64_t N, const double* we, const double* u01, int
    LLPF_SCAN_SERIAL performs the three sums (:66-69, :89-92, :99-102) left to right like the reference.        */
 int llpf_resample_residual(int64_t N, const double* we, const double* u01, int64_t M,
                            int64_t* j_inout, double* bins_out, int32_t scan_mode, int32_t device);
+/* Metropolis resampling at the function boundary (extension, see LLPF_RESAMPLE_METROPOLIS): j_out[M] 1-based ancestors,
+   slot i starts its chain at particle i mod N; B proposals per slot; variates from (seed, stream 7).               */
+int llpf_resample_metropolis(int64_t N, const double* we, int64_t M, int32_t B, uint64_t seed, int64_t* j_out,
+                             int32_t device);
 /* logsumexp!(w, we) utils.jl:18-27 : in-place on host arrays w[N] (normalised log-weights out),
    we[N] out, returns ll = log(sum(exp(w_in)))                                                  */
 int llpf_logsumexp(int64_t N, double* w, double* we, double* ll, int32_t device);

@@ -22,7 +22,7 @@ struct LLPFConfig
     N::Int64; filter::Int32; resampling::Int32
     resample_threshold::Float64; Ts::Float64; seed::UInt64
     scan_mode::Int32; device::Int32; rank::Int32; world::Int32
-    particle_dtype::Int32; single_block::Int32      # 0 = Float64 particles, 1 = Float32 (nx, ny <= 64, linear-Gaussian)
+    particle_dtype::Int32; single_block::Int32; metropolis_steps::Int32; _reserved::Int32      # 0 = Float64 particles, 1 = Float32 (nx, ny <= 64, linear-Gaussian)
 end
 struct LLPFRunOutputs
     ll_steps::Ptr{Float64}; ess_steps::Ptr{Float64}; resampled::Ptr{Int32}; xhat::Ptr{Float64}

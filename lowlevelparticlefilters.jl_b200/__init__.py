@@ -10,7 +10,7 @@ from .filters import (  # noqa: F401
     AbstractParticleFilter, AdvancedParticleFilter, AuxiliaryParticleFilter, CudaDynamics, CudaLikelihood, CudaMeasurement,
     GaussianLikelihood,
     LinearDynamics, LinearMeasurement, MvNormal, ParticleFilter, ParticleFilteringSolution, QuadtankRK4,
-    ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, connect_shards, correct,
+    ResampleMetropolis, ResampleResidual, ResampleStratified, ResampleSystematic, ResamplingStrategy, ancestors, bins, connect_shards, correct,
     effective_particles, expweights, forward_trajectory, index, last_run_ms, launch_count, loglik, loglik_batch, logsumexp,
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
     shard_blob, shouldresample, trajectory_statistics, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,

@@ -15,7 +15,7 @@ OK, ERR_BAD_ARG, ERR_CUDA, ERR_NONFINITE, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NO
 # filter kinds
 FILTER_PF, FILTER_ADVANCED, FILTER_AUX, FILTER_AUX_ADVANCED = range(4)
 # resampling
-RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_RESIDUAL = range(3)
+RESAMPLE_SYSTEMATIC, RESAMPLE_STRATIFIED, RESAMPLE_RESIDUAL, RESAMPLE_METROPOLIS = range(4)
 # scan mode
 SCAN_FAST, SCAN_SERIAL = range(2)
 # dynamics
@@ -47,6 +47,7 @@ class Config(C.Structure):
         ("resample_threshold", C.c_double), ("Ts", C.c_double), ("seed", C.c_uint64),
         ("scan_mode", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
         ("particle_dtype", C.c_int32), ("single_block", C.c_int32),
+        ("metropolis_steps", C.c_int32), ("_reserved", C.c_int32),
     ]
 
 
@@ -121,6 +122,7 @@ def load_library(path=None):
         "llpf_resample_systematic": [C.c_int64, dp, C.c_double, C.c_int64, ip, dp, C.c_int32, C.c_int32],
         "llpf_resample_stratified": [C.c_int64, dp, dp, C.c_int64, ip, dp, C.c_int32, C.c_int32],
         "llpf_resample_residual": [C.c_int64, dp, dp, C.c_int64, ip, dp, C.c_int32, C.c_int32],
+        "llpf_resample_metropolis": [C.c_int64, dp, C.c_int64, C.c_int32, C.c_uint64, ip, C.c_int32],
         "llpf_logsumexp": [C.c_int64, dp, dp, dp, C.c_int32],
         "llpf_shard_blob_size": [C.POINTER(C.c_size_t)],
         "llpf_shard_export": [H, C.c_void_p],

@@ -544,7 +544,9 @@ static cudaError_t launch_init_wide(llpf_filter* f, uint64_t epoch) {
   return cudaGetLastError();
 }
 
-static int resid_of(const llpf_filter* f) { return f->cfg.resampling == LLPF_RESAMPLE_RESIDUAL ? 1 : 0; }
+static int resid_of(const llpf_filter* f) {   // which family of engine instantiations: 0 scan-based, 1 residual, 2 Metropolis
+  return f->cfg.resampling == LLPF_RESAMPLE_RESIDUAL ? 1 : (f->cfg.resampling == LLPF_RESAMPLE_METROPOLIS ? 2 : 0);
+}
 
 // ------------------------------------------------------------------------------------------------
 // user-defined models: run-time compilation of k_engine<NX, NY, LLPF_DYN_USER, RESID> with NVRTC
@@ -807,11 +809,14 @@ static int create_impl(const llpf_config* cfg, const llpf_model* model, const ch
   if (cfg->N < 1 || cfg->N >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "need 1 <= N < 2^31");
   if (cfg->filter < 0 || cfg->filter > 3) return fail(LLPF_ERR_BAD_ARG, "unknown filter kind");
   if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED &&
-      cfg->resampling != LLPF_RESAMPLE_RESIDUAL)
+      cfg->resampling != LLPF_RESAMPLE_RESIDUAL && cfg->resampling != LLPF_RESAMPLE_METROPOLIS)
     return fail(LLPF_ERR_BAD_ARG, "unknown resampling strategy");
   const int world = cfg->world < 1 ? 1 : cfg->world;
-  if (world > 1 && cfg->resampling == LLPF_RESAMPLE_RESIDUAL)
-    return fail(LLPF_ERR_UNSUPPORTED, "residual resampling is single-GPU (sharded filters: systematic or stratified)");
+  if (world > 1 && (cfg->resampling == LLPF_RESAMPLE_RESIDUAL || cfg->resampling == LLPF_RESAMPLE_METROPOLIS))
+    return fail(LLPF_ERR_UNSUPPORTED, "residual / Metropolis resampling are single-GPU (sharded filters: systematic or stratified)");
+  if (cfg->resampling == LLPF_RESAMPLE_METROPOLIS && cfg->particle_dtype == LLPF_PARTICLE_F32)
+    return fail(LLPF_ERR_UNSUPPORTED, "Metropolis resampling: Float64-particle filters");
+  if (cfg->metropolis_steps < 0) return fail(LLPF_ERR_BAD_ARG, "metropolis_steps must be >= 0");
   if (world > MAX_WORLD) return fail(LLPF_ERR_UNSUPPORTED, "at most 8 ranks (one box)");
   if (world > 1) {
     if (cfg->rank < 0 || cfg->rank >= world) return fail(LLPF_ERR_BAD_ARG, "bad rank");
@@ -1027,6 +1032,7 @@ static void base_params(llpf_filter* f, EngineP& P) {
   P.heavy = (int*)(f->arena + f->o_heavy);
   P.tots2 = (u64*)(f->arena + f->o_tots2);
   P.nx = f->hm.nx; P.wide = f->wide ? 1 : 0;
+  P.metro_steps = f->cfg.metropolis_steps;
   P.pack_cnt = (int*)(f->arena + f->o_pack_cnt);
   P.pack_cap = f->n; P.pack_stride = f->pack_stride; P.pack_state_bytes = f->pack_state_bytes;
   P.pack_in = f->world > 1 ? f->arena + f->o_pack : nullptr;
@@ -1982,6 +1988,44 @@ extern "C" int llpf_resample_residual(int64_t N, const double* we, const double*
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(j_inout, d_j, sizeof(long long) * M, cudaMemcpyDeviceToHost));
   if (bins_out) CU(cudaMemcpy(bins_out, d_bins, sizeof(double) * N, cudaMemcpyDeviceToHost));
+  return LLPF_OK;
+}
+
+
+// Metropolis resampling at the function boundary (llpf_metropolis.cuh; extension, not in the reference)
+__global__ void k_resample_metropolis(const double* __restrict__ we, long long N, long long M, int B, RngKey key,
+                                      long long* __restrict__ j_out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
+    long long k = i % N;
+    double wk = we[k];
+    for (int b = 0; 2 * b < B; ++b) {
+      const uint4 r = rng_block(key, ST_METRO, 0u, (unsigned long long)i, (uint32_t)b);
+      const long long j0 = (long long)__umulhi(r.x, (uint32_t)N), j1 = (long long)__umulhi(r.z, (uint32_t)N);
+      const double w0 = we[j0], w1 = we[j1];
+      if (uniform32_open(r.y) * wk <= w0) { k = j0; wk = w0; }
+      if (2 * b + 1 < B && uniform32_open(r.w) * wk <= w1) { k = j1; wk = w1; }
+    }
+    j_out[i] = k + 1;
+  }
+}
+extern "C" int llpf_resample_metropolis(int64_t N, const double* we, int64_t M, int32_t B, uint64_t seed, int64_t* j_out,
+                                        int32_t device) {
+  if (N < 1 || M < 1 || B < 1 || !we || !j_out) return fail(LLPF_ERR_BAD_ARG, "bad argument");
+  if (N >= (1ll << 31) || M >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "N, M < 2^31");
+  int ndev = 0;
+  OKR(llpf_device_count(&ndev));
+  if (device < 0 || device >= ndev) return fail(LLPF_ERR_NO_DEVICE, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  Scratchpad sp;
+  double* d_we = nullptr;
+  long long* d_j = nullptr;
+  CU(sp.alloc(&d_we, (size_t)N)); CU(sp.alloc(&d_j, (size_t)M));
+  CU(cudaMemcpy(d_we, we, sizeof(double) * N, cudaMemcpyHostToDevice));
+  RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), 0u};
+  const int grid = (int)std::min<long long>((M + 255) / 256, 148 * 8);
+  k_resample_metropolis<<<grid, 256>>>(d_we, N, M, B, key, d_j);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(j_out, d_j, sizeof(long long) * M, cudaMemcpyDeviceToHost));
   return LLPF_OK;
 }
 

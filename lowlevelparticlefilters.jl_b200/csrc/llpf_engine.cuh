@@ -180,6 +180,8 @@ struct EngineP {
   int pack_state_bytes;           // offset of the meta int4 {gid, first global slot, count, 0}
   int nx;                         // state dimension (f64 engines)
   int wide;                       // 1: Float32 AoS rows of 64 (llpf_wide.cuh), 0: f64 SoA
+  int metro_steps;                // Metropolis resampling: proposals per slot (llpf_metropolis.cuh)
+  int pad_tail;
 #ifdef LLPF_USER_MODEL
   const double* user_p;   // DYN == 2: the filter's parameter vector `p` (device memory), handed to the user functions
 #endif
@@ -1300,6 +1302,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
 
 }  // namespace llpf
 #include "llpf_residual.cuh"   // resample(ResampleResidual, ...) — uses the scan / scatter helpers above
+#include "llpf_metropolis.cuh" // Metropolis resampling (extension; RESID == 2 instantiations)
 namespace llpf {
 
 // ------------------------------------------------------------------------------------------------
@@ -1654,7 +1657,19 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
   double* const wh = P.w_hist;
   double* const weh = P.we_hist;
   int f_total = 0;
-  if constexpr (RESID != 0) {
+  if constexpr (RESID == 2) {
+    if (res) {   // Metropolis resampling (llpf_metropolis.cuh; not in the reference)
+      resample_metropolis(P, sh, cx.beg, cx.end, cx.bar_target, ws.uniform ? nullptr : ws.w, step_idx,
+                          [=](int i, double wr) {
+                            if (hist_w) {
+                              __stcs(wh + hbase + i, ws.weight_norm_raw(wr));
+                              __stcs(weh + hbase + i, ws.expweight_raw(wr));
+                            }
+                          });
+      f_total = (int)P.N;
+      sc.bins_total = 1.0;
+    }
+  } else if constexpr (RESID != 0) {
     if (res) {   // ResampleResidual  resample.jl:63-117
       WeSrc rs;
       rs.w = ws.w; rs.mode = ws.uniform ? 1 : (ws.pend ? 3 : 2);
@@ -1858,7 +1873,11 @@ __device__ __forceinline__ void aux_step(const EngineP& P, const ModelP<NX, NY>&
   // expnormalize!(w): exp(w-offset)*1/(s+1)   utils.jl:57-63 ; then resample (always)  :205
   double total;
   int f_total;
-  if constexpr (RESID != 0) {   // ResampleResidual
+  if constexpr (RESID == 2) {   // Metropolis resampling on v = w + lambda (ratios: normalisation not needed)
+    resample_metropolis(P, sh, cx.beg, cx.end, cx.bar_target, wraw, step_idx, [](int, double) {});
+    f_total = (int)P.N;
+    total = 1.0;
+  } else if constexpr (RESID != 0) {   // ResampleResidual
     WeSrc rs;
     rs.w = wraw; rs.mode = 3;
     rs.pm = m1; rs.pls = 0.0; rs.inv_s = inv1; rs.weu = 0.0; rs.wu = 0.0; rs.T = mtp;

@@ -2,7 +2,8 @@
 // LLPF_INST_GROUPS translation units (llpf_engine_inst.cu compiled once per group, in parallel: a single TU with all
 // of them takes ~6 min of nvcc).  X(group, NX, NY, DYN, RESID)
 //   DYN   0 linear dynamics, 1 quadtank RK4 (include/llpf.h LLPF_DYN_*)
-//   RESID 0 systematic / stratified resampling, 1 residual resampling (llpf_residual.cuh)
+//   RESID 0 systematic / stratified resampling, 1 residual resampling (llpf_residual.cuh), 2 Metropolis resampling
+//         (llpf_metropolis.cuh; extension, a few instantiations — user-defined models get theirs at run time)
 #pragma once
 #define LLPF_INST_GROUPS 8
 #ifdef LLPF_DISPATCH_MIN   /* quick tuning builds: only the headline instantiation */
@@ -16,5 +17,6 @@
   X(4, 6, 3, 0, 0) X(4, 3, 2, 0, 0) X(4, 3, 3, 0, 1) X(4, 4, 2, 0, 1)                    \
   X(5, 6, 2, 0, 0) X(5, 3, 3, 0, 0) X(5, 4, 1, 0, 1) X(5, 6, 3, 0, 1)                    \
   X(6, 4, 4, 0, 0) X(6, 4, 1, 0, 0) X(6, 4, 3, 0, 1) X(6, 6, 2, 0, 1)                    \
-  X(7, 4, 3, 0, 0) X(7, 4, 4, 0, 1)
+  X(7, 4, 3, 0, 0) X(7, 4, 4, 0, 1)                                                      \
+  X(1, 4, 2, 0, 2) X(3, 2, 1, 0, 2) X(5, 2, 2, 0, 2) X(7, 4, 2, 1, 2)
 #endif

@@ -151,10 +151,10 @@ k_hist_quantile(const double* __restrict__ xh, const double* __restrict__ weh, l
     // ---- pass 0: total weight, smallest / largest key among the non-zero weights, weight of the smallest ----
     u64 tot = 0, kmin = ~0ull, kmax = 0ull;
     for (long long n = threadIdx.x; n < N; n += BLOCK) {
-      const u64 wf = to_fixed(__ldcs(we + n), FIX_SCALE);
-      if (wf) {
+      const double e = __ldcs(we + n);
+      if (e != 0.0) {   // StatsBase drops exactly-zero weights only: a weight of 1e-300 still takes part in the order
         const u64 k = f64_key(__ldcs(x + (size_t)n * nx));
-        tot += wf;
+        tot += to_fixed(e, FIX_SCALE);
         kmin = k < kmin ? k : kmin;
         kmax = k > kmax ? k : kmax;
       }
@@ -179,8 +179,8 @@ k_hist_quantile(const double* __restrict__ xh, const double* __restrict__ weh, l
     {
       u64 w1 = 0;
       for (long long n = threadIdx.x; n < N; n += BLOCK) {
-        const u64 wf = to_fixed(__ldcs(we + n), FIX_SCALE);
-        if (wf && f64_key(__ldcs(x + (size_t)n * nx)) == KMIN) w1 += wf;
+        const double e = __ldcs(we + n);
+        if (e != 0.0 && f64_key(__ldcs(x + (size_t)n * nx)) == KMIN) w1 += to_fixed(e, FIX_SCALE);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) w1 += __shfl_xor_sync(0xffffffffu, w1, o);
@@ -193,8 +193,10 @@ k_hist_quantile(const double* __restrict__ xh, const double* __restrict__ weh, l
     const double hs = h * FIX_SCALE;
     const u64 ht = (hs >= 9.2e18) ? ~0ull : __double2ull_rn(hs);
     double result;
-    if (TOT == 0) {
+    if (KMIN > KMAX) {
       result = __longlong_as_double(0x7ff8000000000000ll);       // all weights zero: NaN
+    } else if (p == 0.0 || TOT == 0) {
+      result = key_f64(KMIN);                                    // h = w_1: v_1 + 0 * (v_2 - v_1)
     } else if (ht >= TOT) {
       result = key_f64(KMAX);                                    // S_k <= h for every k: v[end]
     } else {
@@ -231,8 +233,7 @@ k_hist_quantile(const double* __restrict__ xh, const double* __restrict__ weh, l
       u64 kp = 0;
       bool any = false;
       for (long long n = threadIdx.x; n < N; n += BLOCK) {
-        const u64 wf = to_fixed(__ldcs(we + n), FIX_SCALE);
-        if (!wf) continue;
+        if (__ldcs(we + n) == 0.0) continue;
         const u64 k = f64_key(__ldcs(x + (size_t)n * nx));
         if (k < K && (!any || k > kp)) { kp = k; any = true; }
       }
@@ -246,8 +247,8 @@ k_hist_quantile(const double* __restrict__ xh, const double* __restrict__ weh, l
       __syncthreads();
       const double vk = key_f64(K);
       const double Skold = (double)s_below * FIX_INV, Sk = (double)(s_below + s_wk) * FIX_INV;
-      if (s_below == 0) {
-        result = vk;                                             // cannot happen for h >= w_1 (kept for safety)
+      if (s_kprev == 0 && !(KMIN < K)) {
+        result = vk;                                             // the crossing element is the first one
       } else {
         const double vkold = key_f64(s_kprev);
         result = vkold + (h - Skold) / (Sk - Skold) * (vk - vkold);

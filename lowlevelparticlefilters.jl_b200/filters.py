@@ -50,6 +50,13 @@ class ResampleResidual(ResamplingStrategy):
     code = _abi.RESAMPLE_RESIDUAL
 
 
+class ResampleMetropolis(ResamplingStrategy):
+    """NOT in the reference: Metropolis resampling (Murray, Lee & Jacob 2016) — per output slot a B-step Metropolis chain
+    over the particle indices using weight ratios only (no prefix sum, one grid barrier).  Biased for finite B
+    (`metropolis_steps=` of the filter constructors, default 32).  Single-GPU, Float64 particles."""
+    code = _abi.RESAMPLE_METROPOLIS
+
+
 @dataclass
 class MvNormal:
     """MvNormal(mu, Sigma) / MvNormal(Sigma) — Distributions.MvNormal or SimpleMvNormal (src/utils.jl:241-273)."""
@@ -269,7 +276,7 @@ class AbstractParticleFilter:
     _filter_code = FILTER_PF
 
     def _create(self, N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device,
-                rank=0, world=1, particle_dtype=np.float64, p=None, single_block=False):
+                rank=0, world=1, particle_dtype=np.float64, p=None, single_block=False, metropolis_steps=0):
         """N is the GLOBAL particle count; with world > 1 this process owns the contiguous slice
         [rank*N/world, (rank+1)*N/world) and must call connect_shards() before the first step."""
         self._lib = _abi.load_library()
@@ -286,6 +293,7 @@ class AbstractParticleFilter:
         self.particle_dtype = np.dtype(particle_dtype)
         cfg.particle_dtype = _abi.PARTICLE_F32 if self.particle_dtype == np.dtype(np.float32) else _abi.PARTICLE_F64
         cfg.single_block = 1 if single_block else 0
+        cfg.metropolis_steps = int(metropolis_steps)
         self.single_block = bool(single_block)
         self._cfg = cfg
         self._h = C.c_void_p()
@@ -353,7 +361,8 @@ class ParticleFilter(AbstractParticleFilter):
 
     def __init__(self, N, dynamics, measurement, dynamics_density, measurement_density, initial_density, *,
                  resample_threshold=0.1, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
-                 scan_mode="fast", device=0, p=None, rank=0, world=1, single_block=False, **_ignored):
+                 scan_mode="fast", device=0, p=None, rank=0, world=1, single_block=False, metropolis_steps=0,
+                 **_ignored):
         self.dynamics, self.measurement = dynamics, measurement
         self.dynamics_density, self.measurement_density = dynamics_density, measurement_density
         self.initial_density = initial_density
@@ -376,7 +385,7 @@ class ParticleFilter(AbstractParticleFilter):
             model = _ModelBuffers(dynamics, measurement.C, dynamics_density.Sigma, measurement_density.Sigma,
                                   initial_density)
         self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
-                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p, single_block=single_block)
+                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p, single_block=single_block, metropolis_steps=metropolis_steps)
 
 
 class AdvancedParticleFilter(AbstractParticleFilter):
@@ -384,7 +393,8 @@ class AdvancedParticleFilter(AbstractParticleFilter):
 
     def __init__(self, N, dynamics, measurement, measurement_likelihood, dynamics_density, initial_density, *,
                  resample_threshold=0.5, resampling_strategy=ResampleSystematic, Ts=1.0, seed=0,
-                 scan_mode="fast", device=0, p=None, rank=0, world=1, single_block=False, **_ignored):
+                 scan_mode="fast", device=0, p=None, rank=0, world=1, single_block=False, metropolis_steps=0,
+                 **_ignored):
         self.dynamics, self.measurement = dynamics, measurement
         self.measurement_likelihood = measurement_likelihood
         self.dynamics_density, self.initial_density = dynamics_density, initial_density
@@ -408,7 +418,7 @@ class AdvancedParticleFilter(AbstractParticleFilter):
             model = _ModelBuffers(dynamics, measurement_likelihood.C, dynamics_density.Sigma,
                                   measurement_likelihood.R2, initial_density)
         self._create(N, model, resample_threshold, resampling_strategy, Ts, seed, scan_mode, device, rank, world,
-                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p, single_block=single_block)
+                     particle_dtype=getattr(initial_density, "dtype", np.float64), p=p, single_block=single_block, metropolis_steps=metropolis_steps)
 
 
 class AuxiliaryParticleFilter(AbstractParticleFilter):
@@ -425,7 +435,8 @@ class AuxiliaryParticleFilter(AbstractParticleFilter):
                 setattr(self, name, getattr(inner, name))
             self._create(inner.N_global, inner._model, inner.resample_threshold, inner.resampling_strategy, inner.Ts,
                          inner.seed, cfg.scan_mode, cfg.device, inner.rank, inner.world,
-                         particle_dtype=inner.particle_dtype, p=inner.p, single_block=inner.single_block)
+                         particle_dtype=inner.particle_dtype, p=inner.p, single_block=inner.single_block,
+                         metropolis_steps=inner._cfg.metropolis_steps)
         else:
             self.__init__(ParticleFilter(*args, **kwargs))
 
@@ -538,17 +549,60 @@ def _run(pf, u, y, conv, history, epoch, want_steps=True, want_xhat=True):
     return res
 
 
-def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None):
-    """forward_trajectory(pf,u,y,p) -> ParticleFilteringSolution   filtering.jl:343-384.
-    history=False skips the N x T x/w/we arrays (they are then None); the per-step ll, ESS,
-    resample flags and weighted means are always returned in `sol.extra`."""
-    # Float32-particle (wide) filters do not reduce the 64-component weighted mean inside the fused loop
+def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None, pre_correct_cb=None, post_correct_cb=None,
+                       pre_predict_cb=None, post_predict_cb=None):
+    """forward_trajectory(pf,u,y,p; pre_correct_cb, post_correct_cb, pre_predict_cb, post_predict_cb)
+    -> ParticleFilteringSolution   filtering.jl:343-384.
+    history=False skips the N x T x/w/we arrays (they are then None); the per-step ll, ESS, resample flags and weighted
+    means are always returned in `sol.extra`.
+    Without callbacks the whole trajectory is ONE kernel launch.  With any of the four callbacks of filtering.jl:343 the
+    loop runs step by step through the verbs (one launch per correct! / predict!), calling them exactly where the
+    reference does (:353-362): pre_correct_cb(pf,u,y,p,t), post_correct_cb(pf,u,y,p,t,ll), pre_predict_cb(pf,u,y,p,t,ll),
+    post_predict_cb(pf,u,y,p,t).  The callbacks may inspect or modify the filter through the accessors / set_state.
+    The result is the same trajectory (same RNG counters) as the fused launch."""
     pf._use_p(p)
+    cbs = (pre_correct_cb, post_correct_cb, pre_predict_cb, post_predict_cb)
+    if any(cb is not None for cb in cbs):
+        if isinstance(pf, AuxiliaryParticleFilter):
+            raise TypeError("forward_trajectory(::AuxiliaryParticleFilter) takes no callbacks (filtering.jl:367)")
+        return _forward_trajectory_stepwise(pf, u, y, p, history, epoch, *cbs)
     wide = pf.particle_dtype == np.dtype(np.float32)
     r = _run(pf, u, y, TIME_FORWARD_TRAJECTORY, history, epoch, want_xhat=not wide)
     t = np.arange(r["T"]) * pf.Ts  # range(0, step=Ts, length=T)  solutions.jl:345
     extra = {k: r.get(k) for k in ("ll_steps", "ess", "resampled", "xhat")}
     return ParticleFilteringSolution(pf, r["u"], r["y"], r.get("x"), r.get("w"), r.get("we"), r["ll"], t, extra)
+
+
+def _forward_trajectory_stepwise(pf, u, y, p, history, epoch, pre_correct_cb, post_correct_cb, pre_predict_cb,
+                                 post_predict_cb):
+    """the reference's loop, filtering.jl:351-363, on the step verbs"""
+    u_, _, y_, _, T = _traj_inputs(pf, u, y)
+    nothing = lambda *a: None  # noqa: E731
+    pre_correct_cb, post_correct_cb = pre_correct_cb or nothing, post_correct_cb or nothing
+    pre_predict_cb, post_predict_cb = pre_predict_cb or nothing, post_predict_cb or nothing
+    reset(pf, epoch)
+    N = pf.N
+    x = np.zeros((T, N, pf.nx)) if history else None
+    w = np.zeros((T, N)) if history else None
+    we = np.zeros((T, N)) if history else None
+    ll = 0.0
+    lls, res = np.zeros(T), np.zeros(T, dtype=np.int32)
+    for t in range(T):
+        ti = t * pf.Ts
+        ut = u_[t] if u_ is not None else None
+        pre_correct_cb(pf, ut, y_[t], p, ti)
+        lli = correct(pf, ut, y_[t], None, ti)[0]
+        post_correct_cb(pf, ut, y_[t], p, ti, lli)
+        ll += lli
+        lls[t] = lli
+        if history:
+            x[t], w[t], we[t] = particles(pf), weights(pf), expweights(pf)
+        pre_predict_cb(pf, ut, y_[t], p, ti, lli)
+        res[t] = 1 if shouldresample(pf) else 0
+        predict(pf, ut, None, ti)
+        post_predict_cb(pf, ut, y_[t], p, ti)
+    tt = np.arange(T) * pf.Ts
+    return ParticleFilteringSolution(pf, u_, y_, x, w, we, ll, tt, dict(ll_steps=lls, resampled=res, ess=None, xhat=None))
 
 
 def loglik(pf, u, y, p=None, *, epoch=None, details=False):
@@ -821,8 +875,11 @@ def resample(strategy, we, u01, M=None, j0=None, scan_mode="fast", device=0, ret
             raise ValueError("residual resampling needs M uniforms (only the first M - num are consumed)")
         check(lib, lib.llpf_resample_residual(N, we.ctypes.data_as(dp), u.ctypes.data_as(dp), M,
                                                j.ctypes.data_as(_abi.c_int64_p), b.ctypes.data_as(dp), mode, device))
+    elif strategy is ResampleMetropolis:   # extension: u01 is the integer seed of the counter streams, B = 32 proposals
+        check(lib, lib.llpf_resample_metropolis(N, we.ctypes.data_as(dp), M, 32, int(u01), j.ctypes.data_as(_abi.c_int64_p),
+                                                 device))
     else:
-        raise TypeError("strategy must be ResampleSystematic, ResampleStratified or ResampleResidual")
+        raise TypeError("strategy must be ResampleSystematic, ResampleStratified, ResampleResidual or ResampleMetropolis")
     return (j, b) if return_bins else j
 
 

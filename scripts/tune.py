@@ -32,7 +32,7 @@ if __name__ == "__main__":
             run(20, 300, thr)
         run(10, 300, 0.0)
     elif mode == "residual":
-        for strat in (L.ResampleSystematic, L.ResampleStratified, L.ResampleResidual):
+        for strat in (L.ResampleSystematic, L.ResampleStratified, L.ResampleResidual, L.ResampleMetropolis):
             print(strat.__name__, flush=True)
             for thr in (0.1, 1.0):
                 run(20, 300, thr, resampling_strategy=strat)

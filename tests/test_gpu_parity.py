@@ -974,3 +974,71 @@ def test_sharded_filters_inside_pytest(gpu):
         print(r.stdout[-4000:])
         assert r.returncode == 0, r.stderr[-3000:]
         assert "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_forward_trajectory_callbacks(gpu):
+    """The four callbacks of forward_trajectory (filtering.jl:343,353-362): called in the reference's order with the
+    reference's arguments, and the stepwise loop reproduces the fused single-launch trajectory."""
+    L = gpu
+    s = lg_model(4, 2, 2, seed=0)
+    N, T = 2000, 25
+    u, y = _data(s, T, 4)
+    pf = s.particle_filter(N, seed=6, resample_threshold=0.5)
+    fused = L.forward_trajectory(pf, u, y, epoch=2)
+    log = []
+    sol = L.forward_trajectory(
+        pf, u, y, epoch=2,
+        pre_correct_cb=lambda f, ut, yt, p, t: log.append(("pre_correct", t)),
+        post_correct_cb=lambda f, ut, yt, p, t, ll: log.append(("post_correct", t, ll, L.effective_particles(f))),
+        pre_predict_cb=lambda f, ut, yt, p, t, ll: log.append(("pre_predict", t, ll)),
+        post_predict_cb=lambda f, ut, yt, p, t: log.append(("post_predict", t, L.index(f))))
+    assert [e[0] for e in log[:4]] == ["pre_correct", "post_correct", "pre_predict", "post_predict"] and len(log) == 4 * T
+    assert [e[1] for e in log[::4]] == [float(k) for k in range(T)]
+    assert log[3][2] == 2 and log[-1][2] == T + 1                         # index(pf) after predict!
+    assert abs(sol.ll - fused.ll) <= 1e-12 * abs(fused.ll)
+    assert np.array_equal(sol.extra["resampled"], fused.extra["resampled"])
+    assert np.allclose(sol.x, fused.x, rtol=0, atol=1e-12) and np.allclose(sol.we, fused.we, rtol=1e-10, atol=1e-300)
+    assert np.allclose([e[2] for e in log[1::4]], fused.extra["ll_steps"], rtol=0, atol=1e-10)
+    assert np.allclose([e[3] for e in log[1::4]], fused.extra["ess"], rtol=1e-9)
+    # a callback that intervenes: freezing the particles before every predict! changes the result
+    def freeze(f, ut, yt, p, t, ll):
+        L.set_state(f, np.zeros((N, 4)), L.weights(f), L.index(f))
+    sol2 = L.forward_trajectory(pf, u, y, epoch=2, pre_predict_cb=freeze)
+    assert abs(sol2.ll - fused.ll) > 1e-3
+
+
+def test_metropolis_resampling_extension(gpu):
+    """Metropolis resampling is NOT in the reference (north-star extension): statistical tests only, in the style of
+    test/runtests.jl:108-143 — empirical proportions of the drawn indices match the weights, and a ParticleFilter that
+    uses it estimates the same log-likelihood as the systematic one / the Kalman filter."""
+    L = gpu
+    we = np.array([0.1, 0.5, 0.1, 0.15, 0.15])
+    j = L.resample(L.ResampleMetropolis, we, 12345, M=20000)
+    assert j.min() >= 1 and j.max() <= 5
+    prop = np.bincount(j, minlength=6)[1:] / j.size
+    assert np.all(np.abs(prop - we) < 0.02), prop
+    # a degenerate weight vector: almost every chain ends on the heavy particle
+    w2 = np.full(1000, 1e-6); w2[137] = 1.0
+    j2 = L.resample(L.ResampleMetropolis, w2 / w2.sum(), 7)
+    assert np.mean(j2 == 138) > 0.9
+    s = lg_model(4, 2, 2, seed=0)
+    N, T = 1 << 16, 60
+    u, y = _data(s, T, 2)
+    kf = O.kalman_loglik(s.oracle_model(), u, y)
+    lls = {}
+    for name, strat in (("sys", L.ResampleSystematic), ("met", L.ResampleMetropolis)):
+        vals = []
+        for seed in range(4):
+            pf = s.particle_filter(N, seed=seed, resample_threshold=0.5, resampling_strategy=strat, metropolis_steps=48)
+            r = L.loglik(pf, u, y, epoch=1, details=True)
+            vals.append(r["ll"])
+            assert r["resampled"].sum() > 5
+        lls[name] = np.array(vals)
+    assert abs(lls["met"].mean() - lls["sys"].mean()) < 4 * (lls["sys"].std() + lls["met"].std() + 0.05)
+    assert abs(lls["met"].mean() - kf) < 1.5
+    anc = L.ancestors(pf)                      # state.j of the last Metropolis resample: valid global indices, not sorted
+    assert anc.min() >= 1 and anc.max() <= N
+    # APF and history work with it too
+    pfa = L.AuxiliaryParticleFilter(s.particle_filter(4096, seed=1, resampling_strategy=L.ResampleMetropolis))
+    sol = L.forward_trajectory(pfa, u, y, epoch=1)
+    assert np.isfinite(sol.ll) and np.allclose(sol.we.sum(axis=1), 1.0)
