@@ -3,7 +3,7 @@
 # generic functions.  Every method cites the reference method it shadows.
 module LLPFB200
 
-using LowLevelParticleFilters, StaticArrays, LinearAlgebra
+using LowLevelParticleFilters, StaticArrays, LinearAlgebra, Statistics
 import LowLevelParticleFilters: reset!, predict!, correct!, update!, forward_trajectory, loglik, particles, weights,
     expweights, num_particles, effective_particles, shouldresample, weighted_mean, index, state
 
@@ -22,7 +22,13 @@ struct LLPFConfig
     N::Int64; filter::Int32; resampling::Int32
     resample_threshold::Float64; Ts::Float64; seed::UInt64
     scan_mode::Int32; device::Int32; rank::Int32; world::Int32
-    particle_dtype::Int32; single_block::Int32; metropolis_steps::Int32; _reserved::Int32      # 0 = Float64 particles, 1 = Float32 (nx, ny <= 64, linear-Gaussian)
+    particle_dtype::Int32      # 0 = Float64 particles, 1 = Float32 (nx, ny <= 64, linear-Gaussian)
+    single_block::Int32        # 1: one thread block runs the whole filter (PMMH-sized N; required by llpf_run_batch)
+    metropolis_steps::Int32    # LLPF_RESAMPLE_METROPOLIS: proposals per slot (0 = 32)
+    _reserved::Int32
+end
+struct LLPFHistStats
+    xmean::Ptr{Float64}; xmode::Ptr{Float64}; xcov::Ptr{Float64}; q::Ptr{Float64}; nq::Int32; _pad::Int32; xquantile::Ptr{Float64}
 end
 struct LLPFRunOutputs
     ll_steps::Ptr{Float64}; ess_steps::Ptr{Float64}; resampled::Ptr{Int32}; xhat::Ptr{Float64}
@@ -46,7 +52,9 @@ check(rc) = rc == 0 ? nothing : error("llpf status $rc: " * unsafe_string(ccall(
 mutable struct GPUParticleFilter{M} <: LowLevelParticleFilters.AbstractParticleFilter
     h::Ptr{Cvoid}
     model::M
-    N::Int; nx::Int; nu::Int; ny::Int
+    N::Int                           # LOCAL particle count (accessor arrays have this length)
+    N_global::Int                    # global particle count (history buffers of the trajectory drivers are indexed globally)
+    nx::Int; nu::Int; ny::Int
     Ts::Float64; resample_threshold::Float64
     kind::Int32                      # 0 PF, 1 Advanced, 2 Aux, 3 Aux{Advanced}
     epoch::UInt64
@@ -64,15 +72,51 @@ end
 
 "ParticleFilter(N, ...)  src/PFtypes.jl:65-75 (kind=0) / AdvancedParticleFilter :200-210 (kind=1) / AuxiliaryParticleFilter :38-49 (kind=2)"
 function GPUParticleFilter(N::Integer, m; kind=0, resample_threshold=(kind == 1 ? 0.5 : 0.1), Ts=1.0, seed=0,
-                           resampling=0, scan_mode=0, device=0, rank=0, world=1, particle_eltype=Float64)
+                           resampling=0, scan_mode=0, device=0, rank=0, world=1, particle_eltype=Float64,
+                           single_block=false, metropolis_steps=0)
     mdl, nx, nu, ny = c_model(m)
     cfg = LLPFConfig(N, kind, resampling, resample_threshold, Ts, seed, scan_mode, device, rank, world,
-                     particle_eltype === Float32 ? 1 : 0, 0)
+                     particle_eltype === Float32 ? 1 : 0, single_block ? 1 : 0, metropolis_steps, 0)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve m check(ccall((:llpf_create, lib), Cint, (Ref{LLPFConfig}, Ref{LLPFModel}, Ref{Ptr{Cvoid}}), cfg, mdl, h))
-    pf = GPUParticleFilter(h[], m, Int(N) ÷ world, nx, nu, ny, Float64(Ts), Float64(resample_threshold), Int32(kind), UInt64(0))
+    pf = GPUParticleFilter(h[], m, Int(N) ÷ world, Int(N), nx, nu, ny, Float64(Ts), Float64(resample_threshold), Int32(kind), UInt64(0))
     finalizer(p -> ccall((:llpf_destroy, lib), Cint, (Ptr{Cvoid},), p.h), pf)
 end
+
+# ---- the reference's constructors, overloaded for descriptor-typed arguments (SURVEY §7.2) -----------------------------
+# ParticleFilter(N, dynamics, measurement, df, dg, d0; kw...) src/PFtypes.jl:65-75 requires `measurement::Function`; with the
+# descriptor types below the same call builds the GPU filter instead.  Densities: anything with `cov` / `mean`.
+struct LinearDynamics; A::Matrix{Float64}; B::Matrix{Float64}; end          # dynamics(x,u,p,t) = A*x .+ B*u
+struct LinearMeasurement; C::Matrix{Float64}; end                           # measurement(x,u,p,t) = C*x
+_cov(d) = Matrix{Float64}(cov(d)); _mean(d) = Vector{Float64}(mean(d))
+function LowLevelParticleFilters.ParticleFilter(N::Integer, dyn::LinearDynamics, meas::LinearMeasurement, df, dg, d0;
+                                                resample_threshold=0.1, Ts=1.0, seed=0, kwargs...)
+    GPUParticleFilter(N, LGModel(dyn.A, dyn.B, meas.C, _cov(df), _cov(dg), _mean(d0), _cov(d0)); kind=0, resample_threshold, Ts, seed, kwargs...)
+end
+LowLevelParticleFilters.AuxiliaryParticleFilter(N::Integer, dyn::LinearDynamics, meas::LinearMeasurement, df, dg, d0; kw...) =
+    GPUParticleFilter(N, LGModel(dyn.A, dyn.B, meas.C, _cov(df), _cov(dg), _mean(d0), _cov(d0)); kind=2, kw...)
+
+# ---- user-defined models: dynamics / measurement_likelihood as CUDA device source (llpf_create_user) ---------------------
+"""
+    GPUParticleFilter(N, cuda_source::String, p::Vector{Float64}; nx, nu, ny, R1, mu0, Sigma0, kind=1, kw...)
+`cuda_source` defines `llpf_user::dynamics<nx>` and `llpf_user::loglik<nx>` (include/llpf.h): the reference's closures
+`dynamics(x,u,p,t)` / `measurement_likelihood(x,u,y,p,t)` (src/PFtypes.jl:232,255), compiled at run time into the sweep.
+"""
+function GPUParticleFilter(N::Integer, cuda_source::String, p::Vector{Float64}; nx, nu, ny, R1, mu0, Sigma0, kind=1,
+                           resample_threshold=0.5, Ts=1.0, seed=0, resampling=0, scan_mode=0, device=0)
+    R1m, mu, S0 = Matrix{Float64}(R1), Vector{Float64}(mu0), Matrix{Float64}(Sigma0)
+    mdl = LLPFModel(nx, nu, ny, 2, C_NULL, C_NULL, C_NULL, pointer(R1m), C_NULL, pointer(mu), pointer(S0), ntuple(_ -> 0.0, 8),
+                    Inf, 1.0, 1.0, 1, 0)
+    cfg = LLPFConfig(N, kind, resampling, resample_threshold, Ts, seed, scan_mode, device, 0, 1, 0, 0, 0, 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve R1m mu S0 p check(ccall((:llpf_create_user, lib), Cint,
+        (Ref{LLPFConfig}, Ref{LLPFModel}, Cstring, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}), cfg, mdl, cuda_source, p, length(p), h))
+    pf = GPUParticleFilter(h[], (cuda_source, p), Int(N), Int(N), nx, nu, ny, Float64(Ts), Float64(resample_threshold), Int32(kind), UInt64(0))
+    finalizer(f -> ccall((:llpf_destroy, lib), Cint, (Ptr{Cvoid},), f.h), pf)
+end
+"per-call parameter override `p` (src/filtering.jl:140,164) of a user-defined model"
+set_params!(pf::GPUParticleFilter, p::Vector{Float64}) =
+    check(ccall((:llpf_set_user_params, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32), pf.h, p, length(p)))
 
 # ---- verbs -------------------------------------------------------------------------------------------------
 "reset!(pf)  src/filtering.jl:4-14"
@@ -88,7 +132,8 @@ vecf(v) = collect(Float64, v)
 "correct!(pf,u,y,p,t) -> (ll,0)  src/filtering.jl:164-174"
 function correct!(pf::GPUParticleFilter, u, y, p=nothing, t=index(pf) * pf.Ts)
     ll = Ref{Float64}(0.0)
-    check(ccall((:llpf_correct, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}), pf.h, vecf(u), vecf(y), t, ll))
+    uv, yv = vecf(u), vecf(y)     # passed as Ptr{Float64}: ccall roots array arguments for the duration of the call
+    check(ccall((:llpf_correct, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}), pf.h, uv, yv, t, ll))
     ll[], 0
 end
 "predict!(pf,u,p,t)  src/filtering.jl:140-153"
@@ -97,15 +142,24 @@ predict!(pf::GPUParticleFilter, u, p=nothing, t=index(pf) * pf.Ts) =
 "predict!(pfa,u,y1,p,t)  src/filtering.jl:195-234"
 predict!(pf::GPUParticleFilter, u, y1, p, t) =
     check(ccall((:llpf_predict_aux, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), pf.h, vecf(u), vecf(y1), t))
-"update!(f,u,y,p,t) src/filtering.jl:181-185 ; update!(pfa,u,y,y1,p,t) :187-191"
-function update!(pf::GPUParticleFilter, u, y, p=nothing, t=index(pf) * pf.Ts; y1=nothing)
+"update!(f,u,y,p,t)  src/filtering.jl:181-185"
+function update!(pf::GPUParticleFilter, u, y, p=nothing, t::Real=index(pf) * pf.Ts)
     ll = Ref{Float64}(0.0)
-    y1p = y1 === nothing ? Ptr{Float64}(C_NULL) : pointer(vecf(y1))
-    check(ccall((:llpf_update, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}),
-                pf.h, vecf(u), vecf(y), y1p, t, ll))
+    uv, yv = vecf(u), vecf(y)
+    GC.@preserve uv yv check(ccall((:llpf_update, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}), pf.h, uv, yv, C_NULL, t, ll))
     ll[], 0
 end
-(pf::GPUParticleFilter)(u, y, p=nothing, t=index(pf) * pf.Ts) = update!(pf, u, y, p, t)     # src/filtering.jl:238
+"update!(pfa,u,y,y1,p,t)  src/filtering.jl:187-191 (y1 positional, like the reference)"
+function update!(pf::GPUParticleFilter, u, y, y1::AbstractVector, p, t::Real=index(pf) * pf.Ts)
+    ll = Ref{Float64}(0.0)
+    uv, yv, y1v = vecf(u), vecf(y), vecf(y1)
+    GC.@preserve uv yv y1v check(ccall((:llpf_update, lib), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}), pf.h, uv, yv, y1v, t, ll))
+    ll[], 0
+end
+(pf::GPUParticleFilter)(u, y, p=nothing, t=index(pf) * pf.Ts) = update!(pf, u, y, p, t)                 # src/filtering.jl:238
+(pf::GPUParticleFilter)(u, y, y1::AbstractVector, p, t=index(pf) * pf.Ts) = update!(pf, u, y, y1, p, t)  # :239
 
 flat(v::AbstractVector) = reduce(hcat, v)          # n x T column-major == the memory of Vector{SVector{n}}
 
@@ -118,7 +172,8 @@ function loglik(pf::GPUParticleFilter, u::AbstractVector, y::AbstractVector, p=n
 end
 "forward_trajectory(pf,u,y,p) -> ParticleFilteringSolution  src/filtering.jl:343-384, src/solutions.jl:334-345"
 function forward_trajectory(pf::GPUParticleFilter, u::AbstractVector, y::AbstractVector, p=nothing)
-    U, Y = flat(u), flat(y); T = length(y); N = pf.N
+    U, Y = flat(u), flat(y); T = length(y)
+    N = pf.N_global      # the device history is indexed by GLOBAL particle number; a sharded rank fills its own rows
     x = Matrix{SVector{pf.nx,Float64}}(undef, N, T); w = Matrix{Float64}(undef, N, T); we = similar(w)
     out = LLPFRunOutputs(C_NULL, C_NULL, C_NULL, C_NULL, pointer(reinterpret(Float64, x)), pointer(w), pointer(we))
     ll = Ref{Float64}(0.0); pf.epoch += 1
@@ -137,6 +192,36 @@ function LowLevelParticleFilters.smooth(pf::GPUParticleFilter, M::Integer, u::Ab
         (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, UInt64, Ref{Float64}, Ptr{Float64}, Ptr{Cvoid}),
         pf.h, T, U, Y, M, pf.epoch, ll, pointer(reinterpret(Float64, xb)), C_NULL))
     xb, ll[]
+end
+
+"""
+    lls = loglik_batch(pfs::Vector{<:GPUParticleFilter}, u, y)
+[loglik(pf, u, y) for pf in pfs] in ONE kernel launch (llpf_run_batch; filters created with single_block=true): what
+`metropolis_threaded` (src/smoothing.jl:335-347) needs per MCMC iteration.
+"""
+function loglik_batch(pfs::Vector{<:GPUParticleFilter}, u::AbstractVector, y::AbstractVector)
+    U, Y = flat(u), flat(y); hs = [pf.h for pf in pfs]
+    epochs = UInt64[(pf.epoch += 1) for pf in pfs]; lls = zeros(length(pfs))
+    GC.@preserve U Y hs epochs lls check(ccall((:llpf_run_batch, lib), Cint,
+        (Int32, Ptr{Ptr{Cvoid}}, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{UInt64}, Ptr{Float64}),
+        length(pfs), hs, length(y), U, Y, 1, epochs, lls))
+    lls
+end
+
+"""
+    ll, xmean, xmode, xcov, xq = trajectory_statistics(pf, u, y; q=Float64[])
+forward_trajectory reduced on the device to mean_trajectory / mode_trajectory / weighted_cov / weighted_quantile
+(src/filtering.jl:417-440, 575-595) — the N x T history never leaves HBM (llpf_run_stats).
+"""
+function trajectory_statistics(pf::GPUParticleFilter, u::AbstractVector, y::AbstractVector; q::Vector{Float64}=Float64[])
+    U, Y = flat(u), flat(y); T = length(y); nx = pf.nx
+    xmean = zeros(nx, T); xmode = zeros(nx, T); xcov = zeros(nx, nx, T); xq = zeros(nx, length(q), T)
+    st = LLPFHistStats(pointer(xmean), pointer(xmode), pointer(xcov), pointer(q), length(q), 0, pointer(xq))
+    ll = Ref{Float64}(0.0); pf.epoch += 1
+    GC.@preserve U Y xmean xmode xcov xq q check(ccall((:llpf_run_stats, lib), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, UInt64, Ref{Float64}, Ptr{Cvoid}, Ref{LLPFHistStats}),
+        pf.h, T, U, Y, pf.epoch, ll, C_NULL, st))
+    ll[], xmean, xmode, xcov, xq
 end
 
 # ---- accessors (src/PFtypes.jl:296-334, src/resample.jl:1-10, src/filtering.jl:541-568) --------------------

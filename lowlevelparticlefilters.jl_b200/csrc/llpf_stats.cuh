@@ -197,7 +197,7 @@ k_hist_quantile(const double* __restrict__ xh, const double* __restrict__ weh, l
       result = __longlong_as_double(0x7ff8000000000000ll);       // all weights zero: NaN
     } else if (p == 0.0 || TOT == 0) {
       result = key_f64(KMIN);                                    // h = w_1: v_1 + 0 * (v_2 - v_1)
-    } else if (ht >= TOT) {
+    } else if (p == 1.0 || ht >= TOT) {
       result = key_f64(KMAX);                                    // S_k <= h for every k: v[end]
     } else {
       // ---- radix select: smallest key K with S(<= K) > ht ----

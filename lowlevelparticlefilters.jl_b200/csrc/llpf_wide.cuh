@@ -38,11 +38,15 @@ struct WideP {
   int diagL;              // L is diagonal: x' += diag(L) z (bit-identical to the general loop: the other terms are +0)
 };
 
-// dynamic shared memory of the wide kernel
+// dynamic shared memory of the wide kernel (v2: block-tiled).  The three matrices are stored column by column with every
+// element DUPLICATED into a packed f32x2 pair (a, a): the tile GEMMs pair two particles per FFMA2, so the matrix operand is
+// the same scalar in both halves and comes straight out of a 16-byte shared load (no register shuffling).
+constexpr int WTP = BLOCK;     // particles per tile (one per thread in the load / store / reduce phases)
 struct WideShared {
-  alignas(16) float As[WNX * WNX];
-  alignas(16) float Gs[WNX * WNX];
-  alignas(16) float Ls[WNX * WNX];
+  alignas(16) u64 Ad[WNX * WNX];      // Ad[c*64 + r] = (A[r,c], A[r,c])
+  alignas(16) u64 Gd[WNX * WNX];      // Gd[c*64 + a] = (G[a,c], G[a,c])      (rows a >= ny are zero)
+  alignas(16) u64 Ld[WNX * WNX];      // Ld[c*64 + r] = (L[r,c], L[r,c])      (lower Cholesky factor of R1; zero above the diagonal)
+  alignas(16) float XT[WNX * WTP];    // tile buffer, component-major: XT[c*WTP + p]; x, then z (general L), x', v in turn
   alignas(16) float bu[WNX];
   alignas(16) float yt[WNX];
   alignas(16) float ldiag[WNX];
@@ -77,18 +81,6 @@ __device__ __forceinline__ void stg256(float* p, const float (&v)[8]) {
   asm volatile("st.global.cg.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(p)
                : "memory");
-}
-
-// acc[0..63] += column c of a column-major 64x64 matrix in shared memory, times v:  32 FFMA2 + 16 LDS.128
-__device__ __forceinline__ void axpy_col64(u64 (&acc)[WNX / 2], const float* col, float v) {
-  const u64 vv = pack2(v, v);
-#pragma unroll
-  for (int r4 = 0; r4 < WNX / 4; ++r4) {
-    u64 a01, a23;
-    lds_2x64(col + 4 * r4, a01, a23);
-    acc[2 * r4] = ffma2(a01, vv, acc[2 * r4]);
-    acc[2 * r4 + 1] = ffma2(a23, vv, acc[2 * r4 + 1]);
-  }
 }
 
 // where particle `a` (GLOBAL index) lives: buffer buf_id of the owning rank (peer memory when sharded)
@@ -129,6 +121,46 @@ __device__ __forceinline__ void wide_stage_step(const EngineP& P, const WideP& M
 }
 
 // ---- PF pass for wide models: [predict!(k_prop)] fused with [correct!(k_weigh)]  (cf. pf_pass) ------------
+// v2, block-tiled.  v1 gave every thread one particle and its 64 accumulators and streamed all three matrices from shared
+// memory for every particle: 16 LDS.128 per 32 FFMA2 — shared-memory bound at 27-29 % of the FP32 peak (profiles/
+// r1_v9_ncu_wide.md).  v2 processes a tile of 256 particles per block iteration as two 64 x 64 x 256 GEMMs:
+//   thread (warp w, lane l) owns rows 8w..8w+7 of particles {4l..4l+3} and {128+4l..128+4l+3}: 64 accumulators as 32 packed
+//   f32x2 pairs (two particles per pair); per column c it loads 8 duplicated matrix elements (4 broadcast LDS.128) and
+//   8 particle values (2 conflict-free LDS.128) for 32 FFMA2: 6 LDS.128 instead of 16 per 32 FFMA2.
+// Every accumulator still sees exactly the fmaf chain documented at the top of this file (c ascending from 0, then + Bu,
+// then the noise chain; even / odd column chains for G x'), so the results are bit-identical to v1 and to the oracle.
+// Tile phases (one __syncthreads between them): gather x -> XT | GEMM1 A x (+Bu, +L z) , store x' | x' -> XT | GEMM2 G x',
+// v = yt - d | v -> XT | per particle: q = sum v^2 (fmaf chain over a), w += c0 - q/2, online reduction.
+__device__ __forceinline__ void lds_4x64(const u64* p, u64 (&v)[8]) {   // 8 consecutive u64 (64 B, 16-byte aligned)
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(addr));
+  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[2]), "=l"(v[3]) : "r"(addr + 16));
+  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[4]), "=l"(v[5]) : "r"(addr + 32));
+  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[6]), "=l"(v[7]) : "r"(addr + 48));
+}
+__device__ __forceinline__ void lds_f4_as_pairs(const float* p, u64& a, u64& b) {   // 4 consecutive floats as 2 f32x2 pairs
+  lds_2x64(p, a, b);
+}
+
+// acc[r][q] += M[8w + r, c] * t[c][particle pair q]   for c = c0, c0 + cs, ... < 64 ; q: pairs 0,1 = particles 4l..4l+3,
+// pairs 2,3 = particles 128+4l..128+4l+3 (HALF selects pairs 0..1, 2..3 or all four)
+template <int HALF>
+__device__ __forceinline__ void tile_gemm(u64 (&acc)[8][4], const u64* Md, const float* XT, int w, int l, int c0, int cs) {
+#pragma unroll 2
+  for (int c = c0; c < WNX; c += cs) {
+    u64 m[8];
+    lds_4x64(Md + c * WNX + 8 * w, m);
+    u64 x[4];
+    if (HALF != 1) lds_f4_as_pairs(XT + c * WTP + 4 * l, x[0], x[1]);
+    if (HALF != 0) lds_f4_as_pairs(XT + c * WTP + 128 + 4 * l, x[2], x[3]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (HALF != 1) { acc[r][0] = ffma2(m[r], x[0], acc[r][0]); acc[r][1] = ffma2(m[r], x[1], acc[r][1]); }
+      if (HALF != 0) { acc[r][2] = ffma2(m[r], x[2], acc[r][2]); acc[r][3] = ffma2(m[r], x[3], acc[r][3]); }
+    }
+  }
+}
+
 __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, Shared& sh, WideShared& ws,
                                              Scalars& sc, Ctx& cx, int k_prop, int k_weigh, int flags) {
   if (flags & OPF_RAW_WEIGHTS) { sc.pend = 0; sc.stats_ahead = 0; }
@@ -163,131 +195,185 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
   const int cur = sc.cur;
   float* dst = reinterpret_cast<float*>(res ? P.x[cur ^ 1] : P.x[cur]);
   const int jid = sc.j_identity;
-  const int ny4 = (Mw.ny + 3) & ~3;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool prop = k_prop > 0, weigh = k_weigh > 0;
   Online<1> acc1;
   acc1.init();
   const double dummy[1] = {0.0};
-  for (int i = cx.beg + threadIdx.x; i < cx.end; i += BLOCK) {
+  for (int tb = cx.beg; tb < cx.end; tb += WTP) {   // block-uniform trip count
+    // ---- phase 0: this thread's particle of the tile: ancestor, old weight, row -> XT[:, p] ----
+    const int i = tb + threadIdx.x;
+    const bool valid = i < cx.end;
     const int gi = P.first + i;
-    // ancestor (resample.jl:26-34: slots past the last threshold keep state.j)
-    int a = gi;
-    if (res) {
-      a = __ldcg(P.j + i);
-      if (gi >= f_total) {
-        if (jid) a = gi;
-        __stcg(P.j + i, a);
+    double wraw = 0.0;
+    __syncthreads();                               // the previous tile's readers of XT are done
+    {
+      float xv[8];
+      const float* xin = nullptr;
+      if (valid && (prop || weigh)) {
+        int a = gi;
+        if (res) {   // ancestor (resample.jl:26-34: slots past the last threshold keep state.j)
+          a = __ldcg(P.j + i);
+          if (gi >= f_total) {
+            if (jid) a = gi;
+            __stcg(P.j + i, a);
+          }
+        }
+        if (!res && !wst.uniform) wraw = __ldcg(P.w + i);
+        if (P.world > 1 && a < 0) {   // an ancestor another rank shipped here as a packed entry (expand_packs)
+          const char* e = P.pack_in + (size_t)(-1 - a) * (size_t)P.pack_stride;
+          xin = reinterpret_cast<const float*>(e);
+          __stcg(P.j + i, __ldcg(reinterpret_cast<const int*>(e + P.pack_state_bytes)));   // state.j keeps global ids
+        } else {
+          xin = wide_row(P, cur, prop ? a : gi);
+        }
+      }
+#pragma unroll
+      for (int c8 = 0; c8 < WNX / 8; ++c8) {
+        if (xin) ldg256(xin + 8 * c8, xv);
+        else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) xv[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ws.XT[(8 * c8 + k) * WTP + threadIdx.x] = xv[k];
       }
     }
-    double wraw = 0.0;
-    if (!res && !wst.uniform) wraw = __ldcg(P.w + i);
-    u64 acc[WNX / 2];
-    if (k_prop > 0) {
-      const float* xin;
-      if (P.world > 1 && a < 0) {   // an ancestor another rank shipped here as a packed entry (expand_packs)
-        const char* e = P.pack_in + (size_t)(-1 - a) * (size_t)P.pack_stride;
-        xin = reinterpret_cast<const float*>(e);
-        __stcg(P.j + i, __ldcg(reinterpret_cast<const int*>(e + P.pack_state_bytes)));   // state.j keeps global ids
-      } else {
-        xin = wide_row(P, cur, a);
-      }
+    __syncthreads();
+    if (prop) {
+      // ---- phase 1: x' = A x (+ B u) (+ L z), rows 8w..8w+7 of 8 particles ----
+      u64 acc[8][4];
 #pragma unroll
-      for (int k = 0; k < WNX / 2; ++k) acc[k] = 0ull;
-      // x' = A x : column form, x streamed 8 values (one 32-byte sector) at a time
-#pragma unroll 1
-      for (int c8 = 0; c8 < WNX / 8; ++c8) {
-        float xv[8];
-        ldg256(xin + 8 * c8, xv);
+      for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) axpy_col64(acc, ws.As + (8 * c8 + k) * WNX, xv[k]);
-      }
-      // + B u
+        for (int q = 0; q < 4; ++q) acc[r][q] = 0ull;
+      tile_gemm<2>(acc, ws.Ad, ws.XT, w, l, 0, 1);
 #pragma unroll
-      for (int r4 = 0; r4 < WNX / 4; ++r4) {
-        u64 b01, b23;
-        lds_2x64(ws.bu + 4 * r4, b01, b23);
-        acc[2 * r4] = fadd2(acc[2 * r4], b01);
-        acc[2 * r4 + 1] = fadd2(acc[2 * r4 + 1], b23);
+      for (int r = 0; r < 8; ++r) {   // + B u
+        const float b = ws.bu[8 * w + r];
+        const u64 bb = pack2(b, b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[r][q] = fadd2(acc[r][q], bb);
       }
-      // + L z : 16 Philox blocks of 4 normals (f64 Box-Muller, rounded to f32)
+      // noise: 2 Philox blocks (rows 8w..8w+3, 8w+4..8w+7) per particle, f64 Box-Muller rounded to f32 — the same
+      // counters as v1: block b of particle gi holds the normals of rows 4b..4b+3
       if (Mw.diagL) {
-#pragma unroll 1
-        for (int b = 0; b < WNX / 4; ++b) {
-          const uint4 r = rng_block(P.key, ST_DYN, step_idx, (unsigned long long)(unsigned)gi, (uint32_t)b);
-          const uint32_t ra[2] = {r.x, r.z}, rb[2] = {r.y, r.w};
-          double a0[2], a1[2];
-          normal_pairs<2>(ra, rb, a0, a1, sh.mt);
-          u64 l01, l23;
-          lds_2x64(ws.ldiag + 4 * b, l01, l23);
-          const u64 z01 = pack2((float)a0[0], (float)a1[0]), z23 = pack2((float)a0[1], (float)a1[1]);
-          // acc[2b], acc[2b+1] with a runtime index would force the array into local memory: select statically
 #pragma unroll
-          for (int q = 0; q < WNX / 4; ++q) {
-            if (q == b) {
-              acc[2 * q] = ffma2(l01, z01, acc[2 * q]);
-              acc[2 * q + 1] = ffma2(l23, z23, acc[2 * q + 1]);
+        for (int q = 0; q < 4; ++q) {
+          float z[2][8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int pg = P.first + tb + ((q < 2) ? 0 : 128) + 4 * l + 2 * (q & 1) + h;
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              const uint4 rr = rng_block(P.key, ST_DYN, step_idx, (unsigned long long)(unsigned)pg, (uint32_t)(2 * w + bb));
+              const uint32_t ra[2] = {rr.x, rr.z}, rb[2] = {rr.y, rr.w};
+              double a0[2], a1[2];
+              normal_pairs<2>(ra, rb, a0, a1, sh.mt);
+              z[h][4 * bb] = (float)a0[0]; z[h][4 * bb + 1] = (float)a1[0];
+              z[h][4 * bb + 2] = (float)a0[1]; z[h][4 * bb + 3] = (float)a1[1];
             }
+          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float ld = ws.ldiag[8 * w + r];
+            acc[r][q] = ffma2(pack2(ld, ld), pack2(z[0][r], z[1][r]), acc[r][q]);
           }
         }
       } else {
+        // general L: z tile through XT (thread p generates all 64 normals of its particle), then the chain
+        // acc_r = fmaf(L[r,c], z[c], acc_r) over c ascending (L is zero above the diagonal: those terms add +0 exactly)
+        __syncthreads();                           // GEMM1 readers of XT are done
 #pragma unroll 1
         for (int b = 0; b < WNX / 4; ++b) {
-          const uint4 r = rng_block(P.key, ST_DYN, step_idx, (unsigned long long)(unsigned)gi, (uint32_t)b);
-          const uint32_t ra[2] = {r.x, r.z}, rb[2] = {r.y, r.w};
+          const uint4 rr = rng_block(P.key, ST_DYN, step_idx, (unsigned long long)(unsigned)gi, (uint32_t)b);
+          const uint32_t ra[2] = {rr.x, rr.z}, rb[2] = {rr.y, rr.w};
           double a0[2], a1[2];
           normal_pairs<2>(ra, rb, a0, a1, sh.mt);
-          const float z[4] = {(float)a0[0], (float)a1[0], (float)a0[1], (float)a1[1]};
+          ws.XT[(4 * b) * WTP + threadIdx.x] = (float)a0[0];
+          ws.XT[(4 * b + 1) * WTP + threadIdx.x] = (float)a1[0];
+          ws.XT[(4 * b + 2) * WTP + threadIdx.x] = (float)a0[1];
+          ws.XT[(4 * b + 3) * WTP + threadIdx.x] = (float)a1[1];
+        }
+        __syncthreads();
+        tile_gemm<2>(acc, ws.Ld, ws.XT, w, l, 0, 1);
+      }
+      // store x' (rows 8w..8w+7 = one 32-byte sector per particle) and hand the tile to phase 2 through XT
 #pragma unroll
-          for (int k = 0; k < 4; ++k) axpy_col64(acc, ws.Ls + (4 * b + k) * WNX, z[k]);
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pl = ((q < 2) ? 0 : 128) + 4 * l + 2 * (q & 1) + h;
+          const int ip = tb + pl;
+          if (ip < cx.end) {
+            float o[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) o[r] = h ? hi_f(acc[r][q]) : lo_f(acc[r][q]);
+            stg256(dst + (size_t)ip * WNX + 8 * w, o);
+          }
         }
       }
-      float* xo = dst + (size_t)i * WNX;
+      if (weigh) {
+        __syncthreads();                           // readers of XT (x or z) are done
 #pragma unroll
-      for (int c8 = 0; c8 < WNX / 8; ++c8) {
-        const float o[8] = {lo_f(acc[4 * c8]),     hi_f(acc[4 * c8]),     lo_f(acc[4 * c8 + 1]), hi_f(acc[4 * c8 + 1]),
-                            lo_f(acc[4 * c8 + 2]), hi_f(acc[4 * c8 + 2]), lo_f(acc[4 * c8 + 3]), hi_f(acc[4 * c8 + 3])};
-        stg256(xo + 8 * c8, o);
-      }
-    } else if (k_weigh > 0) {
-      // correct! only: the particle as it is
-      const float* xin = wide_row(P, cur, gi);
-#pragma unroll
-      for (int c8 = 0; c8 < WNX / 8; ++c8) {
-        float xv[8];
-        ldg256(xin + 8 * c8, xv);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[4 * c8 + k] = pack2(xv[2 * k], xv[2 * k + 1]);
+        for (int r = 0; r < 8; ++r) {
+          float* row = ws.XT + (8 * w + r) * WTP;
+          const unsigned a0 = (unsigned)__cvta_generic_to_shared(row + 4 * l);
+          const unsigned a1 = (unsigned)__cvta_generic_to_shared(row + 128 + 4 * l);
+          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a0), "l"(acc[r][0]), "l"(acc[r][1]) : "memory");
+          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a1), "l"(acc[r][2]), "l"(acc[r][3]) : "memory");
+        }
+        __syncthreads();
       }
     }
     double wv;
     if (res) wv = cx.lw1N;                    // reset_weights!  utils.jl:75
     else wv = wst.uniform ? wst.wu : (wst.pend ? (wraw - wst.pm) - wst.pls : wraw);
-    if (k_weigh > 0) {
+    if (weigh) {
       if (!skip) {
-        // loglik = c0 - |yt - G x'|^2 / 2 ; four rows of G at a time, each row two fmaf chains (even / odd columns)
-        float q = 0.f;
-#pragma unroll 1
-        for (int a0 = 0; a0 < ny4; a0 += 4) {
-          u64 d[4] = {0ull, 0ull, 0ull, 0ull};
+        // ---- phase 2: d_a = (even-column chain) + (odd-column chain) of G[a,:] x' ; v_a = yt_a - d_a ----
+        float v[8][8];
 #pragma unroll
-          for (int c4 = 0; c4 < WNX / 4; ++c4) {
+        for (int half = 0; half < 2; ++half) {
+          u64 de[8][4], dd[8][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              u64 g01, g23;
-              lds_2x64(ws.Gs + (a0 + k) * WNX + 4 * c4, g01, g23);
-              d[k] = ffma2(g01, acc[2 * c4], d[k]);
-              d[k] = ffma2(g23, acc[2 * c4 + 1], d[k]);
+          for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { de[r][q] = 0ull; dd[r][q] = 0ull; }
+          if (half == 0) { tile_gemm<0>(de, ws.Gd, ws.XT, w, l, 0, 2); tile_gemm<0>(dd, ws.Gd, ws.XT, w, l, 1, 2); }
+          else { tile_gemm<1>(de, ws.Gd, ws.XT, w, l, 0, 2); tile_gemm<1>(dd, ws.Gd, ws.XT, w, l, 1, 2); }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float y = ws.yt[8 * w + r];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const u64 e = de[r][2 * half + q], o = dd[r][2 * half + q];
+              v[r][4 * half + 2 * q] = y - (lo_f(e) + lo_f(o));
+              v[r][4 * half + 2 * q + 1] = y - (hi_f(e) + hi_f(o));
             }
           }
+        }
+        __syncthreads();                           // GEMM2 readers of XT are done
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float v = ws.yt[a0 + k] - (lo_f(d[k]) + hi_f(d[k]));
-            q = fmaf(v, v, q);
-          }
+        for (int r = 0; r < 8; ++r) {
+          float* row = ws.XT + (8 * w + r) * WTP;
+          *reinterpret_cast<float4*>(row + 4 * l) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          *reinterpret_cast<float4*>(row + 128 + 4 * l) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+        }
+        __syncthreads();
+        // ---- phase 3: loglik = c0 - q/2, q = fmaf(v_a, v_a, q) for a ascending (rows a >= ny: v = 0, no-op) ----
+        float q = 0.f;
+#pragma unroll 8
+        for (int a = 0; a < WNX; ++a) {
+          const float va = ws.XT[a * WTP + threadIdx.x];
+          q = fmaf(va, va, q);
         }
         wv += (double)fmaf(-0.5f, q, Mw.c0);
       }
-      __stcg(P.w + i, wv);
-      acc1.add(wv, dummy, false, sh.mt);
+      if (valid) {
+        __stcg(P.w + i, wv);
+        acc1.add(wv, dummy, false, sh.mt);
+      }
     }
   }
   if (k_prop > 0) {
@@ -301,7 +387,7 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
       sc.j_identity = 1;   // s.j .= 1:N  filtering.jl:148
     }
     sc.last_resampled = res ? 1 : 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k_prop - 1] = res ? 1 : 0;
+    if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0 && P.resampled) P.resampled[k_prop - 1] = res ? 1 : 0;
     sc.t_index += 1;       // filtering.jl:152
   }
   if (k_weigh > 0) {
@@ -317,9 +403,11 @@ k_engine_wide(const __grid_constant__ EngineP P, const __grid_constant__ WideP M
   WideShared& ws = *reinterpret_cast<WideShared*>(llpf_wide_smem);
   math_tab_load(sh.mt);
   for (int k = threadIdx.x; k < WNX * WNX; k += BLOCK) {
-    ws.As[k] = Mw.At[k];
-    ws.Gs[k] = Mw.G[k];
-    ws.Ls[k] = Mw.Lt[k];
+    const int c = k / WNX, r = k % WNX;
+    const float a = Mw.At[k], lv = Mw.Lt[k], g = Mw.G[r * WNX + c];   // At, Lt column-major; G row-major
+    ws.Ad[k] = pack2(a, a);
+    ws.Ld[k] = pack2(lv, lv);
+    ws.Gd[k] = pack2(g, g);
   }
   if (threadIdx.x < WNX) {
     ws.ldiag[threadIdx.x] = Mw.Lt[threadIdx.x * WNX + threadIdx.x];
