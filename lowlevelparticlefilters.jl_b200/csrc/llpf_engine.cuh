@@ -794,6 +794,10 @@ struct Thresholds {
   int twice;               // 1: elements are the double-double TwicePrecision getindex below
   int offset;              // 1-based index of the reference element
   double ref_lo, step_lo;
+  // integer thresholds (FAST scan, systematic, power-of-two M, 2^62 scale): s_i = r + i/M exactly, in 2^-62 fixed point
+  int ipath;               // 1: F(V) = ceil((V - Rf) / 2^ish) on the fixed-point prefix V itself
+  int ish;                 // 62 - log2(M)
+  u64 Rf;                  // floor(r * 2^62)
 };
 
 // the Float64 range of resample.jl:24 as the host resolved it (llpf_julia_range.h): nullptr / rational == 0 -> literal path
@@ -847,7 +851,25 @@ __device__ __forceinline__ Thresholds make_thresholds(const EngineP& P, double t
   // r = rand()*bins[end]/N   (resample.jl:23; note /N, N = length(we))
   th.r = __ddiv_rn(__dmul_rn(u01, total), (double)P.N);
   th.twice = 0; th.offset = 1; th.ref_lo = 0.0; th.step_lo = 0.0;
+  // The fixed-point scan knows every cumulative weight as an exact integer V (units of 2^-62).  For M = 2^k slots the
+  // thresholds r + i/M are exact in the same units up to the fraction of r*2^62, which cannot change an integer
+  // comparison: s_i >= V  <=>  i >= ceil((V - floor(r 2^62)) / 2^(62-k)).  A shift instead of ~25 FP64 / conversion
+  // instructions per evaluation.  It compares against the EXACT r + i/M where the reference rounds the sum to 53 bits:
+  // the two can differ only for a cumulative weight within 2^-53 of a threshold (~1e-4 per resample at N = 2^20, two
+  // orders of magnitude below the FAST scan's own rounding distance to the serial cumsum).
+  th.ipath = 0; th.ish = 0; th.Rf = 0ull;
+  if (P.strategy == 0 && P.scan_mode == 0 && u_slots == nullptr && P.fix_scale == FIX_SCALE && Mslots > 0 &&
+      (Mslots & (Mslots - 1)) == 0) {
+    th.ipath = 1;
+    th.ish = 62 - (31 - __clz(Mslots));
+    th.Rf = __double2ull_rz(th.r * FIX_SCALE);
+  }
   return th;
+}
+__device__ __forceinline__ int first_slot_ge_fixed(const Thresholds& th, u64 V) {
+  if (V <= th.Rf) return 0;
+  const u64 q = (V - th.Rf + ((1ull << th.ish) - 1ull)) >> th.ish;
+  return (int)(q < (u64)th.Mi ? q : (u64)th.Mi);
 }
 __device__ __forceinline__ double resample_u01(const RngKey& key, uint32_t step_idx) {
   const uint4 r = rng_block(key, ST_RESAMPLE, step_idx, 0ull, 0);
@@ -1073,7 +1095,8 @@ __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int 
   // F at every (row, warp) segment start: lane 0 of a segment needs it for its first particle
   __syncthreads();
   for (int q = threadIdx.x; q < rows * NWARP; q += BLOCK)
-    sh.wtf[q] = first_slot_ge(th, P.key, (double)(off + sh.wt[q]) * P.fix_inv);
+    sh.wtf[q] = th.ipath ? first_slot_ge_fixed(th, off + sh.wt[q])
+                         : first_slot_ge(th, P.key, (double)(off + sh.wt[q]) * P.fix_inv);
   __syncthreads();
   ulonglong2 mn = make_ulonglong2(0ull, 0ull);
   {
@@ -1094,11 +1117,11 @@ __device__ __forceinline__ void scatter_pairs(const EngineP& P, Shared& sh, int 
     int fB = 0, fC = 0;
     if (i < end) {
       const double hi0 = (double)(seg + m.x) * P.fix_inv;
-      fB = first_slot_ge(th, P.key, hi0);
+      fB = th.ipath ? first_slot_ge_fixed(th, seg + m.x) : first_slot_ge(th, P.key, hi0);
       fC = fB;
       if (i + 1 < end) {
         const double hi1 = (double)(seg + m.y) * P.fix_inv;
-        fC = (m.y > m.x) ? first_slot_ge(th, P.key, hi1) : fB;
+        if (m.y > m.x) fC = th.ipath ? first_slot_ge_fixed(th, seg + m.y) : first_slot_ge(th, P.key, hi1);
         __stcg(reinterpret_cast<double2*>(P.bins + i), make_double2(hi0, hi1));
       } else {
         __stcg(P.bins + i, hi0);
@@ -1208,7 +1231,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
   LLPF_TS(P, sh, 2);
   double total;
-  u64 off = 0;
+  u64 off = 0, gtot_fixed = 0;
   if (P.scan_mode != 0) {
     if (LLPF_BLOCKIDX == 0 && threadIdx.x == 0) scan_serial(P.bins, P.n);
     grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
@@ -1229,6 +1252,7 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
       }
     }
     total = (double)gtot * P.fix_inv;
+    gtot_fixed = gtot;
     off = gbase + sh.offs[LLPF_BLOCKIDX];
     LLPF_TS(P, sh, 14);
   }
@@ -1236,12 +1260,13 @@ __device__ __forceinline__ int resample_indices(const EngineP& P, Shared& sh, in
   if (gen_u01) u01 = resample_u01(P.key, step_idx);
   Thresholds th = make_thresholds(P, total, u01, Mslots, step_idx, u_slots);
   if (range != nullptr && range->rational) {   // stand-alone entry: the host found Julia's rational range for (r, 1/M, total+r)
+    th.ipath = 0;
     th.twice = 1; th.offset = range->offset;
     th.r = range->ref_hi; th.ref_lo = range->ref_lo; th.step = range->step_hi; th.step_lo = range->step_lo;
   }
   if (pairs) {
     scatter_pairs<JT>(P, sh, beg, end, off, th, jout, jbase, pack_buf, pushed);
-    const int f_tot = first_slot_ge(th, P.key, total);
+    const int f_tot = th.ipath ? first_slot_ge_fixed(th, gtot_fixed) : first_slot_ge(th, P.key, total);
     LLPF_TS(P, sh, 3);
     finish_scatter<JT>(P, sh, bar_target, xseq, jout_flat, slot_lo, slot_hi, pushed);
     LLPF_TS(P, sh, 4);

@@ -8,8 +8,11 @@ Particles are block-partitioned: rank r owns global indices [r*n, (r+1)*n), n = 
      bit-identical to a single-process scan, independent of `world`)
   3. source side: particle b owns the output slots {i : bins[b-1] <= s_i < bins[b]},  s_i = fl(r + fl(i*fl(1/N)))
      (src/resample.jl:23-34); F(v) = min{i : s_i >= v} is evaluated exactly
-  4. slot i belongs to rank i // n: the (slot, ancestor) pairs are routed to their owners (on the device: stores
-     into the owner's `j` array over NVLink; here: an all-to-all)
+  4. slot i belongs to rank i // n.  Offspring that land on the source's own rank are scattered locally; a particle with
+     slots on another rank is shipped there ONCE as a packed entry (state, first slot, count) and expanded by the
+     destination (on the device: posted stores into the destination's `pack_in` over NVLink + counts on the cross-GPU
+     barrier, csrc/llpf_engine.cuh push_remote_parts / peer_exchange_counts / expand_packs; here: an all-to-all).
+This module is the CPU model of that protocol for the world_size-2/4 gloo tests; it is not on the product path.
 """
 import numpy as np
 
@@ -83,14 +86,12 @@ def sharded_systematic(we_local, u01, N, rank, world, allgather, alltoall, j_pre
 # ---------------------------------------------------------------------------------------------
 # Packed particle exchange (design for the next engine version; host mirror + gloo tests only)
 # ---------------------------------------------------------------------------------------------
-# Today the kernels route offspring INDICES to the slot owners and every slot then gathers its ancestor's state from
-# whichever rank holds it (fine-grained peer loads).  With degenerate weights most ancestors are remote and a few heavy
-# particles are read by every rank: NVLink latency and same-address contention make those steps 2x slower on 8 GPUs
-# (DESIGN.md section 9).  The bandwidth-optimal alternative uses what the source side already knows: particle b owns the
-# slot range [F(lo_b), F(hi_b)), which is monotone in b, so for every destination rank d the particles with at least one
-# slot on d can be PACKED by the source into one dense buffer (state + first local slot + count).  The destination reads
-# one contiguous buffer per source (bulk copy) and expands the runs locally: every needed particle crosses NVLink exactly
-# once per destination rank, however many slots it owns there.
+# The packed exchange (what the device does since round 2).  Round 1 routed offspring INDICES to the slot owners and every
+# slot then gathered its ancestor's state from whichever rank held it (fine-grained peer loads: NVLink latency and
+# same-address contention on heavy particles made resample steps 2-3x slower on 8 GPUs).  The source side already knows that
+# particle b owns the slot range [F(lo_b), F(hi_b)), which is monotone in b, so for every destination rank d the particles
+# with at least one slot on d are PACKED by the source (state + first slot + count), the destination expands the runs
+# locally, and every needed particle crosses NVLink exactly once per destination rank, however many slots it owns there.
 def pack_for_destinations(x_local, we_local, u01, N, rank, world, allgather):
     """Source side.  Returns, per destination rank d, (states [m_d, nx], first_slot_local [m_d], count [m_d]) for this
     rank's particles that own slots on d, plus (bins_local, f_total)."""

@@ -771,7 +771,10 @@ def test_smoother_backward_pass_matches_oracle_on_identical_history(gpu, nx, nu,
     pf = s.particle_filter(N, seed=6, scan_mode="serial", resampling_strategy=strat)
     xb, ll = L.smooth(pf, sol["x"], sol["w"], sol["we"], sol["ll"], M, u, y, epoch=4)
     assert xb.shape == (T, M, nx) and ll == sol["ll"]
-    assert _traj_mismatch(xb, ref) <= 0.002
+    # a backward draw can only differ from the oracle's when the drawn quantile lies within rounding distance of a bin edge
+    # (the device sums the transition densities in another order): no such tie occurs in these fixed-seed cases — every
+    # one of the T x M draws picks the oracle's particle
+    assert _traj_mismatch(xb, ref) == 0.0
     assert np.array_equal(xb[-1], ref[-1])                     # the resample at T is bit-exact (serial scan)
     assert L.last_smooth_ms(pf) > 0
 
@@ -788,7 +791,7 @@ def test_smoother_end_to_end_matches_oracle(gpu):
     pf = s.particle_filter(N, seed=3, scan_mode="serial")
     xb, ll = L.smooth(pf, M, u, y, epoch=2)
     assert abs(ll - sol["ll"]) <= LL_RTOL_TIGHT * abs(sol["ll"])
-    assert _traj_mismatch(xb, ref, tol=1e-9) <= 0.01
+    assert _traj_mismatch(xb, ref, tol=1e-9) == 0.0
     # helpers smoothing.jl:350-385
     assert L.smoothed_mean(xb).shape == (4, T) and L.smoothed_trajs(xb).shape == (4, M, T)
     assert len(L.smoothed_cov(xb)) == T and L.smoothed_cov(xb)[0].shape == (4, 4)
@@ -799,7 +802,7 @@ def test_smoother_end_to_end_matches_oracle(gpu):
     refa = oa.smooth(M, u, sola["x"], sola["w"], sola["we"], epoch=2)
     xba, lla = L.smooth(apf, M, u, y, epoch=2)
     assert abs(lla - sola["ll"]) <= LL_RTOL_TIGHT * abs(sola["ll"])
-    assert _traj_mismatch(xba, refa, tol=1e-9) <= 0.01
+    assert _traj_mismatch(xba, refa, tol=1e-9) == 0.0
 
 
 def test_smoother_quadtank_and_errors(gpu):
@@ -813,7 +816,7 @@ def test_smoother_quadtank_and_errors(gpu):
     ref = of.smooth(M, u, sol["x"], sol["w"], sol["we"], epoch=2)
     pf = q.advanced_filter(N, seed=4, scan_mode="serial")
     xb, _ = L.smooth(pf, sol["x"], sol["w"], sol["we"], sol["ll"], M, u, y, epoch=2)
-    assert _traj_mismatch(xb, ref) <= 0.005
+    assert _traj_mismatch(xb, ref) == 0.0
     with pytest.raises(L.LLPFError):                           # @assert M <= N   smoothing.jl:122
         L.smooth(pf, N + 1, u, y)
 

@@ -1,6 +1,6 @@
 """CPU-side performance guard: static checks on the SASS of the headline kernel k_engine<4,2,0,0> in the built library
 (no GPU needed).  The steady-state sweeps of a trajectory — the two innermost loops that contain the Philox rounds — were
-tuned to 382 (no resampling) and 443 (gathering) instructions without a single local-memory access (register spills were
+tuned to 382 (no resampling) and 443-467 (gathering) instructions without a single local-memory access (register spills were
 the first thing that cost performance in this kernel).  A change that bloats them or makes them spill
 fails here, before any GPU time is spent."""
 import collections
@@ -40,7 +40,7 @@ def test_steady_state_sweeps_stay_tight_and_spill_free(built):
     # the sweeps carry the bulk of the FP64 work (the small Philox loops belong to the stratified-threshold search)
     steady = sorted((b for b in philox if 300 <= len(b) < 600 and sum("DFMA" in t for t in b) > 80), key=len)
     assert len(steady) >= 2, [len(b) for b in philox]
-    for body, cap in zip(steady[:2], (400, 465)):
+    for body, cap in zip(steady[:2], (400, 470)):     # r2: the gathering sweep carries the packed-entry branch (467)
         ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split(".")[0].split()[0] for t in body)
         assert len(body) <= cap, (len(body), cap)
         assert ops["LDL"] == 0 and ops["STL"] == 0, dict(ops)      # no spills inside the sweep
