@@ -21,7 +21,7 @@
 #include "llpf_julia_range.h"
 #include "llpf_smooth.cuh"
 #include "llpf_stats.cuh"
-#include "llpf_wide.cuh"
+#include "llpf_wide_common.cuh"
 
 using namespace llpf;
 
@@ -524,15 +524,16 @@ static cudaError_t launch_engine_wide(llpf_filter* f, const EngineP& P) {
   EngineP Pc = P;
   Pc.want_xhat = 0; Pc.xhat = nullptr;
   void* args[] = {(void*)&Pc, (void*)&Mw};
-  return cudaLaunchCooperativeKernel((const void*)k_engine_wide, dim3(P.nblocks), dim3(BLOCK), args,
-                                     sizeof(WideShared), f->stream);
+  return cudaLaunchCooperativeKernel(wide_engine_kernel(), dim3(P.nblocks), dim3(wide_engine_block_threads()), args,
+                                     wide_engine_smem_bytes(), f->stream);
 }
 static int occupancy_engine_wide() {
-  if (cudaFuncSetAttribute(k_engine_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WideShared)) !=
-      cudaSuccess)
+  if (cudaFuncSetAttribute(wide_engine_kernel(), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)wide_engine_smem_bytes()) != cudaSuccess)
     return 0;
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_engine_wide, BLOCK, sizeof(WideShared)) != cudaSuccess)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wide_engine_kernel(), wide_engine_block_threads(),
+                                                    wide_engine_smem_bytes()) != cudaSuccess)
     return 0;
   return occ;
 }

@@ -21,31 +21,17 @@
 //   d_a   = (sum over even c, fmaf chain from 0) + (sum over odd c, fmaf chain from 0) ; v = yt_a - d_a
 //   q     = fmaf(v, v, q) for a ascending ; loglik = fmaf(-0.5, q, c0)  (f32) ; w += (double)loglik
 #pragma once
-#include "llpf_engine.cuh"
+#include "llpf_wide_common.cuh"
 
 namespace llpf {
 
-constexpr int WNX = 64;   // padded state dimension of the wide engine (nx <= 64, ny <= 64; padding is zeros)
-
-struct WideP {
-  const float* At;        // [64][64]  column-major A:  At[c*64 + r] = A[r,c]
-  const float* Lt;        // [64][64]  column-major lower Cholesky factor of R1 (zeros above the diagonal)
-  const float* G;         // [64][64]  row-major whitened measurement matrix (rows >= ny are zero)
-  const float* B;         // [64][MAX_NU] row-major
-  const double* W;        // [ny][ny]  row-major lower: inv(chol(R2))   (yt = W y is formed in f64, then rounded)
-  float c0;               // (float) mvnormal_c0
-  int nx, ny, nu;
-  int diagL;              // L is diagonal: x' += diag(L) z (bit-identical to the general loop: the other terms are +0)
-};
-
-// dynamic shared memory of the wide kernel (v2: block-tiled).  The three matrices are stored column by column with every
-// element DUPLICATED into a packed f32x2 pair (a, a): the tile GEMMs pair two particles per FFMA2, so the matrix operand is
-// the same scalar in both halves and comes straight out of a 16-byte shared load (no register shuffling).
+// dynamic shared memory of the wide kernel (v3: block-tiled, 128-thread blocks, two per SM)
 constexpr int WTP = BLOCK;     // particles per tile (one per thread in the load / store / reduce phases)
+static_assert(WTP == 128, "the thread <-> tile mapping below assumes 128-thread blocks (llpf_wide.cu)");
 struct WideShared {
-  alignas(16) u64 Ad[WNX * WNX];      // Ad[c*64 + r] = (A[r,c], A[r,c])
-  alignas(16) u64 Gd[WNX * WNX];      // Gd[c*64 + a] = (G[a,c], G[a,c])      (rows a >= ny are zero)
-  alignas(16) u64 Ld[WNX * WNX];      // Ld[c*64 + r] = (L[r,c], L[r,c])      (lower Cholesky factor of R1; zero above the diagonal)
+  alignas(16) float As[WNX * WNX];    // column-major A:  As[c*64 + r] = A[r,c]   (two consecutive rows = one f32x2 operand)
+  alignas(16) float Gs[WNX * WNX];    // column-major G:  Gs[c*64 + a] = G[a,c]   (rows a >= ny are zero)
+  alignas(16) float Ls[WNX * WNX];    // column-major lower Cholesky factor of R1 (zero above the diagonal)
   alignas(16) float XT[WNX * WTP];    // tile buffer, component-major: XT[c*WTP + p]; x, then z (general L), x', v in turn
   alignas(16) float bu[WNX];
   alignas(16) float yt[WNX];
@@ -121,42 +107,43 @@ __device__ __forceinline__ void wide_stage_step(const EngineP& P, const WideP& M
 }
 
 // ---- PF pass for wide models: [predict!(k_prop)] fused with [correct!(k_weigh)]  (cf. pf_pass) ------------
-// v2, block-tiled.  v1 gave every thread one particle and its 64 accumulators and streamed all three matrices from shared
-// memory for every particle: 16 LDS.128 per 32 FFMA2 — shared-memory bound at 27-29 % of the FP32 peak (profiles/
-// r1_v9_ncu_wide.md).  v2 processes a tile of 256 particles per block iteration as two 64 x 64 x 256 GEMMs:
-//   thread (warp w, lane l) owns rows 8w..8w+7 of particles {4l..4l+3} and {128+4l..128+4l+3}: 64 accumulators as 32 packed
-//   f32x2 pairs (two particles per pair); per column c it loads 8 duplicated matrix elements (4 broadcast LDS.128) and
-//   8 particle values (2 conflict-free LDS.128) for 32 FFMA2: 6 LDS.128 instead of 16 per 32 FFMA2.
+// v1 gave every thread one particle and its 64 accumulators and streamed all three matrices from shared memory for every
+// particle: 16 LDS.128 per 32 FFMA2 — shared-memory bound at 27-29 % of the FP32 peak (profiles/r1_v9_ncu_wide.md).
+// v3 (v2 was the same with one 256-thread block per SM) processes a tile of 128 particles per block iteration as two
+// 64 x 64 x 128 GEMMs on FFMA2:
+//   thread t = 16 rg + pg owns rows 8rg..8rg+7 of particles {4pg..4pg+3} and {64+4pg..64+4pg+3}: 64 accumulators as 32
+//   f32x2 pairs (two consecutive ROWS per pair); per column c it loads 8 matrix elements (2 LDS.128, two addresses per
+//   warp) and 8 particle values (2 conflict-free LDS.128) for 32 FFMA2: 4 LDS.128 instead of 16 per 32 FFMA2.
 // Every accumulator still sees exactly the fmaf chain documented at the top of this file (c ascending from 0, then + Bu,
 // then the noise chain; even / odd column chains for G x'), so the results are bit-identical to v1 and to the oracle.
 // Tile phases (one __syncthreads between them): gather x -> XT | GEMM1 A x (+Bu, +L z) , store x' | x' -> XT | GEMM2 G x',
 // v = yt - d | v -> XT | per particle: q = sum v^2 (fmaf chain over a), w += c0 - q/2, online reduction.
-__device__ __forceinline__ void lds_4x64(const u64* p, u64 (&v)[8]) {   // 8 consecutive u64 (64 B, 16-byte aligned)
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
-  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(addr));
-  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[2]), "=l"(v[3]) : "r"(addr + 16));
-  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[4]), "=l"(v[5]) : "r"(addr + 32));
-  asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[6]), "=l"(v[7]) : "r"(addr + 48));
-}
-__device__ __forceinline__ void lds_f4_as_pairs(const float* p, u64& a, u64& b) {   // 4 consecutive floats as 2 f32x2 pairs
-  lds_2x64(p, a, b);
-}
+// Two such blocks are resident per SM and run out of step, so one block's FP64 Box-Muller / global-load latency overlaps
+// the other's FFMA2 phases.
 
-// acc[r][q] += M[8w + r, c] * t[c][particle pair q]   for c = c0, c0 + cs, ... < 64 ; q: pairs 0,1 = particles 4l..4l+3,
-// pairs 2,3 = particles 128+4l..128+4l+3 (HALF selects pairs 0..1, 2..3 or all four)
+// acc[rp][p] += M[8rg + 2rp .. +1, c] * t[c][particle p]   for c = c0, c0 + cs, ... < 64
+// p: 0..3 = particles 4pg..4pg+3, 4..7 = particles 64+4pg..64+4pg+3 (HALF selects 0..3, 4..7 or all eight)
 template <int HALF>
-__device__ __forceinline__ void tile_gemm(u64 (&acc)[8][4], const u64* Md, const float* XT, int w, int l, int c0, int cs) {
+__device__ __forceinline__ void tile_gemm(u64 (&acc)[4][8], const float* Mc, const float* XT, int rg, int pg, int c0, int cs) {
 #pragma unroll 2
   for (int c = c0; c < WNX; c += cs) {
-    u64 m[8];
-    lds_4x64(Md + c * WNX + 8 * w, m);
-    u64 x[4];
-    if (HALF != 1) lds_f4_as_pairs(XT + c * WTP + 4 * l, x[0], x[1]);
-    if (HALF != 0) lds_f4_as_pairs(XT + c * WTP + 128 + 4 * l, x[2], x[3]);
+    u64 m[4];
+    lds_2x64(Mc + c * WNX + 8 * rg, m[0], m[1]);
+    lds_2x64(Mc + c * WNX + 8 * rg + 4, m[2], m[3]);
+    float x[8];
+    if (HALF != 1) {
+      const float4 v = *reinterpret_cast<const float4*>(XT + c * WTP + 4 * pg);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+    if (HALF != 0) {
+      const float4 v = *reinterpret_cast<const float4*>(XT + c * WTP + 64 + 4 * pg);
+      x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+    }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (HALF != 1) { acc[r][0] = ffma2(m[r], x[0], acc[r][0]); acc[r][1] = ffma2(m[r], x[1], acc[r][1]); }
-      if (HALF != 0) { acc[r][2] = ffma2(m[r], x[2], acc[r][2]); acc[r][3] = ffma2(m[r], x[3], acc[r][3]); }
+    for (int p = (HALF == 1 ? 4 : 0); p < (HALF == 0 ? 4 : 8); ++p) {
+      const u64 xx = pack2(x[p], x[p]);
+#pragma unroll
+      for (int rp = 0; rp < 4; ++rp) acc[rp][p] = ffma2(m[rp], xx, acc[rp][p]);
     }
   }
 }
@@ -195,7 +182,7 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
   const int cur = sc.cur;
   float* dst = reinterpret_cast<float*>(res ? P.x[cur ^ 1] : P.x[cur]);
   const int jid = sc.j_identity;
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int rg = threadIdx.x >> 4, pg = threadIdx.x & 15;
   const bool prop = k_prop > 0, weigh = k_weigh > 0;
   Online<1> acc1;
   acc1.init();
@@ -240,44 +227,43 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
       }
     }
     __syncthreads();
+    // tile-local particle index of accumulator column p
+    auto pcol = [&](int p) { return ((p < 4) ? 0 : 64) + 4 * pg + (p & 3); };
     if (prop) {
-      // ---- phase 1: x' = A x (+ B u) (+ L z), rows 8w..8w+7 of 8 particles ----
-      u64 acc[8][4];
+      // ---- phase 1: x' = A x (+ B u) (+ L z), rows 8rg..8rg+7 of 8 particles ----
+      u64 acc[4][8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
+      for (int rp = 0; rp < 4; ++rp)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = 0ull;
-      tile_gemm<2>(acc, ws.Ad, ws.XT, w, l, 0, 1);
+        for (int p = 0; p < 8; ++p) acc[rp][p] = 0ull;
+      tile_gemm<2>(acc, ws.As, ws.XT, rg, pg, 0, 1);
+      {   // + B u
+        u64 b[4];
+        lds_2x64(ws.bu + 8 * rg, b[0], b[1]);
+        lds_2x64(ws.bu + 8 * rg + 4, b[2], b[3]);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {   // + B u
-        const float b = ws.bu[8 * w + r];
-        const u64 bb = pack2(b, b);
+        for (int rp = 0; rp < 4; ++rp)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[r][q] = fadd2(acc[r][q], bb);
+          for (int p = 0; p < 8; ++p) acc[rp][p] = fadd2(acc[rp][p], b[rp]);
       }
-      // noise: 2 Philox blocks (rows 8w..8w+3, 8w+4..8w+7) per particle, f64 Box-Muller rounded to f32 — the same
+      // noise: 2 Philox blocks (rows 8rg..8rg+3, 8rg+4..8rg+7) per particle, f64 Box-Muller rounded to f32 — the same
       // counters as v1: block b of particle gi holds the normals of rows 4b..4b+3
       if (Mw.diagL) {
+        u64 ld[4];
+        lds_2x64(ws.ldiag + 8 * rg, ld[0], ld[1]);
+        lds_2x64(ws.ldiag + 8 * rg + 4, ld[2], ld[3]);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float z[2][8];
+        for (int p = 0; p < 8; ++p) {
+          const int pgi = P.first + tb + pcol(p);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int pg = P.first + tb + ((q < 2) ? 0 : 128) + 4 * l + 2 * (q & 1) + h;
-#pragma unroll
-            for (int bb = 0; bb < 2; ++bb) {
-              const uint4 rr = rng_block(P.key, ST_DYN, step_idx, (unsigned long long)(unsigned)pg, (uint32_t)(2 * w + bb));
-              const uint32_t ra[2] = {rr.x, rr.z}, rb[2] = {rr.y, rr.w};
-              double a0[2], a1[2];
-              normal_pairs<2>(ra, rb, a0, a1, sh.mt);
-              z[h][4 * bb] = (float)a0[0]; z[h][4 * bb + 1] = (float)a1[0];
-              z[h][4 * bb + 2] = (float)a0[1]; z[h][4 * bb + 3] = (float)a1[1];
-            }
-          }
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float ld = ws.ldiag[8 * w + r];
-            acc[r][q] = ffma2(pack2(ld, ld), pack2(z[0][r], z[1][r]), acc[r][q]);
+          for (int bb = 0; bb < 2; ++bb) {
+            const uint4 rr = rng_block(P.key, ST_DYN, step_idx, (unsigned long long)(unsigned)pgi, (uint32_t)(2 * rg + bb));
+            const uint32_t ra[2] = {rr.x, rr.z}, rb[2] = {rr.y, rr.w};
+            double a0[2], a1[2];
+            normal_pairs<2>(ra, rb, a0, a1, sh.mt);
+            // rows 8rg + 4bb + {0,1} and {2,3}
+            acc[2 * bb][p] = ffma2(ld[2 * bb], pack2((float)a0[0], (float)a1[0]), acc[2 * bb][p]);
+            acc[2 * bb + 1][p] = ffma2(ld[2 * bb + 1], pack2((float)a0[1], (float)a1[1]), acc[2 * bb + 1][p]);
           }
         }
       } else {
@@ -296,32 +282,29 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
           ws.XT[(4 * b + 3) * WTP + threadIdx.x] = (float)a1[1];
         }
         __syncthreads();
-        tile_gemm<2>(acc, ws.Ld, ws.XT, w, l, 0, 1);
+        tile_gemm<2>(acc, ws.Ls, ws.XT, rg, pg, 0, 1);
       }
-      // store x' (rows 8w..8w+7 = one 32-byte sector per particle) and hand the tile to phase 2 through XT
+      // store x' (rows 8rg..8rg+7 = one 32-byte sector per particle) and hand the tile to phase 2 through XT
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int p = 0; p < 8; ++p) {
+        const int ip = tb + pcol(p);
+        if (ip < cx.end) {
+          float o[8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int pl = ((q < 2) ? 0 : 128) + 4 * l + 2 * (q & 1) + h;
-          const int ip = tb + pl;
-          if (ip < cx.end) {
-            float o[8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) o[r] = h ? hi_f(acc[r][q]) : lo_f(acc[r][q]);
-            stg256(dst + (size_t)ip * WNX + 8 * w, o);
-          }
+          for (int rp = 0; rp < 4; ++rp) { o[2 * rp] = lo_f(acc[rp][p]); o[2 * rp + 1] = hi_f(acc[rp][p]); }
+          stg256(dst + (size_t)ip * WNX + 8 * rg, o);
         }
       }
       if (weigh) {
         __syncthreads();                           // readers of XT (x or z) are done
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          float* row = ws.XT + (8 * w + r) * WTP;
-          const unsigned a0 = (unsigned)__cvta_generic_to_shared(row + 4 * l);
-          const unsigned a1 = (unsigned)__cvta_generic_to_shared(row + 128 + 4 * l);
-          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a0), "l"(acc[r][0]), "l"(acc[r][1]) : "memory");
-          asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a1), "l"(acc[r][2]), "l"(acc[r][3]) : "memory");
+        for (int rp = 0; rp < 4; ++rp) {
+          float* r0 = ws.XT + (8 * rg + 2 * rp) * WTP;
+          float* r1 = r0 + WTP;
+          *reinterpret_cast<float4*>(r0 + 4 * pg) = make_float4(lo_f(acc[rp][0]), lo_f(acc[rp][1]), lo_f(acc[rp][2]), lo_f(acc[rp][3]));
+          *reinterpret_cast<float4*>(r1 + 4 * pg) = make_float4(hi_f(acc[rp][0]), hi_f(acc[rp][1]), hi_f(acc[rp][2]), hi_f(acc[rp][3]));
+          *reinterpret_cast<float4*>(r0 + 64 + 4 * pg) = make_float4(lo_f(acc[rp][4]), lo_f(acc[rp][5]), lo_f(acc[rp][6]), lo_f(acc[rp][7]));
+          *reinterpret_cast<float4*>(r1 + 64 + 4 * pg) = make_float4(hi_f(acc[rp][4]), hi_f(acc[rp][5]), hi_f(acc[rp][6]), hi_f(acc[rp][7]));
         }
         __syncthreads();
       }
@@ -332,33 +315,34 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
     if (weigh) {
       if (!skip) {
         // ---- phase 2: d_a = (even-column chain) + (odd-column chain) of G[a,:] x' ; v_a = yt_a - d_a ----
-        float v[8][8];
+        float v[8][8];   // [row 8rg + r][accumulator column p]
+        u64 yp[4];
+        lds_2x64(ws.yt + 8 * rg, yp[0], yp[1]);
+        lds_2x64(ws.yt + 8 * rg + 4, yp[2], yp[3]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          u64 de[8][4], dd[8][4];
+          u64 de[4][8], dd[4][8];
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
+          for (int rp = 0; rp < 4; ++rp)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { de[r][q] = 0ull; dd[r][q] = 0ull; }
-          if (half == 0) { tile_gemm<0>(de, ws.Gd, ws.XT, w, l, 0, 2); tile_gemm<0>(dd, ws.Gd, ws.XT, w, l, 1, 2); }
-          else { tile_gemm<1>(de, ws.Gd, ws.XT, w, l, 0, 2); tile_gemm<1>(dd, ws.Gd, ws.XT, w, l, 1, 2); }
+            for (int p = 0; p < 8; ++p) { de[rp][p] = 0ull; dd[rp][p] = 0ull; }
+          if (half == 0) { tile_gemm<0>(de, ws.Gs, ws.XT, rg, pg, 0, 2); tile_gemm<0>(dd, ws.Gs, ws.XT, rg, pg, 1, 2); }
+          else { tile_gemm<1>(de, ws.Gs, ws.XT, rg, pg, 0, 2); tile_gemm<1>(dd, ws.Gs, ws.XT, rg, pg, 1, 2); }
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const float y = ws.yt[8 * w + r];
+          for (int rp = 0; rp < 4; ++rp)
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const u64 e = de[r][2 * half + q], o = dd[r][2 * half + q];
-              v[r][4 * half + 2 * q] = y - (lo_f(e) + lo_f(o));
-              v[r][4 * half + 2 * q + 1] = y - (hi_f(e) + hi_f(o));
+            for (int q = 0; q < 4; ++q) {
+              const int p = 4 * half + q;
+              v[2 * rp][p] = lo_f(yp[rp]) - (lo_f(de[rp][p]) + lo_f(dd[rp][p]));
+              v[2 * rp + 1][p] = hi_f(yp[rp]) - (hi_f(de[rp][p]) + hi_f(dd[rp][p]));
             }
-          }
         }
         __syncthreads();                           // GEMM2 readers of XT are done
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          float* row = ws.XT + (8 * w + r) * WTP;
-          *reinterpret_cast<float4*>(row + 4 * l) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
-          *reinterpret_cast<float4*>(row + 128 + 4 * l) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+          float* row = ws.XT + (8 * rg + r) * WTP;
+          *reinterpret_cast<float4*>(row + 4 * pg) = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+          *reinterpret_cast<float4*>(row + 64 + 4 * pg) = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
         }
         __syncthreads();
         // ---- phase 3: loglik = c0 - q/2, q = fmaf(v_a, v_a, q) for a ascending (rows a >= ny: v = 0, no-op) ----
@@ -396,7 +380,7 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
   }
 }
 
-__global__ void __launch_bounds__(BLOCK, 1)
+__global__ void __launch_bounds__(BLOCK, LLPF_MIN_BLOCKS)
 k_engine_wide(const __grid_constant__ EngineP P, const __grid_constant__ WideP Mw) {
   __shared__ Shared sh;
   extern __shared__ __align__(16) unsigned char llpf_wide_smem[];
@@ -404,10 +388,9 @@ k_engine_wide(const __grid_constant__ EngineP P, const __grid_constant__ WideP M
   math_tab_load(sh.mt);
   for (int k = threadIdx.x; k < WNX * WNX; k += BLOCK) {
     const int c = k / WNX, r = k % WNX;
-    const float a = Mw.At[k], lv = Mw.Lt[k], g = Mw.G[r * WNX + c];   // At, Lt column-major; G row-major
-    ws.Ad[k] = pack2(a, a);
-    ws.Ld[k] = pack2(lv, lv);
-    ws.Gd[k] = pack2(g, g);
+    ws.As[k] = Mw.At[k];                 // At, Lt are column-major already
+    ws.Ls[k] = Mw.Lt[k];
+    ws.Gs[k] = Mw.G[r * WNX + c];        // G is row-major: transpose
   }
   if (threadIdx.x < WNX) {
     ws.ldiag[threadIdx.x] = Mw.Lt[threadIdx.x * WNX + threadIdx.x];
@@ -437,65 +420,6 @@ k_engine_wide(const __grid_constant__ EngineP P, const __grid_constant__ WideP M
   }
   grid_barrier(P.bar, (unsigned)P.nblocks, cx.bar_target);
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.sc = sc;
-}
-
-// reset!(pf)  filtering.jl:4-14 for wide models: x0 = mu0 + L0 z  (f32: fmaf chain from 0 over c <= r, then + mu0)
-__global__ void k_init_wide(float* x, long long n, long long first, RngKey key, const float* mu0, const float* L0 /*row-major*/,
-                            int nx) {
-  __shared__ MathTab mt;
-  math_tab_load(mt);
-  __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float z[WNX];
-#pragma unroll 1
-    for (int b = 0; b < WNX / 4; ++b) {
-      const uint4 r = rng_block(key, ST_INIT, 0u, (unsigned long long)(first + i), (uint32_t)b);
-      const uint32_t ra[2] = {r.x, r.z}, rb[2] = {r.y, r.w};
-      double a0[2], a1[2];
-      normal_pairs<2>(ra, rb, a0, a1, mt);
-      z[4 * b] = (float)a0[0]; z[4 * b + 1] = (float)a1[0]; z[4 * b + 2] = (float)a0[1]; z[4 * b + 3] = (float)a1[1];
-    }
-    float* xo = x + (size_t)i * WNX;
-    for (int r = 0; r < WNX; ++r) {
-      float acc = 0.f;
-      if (r < nx) {
-        for (int c = 0; c <= r; ++c) acc = fmaf(L0[r * WNX + c], z[c], acc);
-        acc = mu0[r] + acc;
-      }
-      xo[r] = acc;
-    }
-  }
-}
-
-__global__ void k_export_x_wide(const float* x, long long n, int nx, double* out) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    for (int d = 0; d < nx; ++d) out[(size_t)i * nx + d] = (double)x[(size_t)i * WNX + d];
-}
-__global__ void k_import_x_wide(float* x, long long n, int nx, const double* in) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    for (int d = 0; d < WNX; ++d) x[(size_t)i * WNX + d] = d < nx ? (float)in[(size_t)i * nx + d] : 0.f;
-}
-// (sum we, sum we^2, sum we*x[d]) block partials for weighted_mean / effective_particles  (filtering.jl:541-568)
-__global__ void k_wstats_wide(const double* we, const float* x, long long n, int nx, double* part /*[grid][2+WNX]*/) {
-  __shared__ double sm[8 * (2 + WNX)];
-  double v[2 + WNX];
-  for (int k = 0; k < 2 + WNX; ++k) v[k] = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double e = we[i];
-    v[0] += e;
-    v[1] = fma(e, e, v[1]);
-    for (int d = 0; d < nx; ++d) v[2 + d] = fma(e, (double)x[(size_t)i * WNX + d], v[2 + d]);
-  }
-  for (int k = 0; k < 2 + WNX; ++k)
-    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-  if ((threadIdx.x & 31) == 0)
-    for (int k = 0; k < 2 + WNX; ++k) sm[(threadIdx.x >> 5) * (2 + WNX) + k] = v[k];
-  __syncthreads();
-  if (threadIdx.x < 2 + WNX) {
-    double r = 0.0;
-    for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) r += sm[wq * (2 + WNX) + threadIdx.x];
-    part[(size_t)blockIdx.x * (2 + WNX) + threadIdx.x] = r;
-  }
 }
 
 }  // namespace llpf
