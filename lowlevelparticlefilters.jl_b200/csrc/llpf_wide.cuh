@@ -121,6 +121,15 @@ __device__ __forceinline__ void wide_stage_step(const EngineP& P, const WideP& M
 // Two such blocks are resident per SM and run out of step, so one block's FP64 Box-Muller / global-load latency overlaps
 // the other's FFMA2 phases.
 
+// 4 consecutive floats of MUTABLE shared data (bu, yt: rewritten every pass) as two f32x2 pairs.  lds_2x64 is a
+// non-volatile asm without memory clobber — fine for the matrices, which never change after the prologue, but the
+// compiler may move such a load across the __syncthreads that orders it after the writer.
+__device__ __forceinline__ void lds_pairs_mutable(const float* p, u64& a, u64& b) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  a = pack2(v.x, v.y);
+  b = pack2(v.z, v.w);
+}
+
 // acc[rp][p] += M[8rg + 2rp .. +1, c] * t[c][particle p]   for c = c0, c0 + cs, ... < 64
 // p: 0..3 = particles 4pg..4pg+3, 4..7 = particles 64+4pg..64+4pg+3 (HALF selects 0..3, 4..7 or all eight)
 template <int HALF>
@@ -239,8 +248,8 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
       tile_gemm<2>(acc, ws.As, ws.XT, rg, pg, 0, 1);
       {   // + B u
         u64 b[4];
-        lds_2x64(ws.bu + 8 * rg, b[0], b[1]);
-        lds_2x64(ws.bu + 8 * rg + 4, b[2], b[3]);
+        lds_pairs_mutable(ws.bu + 8 * rg, b[0], b[1]);
+        lds_pairs_mutable(ws.bu + 8 * rg + 4, b[2], b[3]);
 #pragma unroll
         for (int rp = 0; rp < 4; ++rp)
 #pragma unroll
@@ -317,8 +326,8 @@ __device__ __forceinline__ void pf_pass_wide(const EngineP& P, const WideP& Mw, 
         // ---- phase 2: d_a = (even-column chain) + (odd-column chain) of G[a,:] x' ; v_a = yt_a - d_a ----
         float v[8][8];   // [row 8rg + r][accumulator column p]
         u64 yp[4];
-        lds_2x64(ws.yt + 8 * rg, yp[0], yp[1]);
-        lds_2x64(ws.yt + 8 * rg + 4, yp[2], yp[3]);
+        lds_pairs_mutable(ws.yt + 8 * rg, yp[0], yp[1]);
+        lds_pairs_mutable(ws.yt + 8 * rg + 4, yp[2], yp[3]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           u64 de[4][8], dd[4][8];
