@@ -207,7 +207,16 @@ int llpf_set_model(llpf_handle h, const llpf_model* model);
    used; model->dynamics must be LLPF_DYN_USER; A, B, C, R2 may be NULL.  p[np]: the parameter vector `p` handed to both
    functions (copied to the device; llpf_set_user_params replaces it, e.g. between PMMH proposals, without recompiling).
    Compile errors: LLPF_ERR_BAD_ARG with the NVRTC log in llpf_last_error().  Needs libnvrtc.so.12 at run time
-   (searched in the loader path, $LLPF_NVRTC_PATH, /usr/local/cuda/lib64).                                             */
+   (searched in the loader path, $LLPF_NVRTC_PATH, /usr/local/cuda/lib64).
+   Particles with per-particle sufficient statistics (the reference's RBParticle = nonlinear state + mean and covariance
+   of a per-particle Kalman filter, rbpf.jl:1-5, :163-283): a source that contains the token LLPF_USER_STATE_HOOKS must
+   also define
+         template <> __device__ void add_noise<NX>(double (&x)[NX], const double (&xprev)[NX], const double (&nz)[NX],
+                                                   const double* u, const double* p, double t);   // replaces x += nz
+         template <> __device__ void correct_state<NX>(double (&x)[NX], const double* u, const double* y,
+                                                       const double* p, double t);   // mutation of the particle by correct!
+   (ParticleFilter / AdvancedParticleFilter kinds; R1 and Sigma0 may then be positive SEMI-definite: deterministic
+   components have zero rows).  The Python / Julia `RBPF` constructors generate such a source from the matrices.        */
 int llpf_create_user(const llpf_config* cfg, const llpf_model* model, const char* cuda_source,
                      const double* p, int32_t np, llpf_handle* out);
 int llpf_set_user_params(llpf_handle h, const double* p, int32_t np);

@@ -15,6 +15,7 @@ from .filters import (  # noqa: F401
     mean_trajectory, mode_trajectory, num_particles, particles, predict, resample, reset, set_state,
     shard_blob, shouldresample, trajectory_statistics, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
     weighted_mean, weights, xprev)
+from .rbpf import KalmanFilter, RBMeasurementModel, RBPF, rb_particles, rbpf_source  # noqa: F401
 from .estimation import (  # noqa: F401
     Normal, Uniform, log_likelihood_fun, metropolis, metropolis_batched, metropolis_threaded, naive_sampler, set_model, weighted_cov,
     weighted_quantile)

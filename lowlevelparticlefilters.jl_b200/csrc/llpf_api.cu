@@ -70,6 +70,33 @@ static bool chol_lower(const double* S, int n, std::vector<double>& L) {
   }
   return true;
 }
+// Positive SEMI-definite variant for user-defined models whose particles carry deterministic components (the mean and
+// covariance of a per-particle Kalman filter, rbpf.jl:136-150: only the nonlinear sub-state is random): a zero pivot is
+// accepted when the rest of its column is zero too, and gives a zero column of L.
+static bool chol_lower_psd(const double* S, int n, std::vector<double>& L) {
+  L.assign((size_t)n * n, 0.0);
+  for (int jc = 0; jc < n; ++jc) {
+    double d = CMH(S, jc, jc, n);
+    for (int k = 0; k < jc; ++k) d -= CMH(L, jc, k, n) * CMH(L, jc, k, n);
+    if (!(d >= 0.0)) return false;
+    if (d == 0.0) {
+      for (int i = jc + 1; i < n; ++i) {
+        double v = CMH(S, i, jc, n);
+        for (int k = 0; k < jc; ++k) v -= CMH(L, i, k, n) * CMH(L, jc, k, n);
+        if (v != 0.0) return false;
+      }
+      continue;
+    }
+    d = std::sqrt(d);
+    CMH(L, jc, jc, n) = d;
+    for (int i = jc + 1; i < n; ++i) {
+      double v = CMH(S, i, jc, n);
+      for (int k = 0; k < jc; ++k) v -= CMH(L, i, k, n) * CMH(L, jc, k, n);
+      CMH(L, i, jc, n) = v / d;
+    }
+  }
+  return true;
+}
 // inverse of a lower-triangular matrix (column-major)
 static void inv_lower(const std::vector<double>& L, int n, std::vector<double>& W) {
   W.assign((size_t)n * n, 0.0);
@@ -112,8 +139,8 @@ static int build_host_model(const llpf_model* m, HostModel& H, bool wide) {
     H.A.clear(); H.B.clear();
     H.C.assign((size_t)ny * nx, 0.0);
     H.mu0.assign(m->mu0, m->mu0 + nx);
-    if (!chol_lower(m->R1, nx, H.L1)) return fail(LLPF_ERR_NOT_POSDEF, "R1 is not positive definite");
-    if (!chol_lower(m->Sigma0, nx, H.L0)) return fail(LLPF_ERR_NOT_POSDEF, "Sigma0 is not positive definite");
+    if (!chol_lower_psd(m->R1, nx, H.L1)) return fail(LLPF_ERR_NOT_POSDEF, "R1 is not positive semi-definite");
+    if (!chol_lower_psd(m->Sigma0, nx, H.L0)) return fail(LLPF_ERR_NOT_POSDEF, "Sigma0 is not positive semi-definite");
     H.L2.assign((size_t)ny * ny, 0.0); H.W.assign((size_t)ny * ny, 0.0);
     for (int i = 0; i < ny; ++i) { CMH(H.L2, i, i, ny) = 1.0; CMH(H.W, i, i, ny) = 1.0; }
     H.G.assign((size_t)ny * nx, 0.0);
@@ -619,7 +646,10 @@ int compile_user_kernel(int device, int nx, int ny, int resid, const char* user_
   if (it != g_user_kernels.end()) { *out = it->second.kernel; return LLPF_OK; }
   std::string why;
   if (!nvrtc_open(why)) return fail(LLPF_ERR_UNSUPPORTED, "user-defined model: " + why);
-  std::string src = "#define LLPF_USER_MODEL\n#include \"llpf_engine.cuh\"\n#line 1 \"user_model.cu\"\n";
+  std::string src = "#define LLPF_USER_MODEL\n";
+  // a source that defines llpf_user::add_noise / correct_state says so by containing this token (llpf.h, llpf_create_user)
+  if (std::strstr(user_src, "LLPF_USER_STATE_HOOKS")) src += "#define LLPF_USER_STATE_HOOKS\n";
+  src += "#include \"llpf_engine.cuh\"\n#line 1 \"user_model.cu\"\n";
   src += user_src;
   src += "\nnamespace llpf {\ntemplate __global__ void k_engine<" + std::to_string(nx) + ", " + std::to_string(ny) + ", 2, " +
          std::to_string(resid) + ">(const __grid_constant__ EngineP, const __grid_constant__ ModelP<" + std::to_string(nx) +

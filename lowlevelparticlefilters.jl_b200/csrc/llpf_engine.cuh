@@ -50,6 +50,21 @@ template <int NX>
 __device__ void dynamics(double (&x)[NX], const double* u, const double* p, double t);
 template <int NX>
 __device__ double loglik(const double (&x)[NX], const double* u, const double* y, const double* p, double t);
+#ifdef LLPF_USER_STATE_HOOKS
+// Particles that carry more than a state vector (the reference's RBParticle: nonlinear state + mean and covariance of a
+// per-particle Kalman filter, rbpf.jl:1-5) need two more places to run code:
+//  * add_noise: how the drawn noise nz = L1*z enters the propagated particle (x = f(xprev) already; xprev is the particle
+//    the step started from). Default behaviour without the hooks: x += nz (PFtypes.jl:135). rbpf.jl:205-227 also feeds the
+//    noise of the nonlinear state into the linear state's mean through a gain that depends on the particle's covariance.
+//  * correct_state: the part of correct! that mutates the particle after its weight was computed (rbpf.jl:252-277: the
+//    Kalman measurement update of the linear sub-state); called with the same (u, y, t) as loglik, skipped with it when
+//    the measurement is missing.
+template <int NX>
+__device__ void add_noise(double (&x)[NX], const double (&xprev)[NX], const double (&nz)[NX], const double* u,
+                          const double* p, double t);
+template <int NX>
+__device__ void correct_state(double (&x)[NX], const double* u, const double* y, const double* p, double t);
+#endif
 }  // namespace llpf_user
 #endif
 
@@ -1799,6 +1814,29 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
           __stcs(weh + hbase + i, ws.expweight(i));
         }
       }
+#if defined(LLPF_USER_MODEL) && defined(LLPF_USER_STATE_HOOKS)
+      // particles with per-particle sufficient statistics (llpf_user::add_noise / correct_state above): the particle is
+      // stored after correct! has mutated it, also on a pass that only weighs
+      static_assert(DYN == 2, "state hooks belong to user-defined models");
+      if (prop_) {
+        double xp[NX];
+#pragma unroll
+        for (int d = 0; d < NX; ++d) xp[d] = x[d];
+        dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
+        llpf_user::add_noise<NX>(x, xp, z, sh.u_prop, sh.user_p, tprop);
+      }
+      if (weigh_) {
+        if (!skip_) {
+          const double tw = step_time(P, k_weigh);
+          wv += weigh_loglik<NX, NY, DYN>(M, sh, yt, x, tw);
+          llpf_user::correct_state<NX>(x, sh.u_weigh, sh.y_raw, sh.user_p, tw);
+        }
+        if (hist_x_) store_hist_x<NX>(P, k_weigh, gi, x);
+        __stcg(P.w + i, wv);
+        acc.add(wv, x, with_x_, sh.mt);
+      }
+      if (prop_ || (weigh_ && !skip_)) store_x<NX>(dst, P.ld, i, x);
+#else
       if (prop_) {
         dynamics_mean<NX, NY, DYN>(M, sh, bu, tprop, x);
 #pragma unroll
@@ -1815,6 +1853,7 @@ __device__ __forceinline__ void pf_pass(const EngineP& P, const ModelP<NX, NY>& 
         __stcg(P.w + i, wv);
         acc.add(wv, x, with_x_, sh.mt);
       }
+#endif
     }
   };
   const bool steady = (k_prop > 0) && (k_weigh > 0) && !hist_w && (P.x_hist == nullptr) && !skip && !with_x;

@@ -182,16 +182,18 @@ def _user_source(nx, dyn_body, lik_body):
 class _UserModelBuffers:
     """Model struct + generated CUDA source of a filter whose dynamics and / or likelihood are device code."""
 
-    def __init__(self, dynamics, likelihood_body, ny, R1, d0):
+    def __init__(self, dynamics, likelihood_body, ny, R1, d0, source=None, nu=None):
         nx = len(d0)
-        if isinstance(dynamics, CudaDynamics):
+        if source is not None:          # complete llpf_user source generated elsewhere (rbpf.py)
+            nu, dyn_body = int(nu or 0), None
+        elif isinstance(dynamics, CudaDynamics):
             nu, dyn_body = int(dynamics.nu), dynamics.body
         elif isinstance(dynamics, LinearDynamics):
             nu = 0 if dynamics.B is None else np.asarray(dynamics.B).reshape(nx, -1).shape[1]
             dyn_body = _linear_dynamics_body(dynamics.A, dynamics.B, nx, nu)
         else:
             raise TypeError("with user-defined device code the dynamics must be CudaDynamics or LinearDynamics")
-        self.source = _user_source(nx, dyn_body, likelihood_body)
+        self.source = source if source is not None else _user_source(nx, dyn_body, likelihood_body)
         m = _abi.Model()
         self.keep = []
         null = C.cast(None, dp)
