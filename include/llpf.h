@@ -336,6 +336,23 @@ int llpf_last_run_ms(llpf_handle h, float* ms);
 /* raw device pointers of the SoA state for zero-copy consumers: x is [nx][n] doubles, w is [n]  */
 int llpf_device_pointers(llpf_handle h, void** x_dev, void** w_dev, void** stream);
 
+/* ---- Ensemble Kalman filter (reference src/enkf.jl: stochastic EnKF with perturbed observations) --------------------
+ * SURVEY §8f rank 4.  The ensemble is the particle buffer of an ordinary handle: create it with llpf_create (filter =
+ * LLPF_FILTER_PF, Float64 particles, descriptor dynamics, world = 1; C is the linear measurement, R1 / R2 / mu0 / Sigma0 as in
+ * EnsembleKalmanFilter(dynamics, measurement, R1, R2, d0, N), enkf.jl:94-141), then use these verbs instead of the
+ * particle-filter ones.  Matrices in the outputs are row-major (symmetric ones either way).                              */
+int llpf_enkf_set_inflation(llpf_handle h, double inflation);                      /* kwarg `inflation`  enkf.jl:106,261-266 */
+int llpf_enkf_reset(llpf_handle h, uint64_t epoch);                                /* reset!(enkf)       enkf.jl:205-224     */
+int llpf_enkf_state(llpf_handle h, double* mean, double* cov, int64_t* t_index);   /* state / covariance / index :178-193    */
+int llpf_enkf_predict(llpf_handle h, const double* u, double t);                   /* predict!           enkf.jl:228-272     */
+int llpf_enkf_correct(llpf_handle h, const double* u, const double* y, double t,   /* correct! -> (; ll, e, S, K) :281-356   */
+                      double* ll, double* e, double* S, double* K);
+/* forward_trajectory(enkf, u, y) (filtering.jl:282-325) in ONE launch: reset!(epoch), then per step (x, R) recorded,
+   correct!, (xt, Rt, e) recorded, predict!.  Host outputs, any may be NULL: x, xt [T][nx]; R, Rt [T][nx*nx]; e [T][ny];
+   ll_steps [T]; S [T][ny*ny]; K [T][nx*ny]; *ll = sum of ll_steps.                                                          */
+int llpf_enkf_run(llpf_handle h, int64_t T, const double* u, const double* y, uint64_t epoch, double* ll, double* x,
+                  double* R, double* xt, double* Rt, double* e, double* ll_steps, double* S, double* K);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,9 @@ from .filters import (  # noqa: F401
     shard_blob, shouldresample, trajectory_statistics, smooth, smoothed_cov, smoothed_mean, smoothed_trajs, last_smooth_ms, state, update,
     weighted_mean, weights, xprev)
 from .rbpf import KalmanFilter, RBMeasurementModel, RBPF, rb_particles, rbpf_source  # noqa: F401
+from .enkf import (  # noqa: F401
+    EnsembleKalmanFilter, KalmanFilteringSolution, enkf_correct, enkf_covariance, enkf_forward_trajectory, enkf_particles,
+    enkf_predict, enkf_reset, enkf_state, enkf_update)
 from .estimation import (  # noqa: F401
     Normal, Uniform, log_likelihood_fun, metropolis, metropolis_batched, metropolis_threaded, naive_sampler, set_model, weighted_cov,
     weighted_quantile)

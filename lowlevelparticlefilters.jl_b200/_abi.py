@@ -124,6 +124,12 @@ def load_library(path=None):
         "llpf_resample_residual": [C.c_int64, dp, dp, C.c_int64, ip, dp, C.c_int32, C.c_int32],
         "llpf_resample_metropolis": [C.c_int64, dp, C.c_int64, C.c_int32, C.c_uint64, ip, C.c_int32],
         "llpf_logsumexp": [C.c_int64, dp, dp, dp, C.c_int32],
+        "llpf_enkf_set_inflation": [H, C.c_double],
+        "llpf_enkf_reset": [H, C.c_uint64],
+        "llpf_enkf_state": [H, dp, dp, ip],
+        "llpf_enkf_predict": [H, dp, C.c_double],
+        "llpf_enkf_correct": [H, dp, dp, C.c_double, dp, dp, dp, dp],
+        "llpf_enkf_run": [H, C.c_int64, dp, dp, C.c_uint64, dp, dp, dp, dp, dp, dp, dp, dp, dp],
         "llpf_shard_blob_size": [C.POINTER(C.c_size_t)],
         "llpf_shard_export": [H, C.c_void_p],
         "llpf_shard_connect": [H, C.c_void_p],

@@ -113,7 +113,7 @@ static void inv_lower(const std::vector<double>& L, int n, std::vector<double>& 
 struct HostModel {
   int nx = 0, nu = 0, ny = 0, dyn = 0;
   bool wide = false;   // Float32 particles, nx/ny up to 64: the engine of llpf_wide.cuh
-  std::vector<double> A, B, C, mu0, L0, L1, L2, W, G;  // column-major
+  std::vector<double> A, B, C, mu0, L0, L1, L2, W, G, R2;  // column-major
   double c0 = 0;
   double dynp[8] = {0}, t_switch = 0, a1_factor = 1, integ_Ts = 1;
   int supersample = 1;
@@ -162,6 +162,7 @@ static int build_host_model(const llpf_model* m, HostModel& H, bool wide) {
     return fail(LLPF_ERR_BAD_ARG, "unknown dynamics kind");
   }
   H.C.assign(m->C, m->C + (size_t)ny * nx);
+  H.R2.assign(m->R2, m->R2 + (size_t)ny * ny);
   H.mu0.assign(m->mu0, m->mu0 + nx);
   if (!chol_lower(m->R1, nx, H.L1)) return fail(LLPF_ERR_NOT_POSDEF, "R1 is not positive definite");
   if (!chol_lower(m->R2, ny, H.L2)) return fail(LLPF_ERR_NOT_POSDEF, "R2 is not positive definite");
@@ -430,6 +431,13 @@ struct llpf_filter {
   long long launches = 0;
   float last_ms = 0.f, last_smooth_ms = 0.f;
   int max_blocks = 1;
+  // Ensemble Kalman filter verbs (llpf_enkf_*): state block {ll, t, mean, cov, status}, reduction scratch, inflation
+  double* enkf_st = nullptr;
+  double* enkf_partials = nullptr;
+  double* enkf_out = nullptr;
+  size_t enkf_out_doubles = 0;
+  int enkf_blocks = 0;
+  double enkf_inflation = 1.0;
   launch_fn launch = nullptr;
   init_fn init = nullptr;
   // wide (Float32-particle) engine: device copies of the model in the layouts of WideP
@@ -714,7 +722,13 @@ static std::vector<double> pack_modelp_runtime(const HostModel& H) {
   for (int r = 0; r < nx; ++r)
     for (int c = 0; c < H.nu; ++c)
       if (!H.B.empty()) B[r * MAX_NU + c] = CMH(H.B, r, c, nx);
-  tail[0] = H.c0;                               // c0 ; qt[8] stays zero
+  tail[0] = H.c0;                               // c0 ; qt[8] stays zero except for the quadtank descriptor
+  if (H.dyn == LLPF_DYN_QUADTANK_RK4) {         // as fill_modelp
+    const double k1 = H.dynp[1], k2 = H.dynp[2], Aa = H.dynp[3], a = H.dynp[4], g = H.dynp[5];
+    const double qt[8] = {-a / Aa, -(a * H.a1_factor) / Aa, a / Aa, 2 * 9.81, g * k1 / Aa, g * k2 / Aa, (1 - g) * k2 / Aa,
+                          (1 - g) * k1 / Aa};
+    for (int k = 0; k < 8; ++k) tail[1 + k] = qt[k];
+  }
   tail[9] = H.t_switch;
   tail[10] = H.integ_Ts / (double)H.supersample;
   int ints[2] = {H.supersample, H.nu};
@@ -804,6 +818,7 @@ extern "C" int llpf_destroy(llpf_handle h) {
   cudaFree(h->w_W);
   cudaFree(h->d_user_p);
   cudaFree(h->d_batch); cudaFree(h->d_batch_sc);
+  cudaFree(h->enkf_st); cudaFree(h->enkf_partials); cudaFree(h->enkf_out);
   if (h->pin_sc) cudaFreeHost(h->pin_sc);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -2159,4 +2174,190 @@ extern "C" int llpf_device_pointers(llpf_handle h, void** x_dev, void** w_dev, v
   if (w_dev) *w_dev = h->w;
   if (stream) *stream = (void*)h->stream;
   return LLPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ensemble Kalman filter (reference src/enkf.jl; kernel in llpf_enkf.cuh / llpf_enkf.cu)
+// ------------------------------------------------------------------------------------------------
+namespace llpf {
+const void* enkf_kernel(int nx, int ny, int dyn);
+// mirrors EnkfP of llpf_enkf.cuh (this translation unit does not include the kernel)
+struct EnkfPHost {
+  double* x; long long ld; long long N;
+  int n, nblocks, chunk, nu;
+  unsigned int* bar; double* partials;
+  const double* u; const double* y;
+  int T, do_correct, do_predict, use_t_single;
+  double Ts, t_single, inflation;
+  RngKey key;
+  double* st;
+  double *o_x, *o_R, *o_xt, *o_Rt, *o_e, *o_ll, *o_S, *o_K;
+};
+constexpr int kEnkfKmax = 128;   // ENKF_KMAX
+}  // namespace llpf
+
+static int enkf_prepare(llpf_filter* f, const void** kernel) {
+  if (f->hm.wide || f->hm.dyn == LLPF_DYN_USER || f->world > 1 || f->cfg.filter != LLPF_FILTER_PF)
+    return fail(LLPF_ERR_UNSUPPORTED, "EnKF verbs need a single-GPU Float64 ParticleFilter-kind handle with descriptor dynamics "
+                                      "and a linear measurement");
+  *kernel = enkf_kernel(f->hm.nx, f->hm.ny, f->hm.dyn);
+  if (!*kernel) return fail(LLPF_ERR_UNSUPPORTED, "no EnKF kernel instantiated for this (nx, ny, dynamics)");
+  const int nx = f->hm.nx;
+  if (!f->enkf_st) {
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, *kernel, BLOCK, 0));
+    if (occ < 1) return fail(LLPF_ERR_CUDA, "EnKF kernel does not fit on an SM");
+    long long nb = (f->n + BLOCK - 1) / BLOCK;
+    nb = std::min<long long>(nb, std::min(occ * f->num_sms, MAX_BLOCKS - 1));
+    f->enkf_blocks = (int)std::max<long long>(nb, 1);
+    CU(cudaMalloc(&f->enkf_st, sizeof(double) * (size_t)(2 + nx + nx * nx + 1)));
+    CU(cudaMemsetAsync(f->enkf_st, 0, sizeof(double) * (size_t)(2 + nx + nx * nx + 1), f->stream));
+    CU(cudaMalloc(&f->enkf_partials, sizeof(double) * (size_t)2 * f->enkf_blocks * kEnkfKmax));
+  }
+  return LLPF_OK;
+}
+
+// one launch of k_enkf; `out` (host, nullable pointers) receives the per-step outputs of the T steps
+struct EnkfHostOut { double *x, *R, *xt, *Rt, *e, *ll, *S, *K; };
+static int enkf_launch(llpf_filter* f, int T, const double* d_u, const double* d_y, int do_correct, int do_predict,
+                       bool use_t, double t, const EnkfHostOut& out) {
+  const void* k = nullptr;
+  OKR(enkf_prepare(f, &k));
+  const int nx = f->hm.nx, ny = f->hm.ny;
+  const size_t Tn = (size_t)std::max(T, 1);
+  const size_t sizes[8] = {Tn * nx, Tn * nx * nx, Tn * nx, Tn * nx * nx, Tn * ny, Tn, Tn * ny * ny, Tn * nx * ny};
+  double* const host[8] = {out.x, out.R, out.xt, out.Rt, out.e, out.ll, out.S, out.K};
+  size_t need = 0;
+  for (int q = 0; q < 8; ++q) if (host[q]) need += sizes[q];
+  if (need > f->enkf_out_doubles) {
+    cudaFree(f->enkf_out); f->enkf_out = nullptr; f->enkf_out_doubles = 0;
+    CU(cudaMalloc(&f->enkf_out, sizeof(double) * need));
+    f->enkf_out_doubles = need;
+  }
+  double* dev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  { size_t o = 0; for (int q = 0; q < 8; ++q) if (host[q]) { dev[q] = f->enkf_out + o; o += sizes[q]; } }
+  llpf::EnkfPHost P;
+  std::memset(&P, 0, sizeof(P));
+  P.x = f->x[f->hsc.cur]; P.ld = f->ld; P.N = f->N; P.n = (int)f->n;
+  P.nblocks = f->enkf_blocks;
+  P.chunk = (int)((f->n + P.nblocks - 1) / P.nblocks);
+  P.nu = f->hm.nu;
+  P.bar = f->bar; P.partials = f->enkf_partials;
+  P.u = d_u; P.y = d_y;
+  P.T = T; P.do_correct = do_correct; P.do_predict = do_predict; P.use_t_single = use_t ? 1 : 0;
+  P.Ts = f->cfg.Ts; P.t_single = t; P.inflation = f->enkf_inflation;
+  P.key = RngKey{(uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), (uint32_t)f->epoch << 8};
+  P.st = f->enkf_st;
+  P.o_x = dev[0]; P.o_R = dev[1]; P.o_xt = dev[2]; P.o_Rt = dev[3]; P.o_e = dev[4]; P.o_ll = dev[5]; P.o_S = dev[6]; P.o_K = dev[7];
+  std::vector<double> M = pack_modelp_runtime(f->hm);
+  std::vector<double> E((size_t)ny * nx + 2 * (size_t)ny * ny, 0.0);   // EnkfM: C, R2, L2 row-major
+  for (int a = 0; a < ny; ++a) {
+    for (int c = 0; c < nx; ++c) E[(size_t)a * nx + c] = CMH(f->hm.C, a, c, ny);
+    for (int c = 0; c < ny; ++c) {
+      E[(size_t)ny * nx + (size_t)a * ny + c] = CMH(f->hm.R2, a, c, ny);
+      E[(size_t)ny * nx + (size_t)ny * ny + (size_t)a * ny + c] = CMH(f->hm.L2, a, c, ny);
+    }
+  }
+  CU(cudaMemsetAsync(f->bar, 0, sizeof(unsigned) * BAR_TOTAL_WORDS, f->stream));
+  void* args[] = {(void*)&P, (void*)M.data(), (void*)E.data()};
+  CU(cudaEventRecord(f->ev0, f->stream));
+  CU(cudaLaunchCooperativeKernel(k, dim3(P.nblocks), dim3(BLOCK), args, 0, f->stream));
+  CU(cudaEventRecord(f->ev1, f->stream));
+  f->launches += 1;
+  for (int q = 0; q < 8; ++q)
+    if (host[q]) CU(cudaMemcpyAsync(host[q], dev[q], sizeof(double) * sizes[q], cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  CU(cudaEventElapsedTime(&f->last_ms, f->ev0, f->ev1));
+  return LLPF_OK;
+}
+
+static int enkf_read_state(llpf_filter* f, double* ll, double* tindex, double* mean, double* cov) {
+  const int nx = f->hm.nx;
+  std::vector<double> st((size_t)2 + nx + nx * nx + 1);
+  CU(cudaMemcpyAsync(st.data(), f->enkf_st, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, f->stream));
+  CU(cudaStreamSynchronize(f->stream));
+  if (ll) *ll = st[0];
+  if (tindex) *tindex = st[1];
+  if (mean) std::memcpy(mean, st.data() + 2, sizeof(double) * nx);
+  if (cov) std::memcpy(cov, st.data() + 2 + nx, sizeof(double) * nx * nx);
+  if (st.back() != 0.0) return fail(LLPF_ERR_NOT_POSDEF, "Cholesky factorization of innovation covariance failed (enkf.jl:324)");
+  if (!(std::fabs(st[0]) <= 1.7976931348623157e308)) return fail(LLPF_ERR_NONFINITE, "EnKF log-likelihood is not finite");
+  return LLPF_OK;
+}
+
+extern "C" int llpf_enkf_set_inflation(llpf_handle h, double inflation) {
+  OKR(check_handle(h));
+  if (!(inflation > 0.0)) return fail(LLPF_ERR_BAD_ARG, "inflation must be positive");
+  h->enkf_inflation = inflation;
+  return LLPF_OK;
+}
+
+// reset!(enkf)  enkf.jl:205-224: redraw the ensemble from d0 (RNG stream 0 of `epoch`), t = 0, cached mean / covariance
+extern "C" int llpf_enkf_reset(llpf_handle h, uint64_t epoch) {
+  OKR(check_handle(h));
+  const void* k = nullptr;
+  OKR(enkf_prepare(h, &k));
+  OKR(llpf_reset(h, epoch));
+  const int nx = h->hm.nx;
+  CU(cudaMemsetAsync(h->enkf_st, 0, sizeof(double) * (size_t)(2 + nx + nx * nx + 1), h->stream));
+  return enkf_launch(h, 0, nullptr, nullptr, 0, 0, true, 0.0, EnkfHostOut{});
+}
+
+// state(enkf), covariance(enkf)  enkf.jl:186-193 (cached by the last verb); cov row-major nx*nx (symmetric); t = enkf.t
+extern "C" int llpf_enkf_state(llpf_handle h, double* mean, double* cov, int64_t* t_index) {
+  OKR(check_handle(h));
+  if (!h->enkf_st) return fail(LLPF_ERR_BAD_ARG, "call llpf_enkf_reset first");
+  CU(cudaSetDevice(h->device));
+  double ti = 0;
+  std::vector<double> st((size_t)2 + h->hm.nx + h->hm.nx * h->hm.nx + 1);
+  CU(cudaMemcpyAsync(st.data(), h->enkf_st, sizeof(double) * st.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  ti = st[1];
+  if (mean) std::memcpy(mean, st.data() + 2, sizeof(double) * h->hm.nx);
+  if (cov) std::memcpy(cov, st.data() + 2 + h->hm.nx, sizeof(double) * h->hm.nx * h->hm.nx);
+  if (t_index) *t_index = (int64_t)ti;
+  return LLPF_OK;
+}
+
+// predict!(enkf, u, p, t)  enkf.jl:228-272
+extern "C" int llpf_enkf_predict(llpf_handle h, const double* u, double t) {
+  OKR(check_handle(h));
+  if (!h->enkf_st) return fail(LLPF_ERR_BAD_ARG, "call llpf_enkf_reset first");
+  CU(cudaSetDevice(h->device));
+  OKR(stage_inputs(h, u, nullptr, nullptr));
+  OKR(enkf_launch(h, 1, h->stage_u, h->stage_y, 0, 1, true, t, EnkfHostOut{}));
+  return enkf_read_state(h, nullptr, nullptr, nullptr, nullptr);
+}
+
+// correct!(enkf, u, y, p, t) -> (; ll, e, S, K)  enkf.jl:281-356 (S, K row-major ny*ny / nx*ny; any of them may be NULL)
+extern "C" int llpf_enkf_correct(llpf_handle h, const double* u, const double* y, double t, double* ll, double* e, double* S,
+                                 double* K) {
+  OKR(check_handle(h));
+  if (!h->enkf_st) return fail(LLPF_ERR_BAD_ARG, "call llpf_enkf_reset first");
+  if (!y) return fail(LLPF_ERR_BAD_ARG, "y is null");
+  CU(cudaSetDevice(h->device));
+  OKR(stage_inputs(h, u, y, nullptr));
+  EnkfHostOut out{};
+  out.e = e; out.S = S; out.K = K; out.ll = ll;
+  OKR(enkf_launch(h, 1, h->stage_u, h->stage_y, 1, 0, true, t, out));
+  return enkf_read_state(h, nullptr, nullptr, nullptr, nullptr);
+}
+
+// forward_trajectory(enkf, u, y)  filtering.jl:282-325: reset!, then per step record (x, R), correct!, record (xt, Rt, e),
+// predict!; one launch.  Outputs (host, any may be NULL): x, xt [T][nx]; R, Rt [T][nx*nx]; e [T][ny]; ll_steps [T];
+// S [T][ny*ny]; K [T][nx*ny].  *ll = sum of the step log-likelihoods.
+extern "C" int llpf_enkf_run(llpf_handle h, int64_t T, const double* u, const double* y, uint64_t epoch, double* ll,
+                             double* x, double* R, double* xt, double* Rt, double* e, double* ll_steps, double* S, double* K) {
+  OKR(check_handle(h));
+  if (T < 1 || T > (1 << 30) || !y) return fail(LLPF_ERR_BAD_ARG, "need T >= 1 and y");
+  const int nu = h->hm.nu, ny = h->hm.ny;
+  if (nu > 0 && !u) return fail(LLPF_ERR_BAD_ARG, "u is null");
+  OKR(llpf_enkf_reset(h, epoch));
+  OKR(ensure_run_buffers(h, T));
+  if (nu > 0) CU(cudaMemcpyAsync(h->d_u, u, sizeof(double) * (size_t)T * nu, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_y, y, sizeof(double) * (size_t)T * ny, cudaMemcpyHostToDevice, h->stream));
+  EnkfHostOut out{};
+  out.x = x; out.R = R; out.xt = xt; out.Rt = Rt; out.e = e; out.ll = ll_steps; out.S = S; out.K = K;
+  OKR(enkf_launch(h, (int)T, h->d_u, h->d_y, 1, 1, false, 0.0, out));
+  return enkf_read_state(h, ll, nullptr, nullptr, nullptr);
 }
