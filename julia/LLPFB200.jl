@@ -267,4 +267,114 @@ function resample_residual(we::Vector{Float64}, u01::Vector{Float64}; M=length(w
     j, bins
 end
 
+# ---- Rao-Blackwellized particle filter (src/rbpf.jl) on the user-model boundary ------------------------------------------
+_lit(v) = string(Float64(v))          # shortest round-trip decimal: parses back to the same Float64
+function _cmat(M, rows, cols)
+    A = zeros(rows, max(cols, 1))
+    (cols > 0 && M !== nothing) && (A[:, 1:cols] .= reshape(Matrix{Float64}(M), rows, cols))
+    "{" * join(["{" * join(_lit.(A[r, :]), ", ") * "}" for r in 1:rows], ", ") * "}"
+end
+"""
+    rbpf_source(nxn, nxl, ny, nu, A, B, C, An, R1l, R1n, R2, fn_body, g_body)
+The `llpf_user` source of an RBPF (include/llpf.h, LLPF_USER_STATE_HOOKS): a particle is `[xn; xl; tril(R)]`, the arithmetic of
+src/rbpf.jl:163-283 is csrc/llpf_rbpf.cuh.  `fn_body` writes fn(xn,u,p,t) into `fn[]`, `g_body` writes g(xn,u,p,t) into `yn[]`.
+"""
+function rbpf_source(nxn, nxl, ny, nu, A, B, C, An, R1l, R1n, R2, fn_body, g_body)
+    nx = nxn + nxl + nxl * (nxl + 1) ÷ 2
+    zan = An === nothing || iszero(An); zc = C === nothing || iszero(C)
+    k = join([_cmat(A, nxl, nxl), _cmat(B, nxl, nu), _cmat(C, ny, nxl), _cmat(An, nxn, nxl), _cmat(R1l, nxl, nxl),
+              _cmat(R1n, nxn, nxn), _cmat(R2, ny, ny), string(Int(zan)), string(Int(zc))], ", ")
+    T = "$nxn, $nxl, $ny, $nu, $nx"
+    """
+    // LLPF_USER_STATE_HOOKS : Rao-Blackwellized particle filter (rbpf.jl)
+    #include "llpf_rbpf.cuh"
+    namespace llpf_user {
+    using RB = llpf_rbpf::Consts<$nxn, $nxl, $ny, $nu>;
+    __device__ __forceinline__ RB rb_consts() { const RB k = {$k}; return k; }
+    __device__ __forceinline__ void rb_fn(const double (&xn)[$nxn], const double* u, const double* p, double t, double (&fn)[$nxn]) { $fn_body }
+    __device__ __forceinline__ void rb_g(const double (&xn)[$nxn], const double* u, const double* p, double t, double (&yn)[$ny]) { $g_body }
+    __device__ __forceinline__ void rb_xn(const double (&x)[$nx], double (&xn)[$nxn]) { for (int r = 0; r < $nxn; ++r) xn[r] = x[r]; }
+    template <> __device__ void dynamics<$nx>(double (&x)[$nx], const double* u, const double* p, double t) {
+      const RB k = rb_consts(); double xn[$nxn], fn[$nxn]; rb_xn(x, xn); rb_fn(xn, u, p, t, fn); llpf_rbpf::predict_mean<$T>(x, fn, u, k); }
+    template <> __device__ void add_noise<$nx>(double (&x)[$nx], const double (&xprev)[$nx], const double (&nz)[$nx], const double* u, const double* p, double t) {
+      const RB k = rb_consts(); llpf_rbpf::add_noise<$T>(x, xprev, nz, k); }
+    template <> __device__ double loglik<$nx>(const double (&x)[$nx], const double* u, const double* y, const double* p, double t) {
+      const RB k = rb_consts(); double xn[$nxn], yn[$ny]; rb_xn(x, xn); rb_g(xn, u, p, t, yn); return llpf_rbpf::loglik<$T>(x, yn, y, k); }
+    template <> __device__ void correct_state<$nx>(double (&x)[$nx], const double* u, const double* y, const double* p, double t) {
+      const RB k = rb_consts(); double xn[$nxn], yn[$ny]; rb_xn(x, xn); rb_g(xn, u, p, t, yn); llpf_rbpf::correct_state<$T>(x, yn, y, k); }
+    }
+    """
+end
+"""
+    RBPF(N, kf::KalmanFilter, fn_body::String, g_body::String, R1n, d0n; An=nothing, nu, ny, kw...)
+RBPF(N, kf, dynamics, nl_measurement_model, R1n, d0n; An, nu) of src/rbpf.jl:113-133 with the two closures given as device
+snippets and constant matrices taken from `kf` (A, B, C, R1, R2, d0).  Returns a GPUParticleFilter: every generic verb applies.
+"""
+function RBPF(N::Integer, kf, fn_body::String, g_body::String, R1n, d0n; An=nothing, nu::Int, ny::Int=size(kf.R2, 1),
+              resample_threshold=0.1, Ts=1.0, seed=0, p=Float64[], kw...)
+    nxn, nxl = length(_mean(d0n)), length(_mean(kf.d0))
+    nx = nxn + nxl + nxl * (nxl + 1) ÷ 2
+    nx <= 8 || error("RBPF particle [xn; xl; tril(R)] has $nx components; the f64 engine carries at most 8")
+    src = rbpf_source(nxn, nxl, ny, nu, kf.A, nu > 0 ? kf.B : nothing, kf.C, An, kf.R1, R1n, kf.R2, fn_body, g_body)
+    R1c = zeros(nx, nx); R1c[1:nxn, 1:nxn] .= Matrix{Float64}(R1n)
+    mu0 = zeros(nx); S0 = zeros(nx, nx)
+    mu0[1:nxn] .= _mean(d0n); S0[1:nxn, 1:nxn] .= _cov(d0n); mu0[nxn+1:nxn+nxl] .= _mean(kf.d0)
+    R0 = Matrix{Float64}(_cov(kf.d0))
+    mu0[nxn+nxl+1:end] .= [R0[r, c] for r in 1:nxl for c in 1:r]
+    GPUParticleFilter(N, src, Vector{Float64}(p); nx, nu, ny, R1=R1c, mu0, Sigma0=S0, kind=0, resample_threshold, Ts, seed, kw...)
+end
+
+# ---- Ensemble Kalman filter (src/enkf.jl): the llpf_enkf_* verbs on an ordinary handle --------------------------------------
+mutable struct GPUEnsembleKalmanFilter <: LowLevelParticleFilters.AbstractKalmanFilter
+    pf::GPUParticleFilter          # the handle: its particle buffer is the ensemble
+    inflation::Float64
+end
+"EnsembleKalmanFilter(dynamics, measurement, R1, R2, d0, N; nu, ny, inflation)  src/enkf.jl:94-141 (descriptor arguments)"
+function LowLevelParticleFilters.EnsembleKalmanFilter(dyn::LinearDynamics, meas::LinearMeasurement, R1, R2, d0, N::Integer;
+                                                      inflation=1.0, Ts=1.0, seed=0, kw...)
+    pf = GPUParticleFilter(N, LGModel(dyn.A, dyn.B, meas.C, Matrix{Float64}(R1), Matrix{Float64}(R2), _mean(d0), _cov(d0)); kind=0, Ts, seed)
+    check(ccall((:llpf_enkf_set_inflation, lib), Cint, (Ptr{Cvoid}, Float64), pf.h, inflation))
+    check(ccall((:llpf_enkf_reset, lib), Cint, (Ptr{Cvoid}, UInt64), pf.h, 0))
+    GPUEnsembleKalmanFilter(pf, inflation)
+end
+function _enkf_state(e::GPUEnsembleKalmanFilter)
+    m = zeros(e.pf.nx); c = zeros(e.pf.nx, e.pf.nx); t = Ref{Int64}(0)
+    check(ccall((:llpf_enkf_state, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}), e.pf.h, m, c, t))
+    m, c, Int(t[])
+end
+LowLevelParticleFilters.state(e::GPUEnsembleKalmanFilter) = _enkf_state(e)[1]            # enkf.jl:186
+LowLevelParticleFilters.covariance(e::GPUEnsembleKalmanFilter) = _enkf_state(e)[2]       # enkf.jl:193 (symmetric)
+index(e::GPUEnsembleKalmanFilter) = _enkf_state(e)[3]
+particles(e::GPUEnsembleKalmanFilter) = particles(e.pf)
+num_particles(e::GPUEnsembleKalmanFilter) = e.pf.N
+function reset!(e::GPUEnsembleKalmanFilter)                                              # enkf.jl:205-224
+    e.pf.epoch += 1
+    check(ccall((:llpf_enkf_reset, lib), Cint, (Ptr{Cvoid}, UInt64), e.pf.h, e.pf.epoch))
+end
+predict!(e::GPUEnsembleKalmanFilter, u, p=nothing, t::Real=index(e) * e.pf.Ts) =         # enkf.jl:228-272
+    check(ccall((:llpf_enkf_predict, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64), e.pf.h, vecf(u), t))
+function correct!(e::GPUEnsembleKalmanFilter, u, y, p=nothing, t::Real=index(e) * e.pf.Ts)   # enkf.jl:281-356
+    nx, ny = e.pf.nx, e.pf.ny
+    ll = Ref{Float64}(0.0); ev = zeros(ny); S = zeros(ny, ny); K = zeros(ny, nx)        # K arrives row-major nx x ny
+    check(ccall((:llpf_enkf_correct, lib), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}), e.pf.h, vecf(u), vecf(y), t, ll, ev, S, K))
+    (; ll=ll[], e=ev, S, Sᵪ=cholesky(Symmetric(S)), K=permutedims(K))
+end
+function update!(e::GPUEnsembleKalmanFilter, u, y, p=nothing, t::Real=index(e) * e.pf.Ts)   # enkf.jl:361-366
+    r = correct!(e, u, y, p, t); predict!(e, u, p, t); r
+end
+function forward_trajectory(e::GPUEnsembleKalmanFilter, u::AbstractVector, y::AbstractVector, p=nothing)   # filtering.jl:282-325
+    T, nx, ny = length(y), e.pf.nx, e.pf.ny
+    U = e.pf.nu > 0 ? Matrix{Float64}(reduce(hcat, u)) : zeros(0, T); Y = Matrix{Float64}(reduce(hcat, y))
+    x = zeros(nx, T); xt = zeros(nx, T); R = zeros(nx, nx, T); Rt = zeros(nx, nx, T); ev = zeros(ny, T); lls = zeros(T)
+    S = zeros(ny, ny, T); K = zeros(ny, nx, T); ll = Ref{Float64}(0.0)
+    e.pf.epoch += 1
+    check(ccall((:llpf_enkf_run, lib), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, UInt64, Ref{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                e.pf.h, T, U, Y, e.pf.epoch, ll, x, R, xt, Rt, ev, lls, S, K))
+    cols(M) = [M[:, k] for k in 1:T]; mats(M) = [M[:, :, k] for k in 1:T]
+    LowLevelParticleFilters.KalmanFilteringSolution(e, u, y, cols(x), cols(xt), mats(R), mats(Rt), ll[], cols(ev),
+        [permutedims(K[:, :, k]) for k in 1:T], [cholesky(Symmetric(S[:, :, k])) for k in 1:T], nothing, range(0, step=e.pf.Ts, length=T))
+end
+
 end # module
