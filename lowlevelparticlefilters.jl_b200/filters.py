@@ -569,6 +569,12 @@ def forward_trajectory(pf, u, y, p=None, *, history=True, epoch=None, pre_correc
             raise TypeError("forward_trajectory(::AuxiliaryParticleFilter) takes no callbacks (filtering.jl:367)")
         return _forward_trajectory_stepwise(pf, u, y, p, history, epoch, *cbs)
     wide = pf.particle_dtype == np.dtype(np.float32)
+    if wide and history:
+        # the Float32 wide engine records no history inside its fused loop (llpf_run: LLPF_ERR_UNSUPPORTED): the solution
+        # is assembled by the reference's own loop on the step verbs and accessors — same RNG counters, same trajectory
+        sol = _forward_trajectory_stepwise(pf, u, y, p, True, epoch, None, None, None, None)
+        sol.extra["xhat"] = np.einsum("tnd,tn->td", sol.x, sol.we)       # weighted_mean per step  filtering.jl:541-548
+        return sol
     r = _run(pf, u, y, TIME_FORWARD_TRAJECTORY, history, epoch, want_xhat=not wide)
     t = np.arange(r["T"]) * pf.Ts  # range(0, step=Ts, length=T)  solutions.jl:345
     extra = {k: r.get(k) for k in ("ll_steps", "ess", "resampled", "xhat")}

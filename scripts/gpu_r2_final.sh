@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round-2 evidence run on one B200: everything profiles/README.md lists under r2_*.
+mkdir -p gpurun_out
+O=gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.max.mem,power.limit --format=csv > $O/r2_gpus.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_smoke.log 2>&1; echo "smoke rc=$?" | tee -a $O/r2_smoke.log
+timeout 1200 python -m pytest tests -m gpu -q > $O/r2_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $O/r2_pytest_gpu.log
+tail -4 $O/r2_pytest_gpu.log
+for c in 2 3 4 5; do
+  python bench.py --config $c > $O/r2_bench_c$c.json 2> $O/r2_bench_c$c.err
+  python -c "import json;d=json.loads(open('$O/r2_bench_c$c.json').read().strip().splitlines()[-1]);print('config $c: ms %.3f value %.3e e2e %.3e frac %.3f cpu %.3e'%(d['ms_per_step'],d['value'],d['e2e']['value'],d['roofline']['frac'],d['cpu_baseline']['value']))"
+done
+python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_reference.json 2> $O/r2_bench_reference.err; tail -c 600 $O/r2_bench_reference.json
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/r2_bench_under_ncu.log 2>&1
+python scripts/tune.py quick > $O/r2_tune_quick.log 2>&1; grep "us/step" $O/r2_tune_quick.log
+python scripts/tune.py residual > $O/r2_tune_strategies.log 2>&1
+python scripts/pmmh_timing.py > $O/r2_pmmh_timing.log 2>&1; tail -4 $O/r2_pmmh_timing.log
+python scripts/enkf_timing.py > $O/r2_enkf_rbpf_timing.log 2>&1; cat $O/r2_enkf_rbpf_timing.log
+ncu --set full --clock-control none --import-source on -k regex:k_engine_wide -s 1 -c 1 -o $O/r2_wide_v3 -f \
+  python bench.py --config 5 --T 20 --steps 1 --warmup 1 --no-cpu-baseline > $O/r2_ncu_wide_v3.log 2>&1
+ls -la $O/r2_wide_v3.ncu-rep

@@ -665,6 +665,27 @@ def test_f32_wide_loglik_matches_oracle(gpu, scan_mode, thr):
     assert abs(sol.ll - got["ll"]) <= 1e-12 * abs(got["ll"])
 
 
+def test_f32_wide_forward_trajectory_history_matches_oracle(gpu):
+    """x / w / we history and per-step weighted means of a Float32 wide filter (assembled on the step verbs: the fused loop of
+    the wide engine records none) against the oracle's f32 mode; the log-likelihood equals the fused launch's."""
+    L = gpu
+    s = lg_large_model(seed=3)
+    N, T = 512, 8
+    u, y = _data(s, T, 6)
+    pf = s.particle_filter(N, seed=4, scan_mode="serial", resample_threshold=0.5)
+    of = s.oracle_filter(N, seed=4, resample_threshold=0.5)
+    sol = L.forward_trajectory(pf, u, y, epoch=2)
+    ref = of.forward_trajectory(u, y, epoch=2, history=True)
+    assert sol.x.shape == (T, N, s.nx) and sol.w.shape == (T, N)
+    assert abs(sol.ll - ref["ll"]) <= F32_LL_RTOL * abs(ref["ll"])
+    assert np.array_equal(sol.extra["resampled"], ref["resampled"])
+    assert np.abs(sol.x - ref["x"]).max() <= F32_X_ATOL * max(1.0, np.abs(ref["x"]).max())
+    assert np.allclose(sol.w, ref["w"], rtol=0, atol=1e-4) and np.allclose(sol.we, ref["we"], rtol=1e-4, atol=1e-9)
+    assert np.allclose(L.mean_trajectory(sol), np.einsum("tnd,tn->td", ref["x"], ref["we"]), rtol=0, atol=1e-4)
+    fused = L.forward_trajectory(pf, u, y, epoch=2, history=False)
+    assert abs(fused.ll - sol.ll) <= 1e-12 * abs(sol.ll)
+
+
 def test_f32_wide_unsupported_combinations_fail_loudly(gpu):
     L = gpu
     s = lg_large_model(seed=2)
@@ -673,7 +694,7 @@ def test_f32_wide_unsupported_combinations_fail_loudly(gpu):
     pf = s.particle_filter(256, seed=1)
     u, y = _data(s, 4, 1)
     with pytest.raises(L.LLPFError):
-        L.forward_trajectory(pf, u, y)                  # x/w/we history of a wide filter: not recorded in the loop
+        L.smooth(pf, 8, u, y)                           # the smoother needs the device-resident history
     s8 = lg_model(4, 2, 2, seed=0)
     with pytest.raises(L.LLPFError):
         lg_large_model(65, 2, 4).particle_filter(64)    # nx > 64
