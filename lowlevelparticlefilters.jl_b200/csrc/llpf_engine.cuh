@@ -283,6 +283,18 @@ __device__ __forceinline__ u64 ld_acquire_sys_u64(const u64* p) {
 __device__ __forceinline__ void st_release_sys_u64(u64* p, u64 v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// release fence at system scope: what a message-passing pattern over NVLink needs (`__threadfence_system()` is the
+// sequentially-consistent fence.sc.sys, measured at ~5 us per use on the critical path of a sharded resample)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// Packed particle exchange, release side (tuning switch; 3 is what ships):
+//   1: every pushing thread fences, block 0 posts the count with a relaxed store
+//   2: no per-thread fence, block 0 posts with st.release.sys (relies on cumulativity through the grid barrier alone;
+//      2.5 us per resample step faster than 3 on 2 GPUs, bit-identical in the parity runs; not shipped: 3 also holds if a
+//      pushing SM's posted writes were not covered by another SM's release)
+//   3: both
+#ifndef LLPF_XCHG_VARIANT
+#define LLPF_XCHG_VARIANT 3
+#endif
 __device__ __forceinline__ void st_relaxed_sys_u64(u64* p, u64 v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -393,7 +405,7 @@ __device__ __forceinline__ void peer_allgather(const EngineP& P, Shared& sh, u64
 }
 
 // cross-GPU barrier carrying one value per rank (the length of the rank's heavy-run list).  Call right after a
-// local grid barrier; every thread that stored into peer memory must have executed __threadfence_system()
+// local grid barrier; every thread that stored into peer memory must have executed a system-scope release fence
 // before arriving at that barrier, so all of this rank's peer stores are performed before block 0 posts.
 __device__ __forceinline__ void peer_barrier(const EngineP& P, Shared& sh, u64& xseq, double payload,
                                              double (&all)[MAX_WORLD][1]) {
@@ -1014,8 +1026,8 @@ __device__ __forceinline__ void push_remote_parts(const EngineP& P, int pack_buf
 }
 
 // Cross-GPU barrier that closes the scatter of a sharded resample; it carries, per destination, the number of packed
-// entries this rank pushed there.  Call right after the local grid barrier (every pushing thread executed
-// __threadfence_system() before arriving at it, so the entries are performed before block 0 posts the count).
+// entries this rank pushed there.  Call right after the local grid barrier (every pushing thread executed a system-scope
+// release fence before arriving at it, and block 0 posts the count with st.release.sys).
 // incoming[r] = entries rank r pushed into MY pack_in (0 for r == rank).
 __device__ __forceinline__ void peer_exchange_counts(const EngineP& P, Shared& sh, u64& xseq, int (&incoming)[MAX_WORLD]) {
   xseq += 1;
@@ -1025,7 +1037,11 @@ __device__ __forceinline__ void peer_exchange_counts(const EngineP& P, Shared& s
     const int r = threadIdx.x;
     const unsigned c = (unsigned)__ldcg(P.pack_cnt + r);
     u64* out = reinterpret_cast<u64*>(P.peer_mbox[r]) + ((size_t)par * MAX_WORLD + P.rank) * MBOX_WORDS;
+#if LLPF_XCHG_VARIANT == 1
     st_relaxed_sys_u64(out, tag | (u64)c);
+#else
+    st_release_sys_u64(out, tag | (u64)c);   // cumulative: everything ordered before it by the grid barrier is released with it
+#endif
   }
   uint32_t* words = reinterpret_cast<uint32_t*>(sh.peer_vals);
   __syncthreads();                                               // earlier readers of sh.peer_vals are done
@@ -1034,7 +1050,11 @@ __device__ __forceinline__ void peer_exchange_counts(const EngineP& P, Shared& s
     u64 v;
     do { v = ld_relaxed_sys_u64(in); } while ((v & 0xffffffff00000000ull) != tag);
     words[threadIdx.x] = (uint32_t)v;
-    __threadfence_system();                                      // acquire side: the entries behind the count are read next
+    LLPF_TS(P, sh, 15);
+    // acquire side: the entries behind the count are read next (by the whole block, after the barrier below).  An acquire
+    // LOAD of the word just seen, not a fence: fence.acq_rel.sys here cost 7 us per resample step on 2 GPUs (79.5 -> 72.4 us),
+    // fence.sc.sys (__threadfence_system) another 1 us (profiles/r2_xchg_ab.log)
+    (void)ld_acquire_sys_u64(in);
   }
   __syncthreads();
 #pragma unroll
@@ -1198,7 +1218,9 @@ __device__ __forceinline__ void expand_packs(const EngineP& P, JT* jout_flat, co
 template <class JT>
 __device__ __forceinline__ void finish_scatter(const EngineP& P, Shared& sh, unsigned& bar_target, u64& xseq,
                                                JT* jout_flat, int slot_lo, int slot_hi, int pushed) {
-  if (pushed) __threadfence_system();   // my packed entries are performed system-wide before I arrive
+#if LLPF_XCHG_VARIANT != 2
+  if (pushed) fence_acq_rel_sys();      // release side: my packed entries are ordered before the count block 0 posts
+#endif
   grid_barrier(P.bar, (unsigned)P.nblocks, bar_target);
   LLPF_TS(P, sh, 10);
   if (P.world > 1) {

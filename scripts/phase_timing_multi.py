@@ -28,4 +28,12 @@ if rank == 0:
                   f"counts-xchg {seg(10,11,m):6.2f} | expand {seg(11,12,m):6.2f} | bar {seg(12,13,m):6.2f} | heavy-fill {seg(13,4,m):6.2f}")
         print(f" {name:8s}: scan1 {seg(0,1,m):6.2f} | bar {seg(1,2,m):6.2f} | scatter(+totals xchg) {seg(2,3,m):6.2f} | bar+peerbar {seg(3,4,m):6.2f} | main {seg(4,5,m) if name=='res' else seg(0,5,m):6.2f} | "
               f"blk-red {seg(5,6,m):6.2f} | bar {seg(6,7,m):6.2f} | combine {seg(7,9,m):6.2f} | xchg {seg(9,8,m):6.2f} | total {seg(0,8,m):6.2f}")
+dist.barrier()
+if rank == 1:   # rank 1's thread 0 is the one that polls rank 0's count word: where the counts exchange spends its time
+    ts = np.fromfile("/tmp/phases_1.bin", dtype=np.int64).reshape(-1, 16)[1:T]
+    res = d["resampled"][:T - 1].astype(bool); ghz = 1.95
+    def seg1(a, b, m):
+        v = ts[m, b] - ts[m, a]; v = v[(ts[m, a] > 0) & (ts[m, b] > 0)]; return v.mean() / ghz / 1e3 if v.size else float("nan")
+    print(f"   rank 1 : fence+bar {seg1(3,10,res):6.2f} | counts: post+poll {seg1(10,15,res):6.2f} | fence.sys after the poll {seg1(15,11,res):6.2f} | "
+          f"expand {seg1(11,12,res):6.2f} | bar {seg1(12,13,res):6.2f}")
 dist.destroy_process_group()
