@@ -854,6 +854,9 @@ static int create_impl(const llpf_config* cfg, const llpf_model* model, const ch
   if (user && (user_np < 0 || (user_np > 0 && !user_p))) return fail(LLPF_ERR_BAD_ARG, "bad parameter vector");
   if (cfg->N < 1 || cfg->N >= (1ll << 31)) return fail(LLPF_ERR_BAD_ARG, "need 1 <= N < 2^31");
   if (cfg->filter < 0 || cfg->filter > 3) return fail(LLPF_ERR_BAD_ARG, "unknown filter kind");
+  if (user && std::strstr(user_src, "LLPF_USER_STATE_HOOKS") && cfg->filter >= LLPF_FILTER_AUX)
+    return fail(LLPF_ERR_UNSUPPORTED, "user models with state hooks (add_noise / correct_state, e.g. RBPF) run as ParticleFilter / "
+                                      "AdvancedParticleFilter: the auxiliary filter's two-stage step does not call the hooks");
   if (cfg->resampling != LLPF_RESAMPLE_SYSTEMATIC && cfg->resampling != LLPF_RESAMPLE_STRATIFIED &&
       cfg->resampling != LLPF_RESAMPLE_RESIDUAL && cfg->resampling != LLPF_RESAMPLE_METROPOLIS)
     return fail(LLPF_ERR_BAD_ARG, "unknown resampling strategy");

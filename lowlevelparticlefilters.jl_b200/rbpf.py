@@ -129,6 +129,7 @@ class RBPF(F.AbstractParticleFilter):
         if nx > 8:
             raise ValueError(f"RBPF particle [xn; xl; tril(R)] has {nx} components; the f64 engine carries at most 8")
         self.kf, self.dynamics, self.nl_measurement_model = kf, dynamics, mm
+        self.measurement = mm
         self.R1n, self.d0n, self.An = np.atleast_2d(np.asarray(R1n, dtype=np.float64)), d0n, An
         self.nxn, self.nxl = nxn, nxl
         src = rbpf_source(nxn, nxl, ny, nu, kf.A, kf.B, kf.C, An, kf.R1, self.R1n, mm.R2, dynamics, mm.measurement)

@@ -161,6 +161,16 @@ def test_device_rbpf_step_verbs_equal_the_fused_trajectory(gpu):
 
 
 @pytest.mark.gpu
+def test_device_rbpf_refuses_the_auxiliary_filter(gpu):
+    """the auxiliary filter's two-stage step does not call the state hooks: it must fail loudly, not run a wrong filter"""
+    L = gpu
+    kf, u, y, fn_c, g_c, fn_p, g_p, R1n, d0n, An = CASES["mixed"](5)
+    pf = _device_filter(L, 64, kf, fn_c, g_c, R1n, d0n, An, 0, 1)
+    with pytest.raises(L.LLPFError):
+        L.AuxiliaryParticleFilter(pf)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("case", ["linear", "nonlinear"])
 def test_device_rbpf_meets_the_reference_criterion(gpu, case):
     """test_rbpf.jl:111,141 at the reference's own size: N = 500 particles, T = 500 steps, ll within 1 % of the KF"""
