@@ -38,9 +38,9 @@
 // user-defined models (DYN == LLPF_DYN_USER = 2): the reference takes arbitrary closures `dynamics(x,u,p,t)` and
 // `measurement_likelihood(x,u,y,p,t)` (src/PFtypes.jl:128,232).  Closures cannot cross a C-ABI, device source can: a
 // translation unit that defines these two templates (or specialisations) and instantiates k_engine<NX,NY,2,RESID> gets a
-// filter with those functions inlined into the sweep — compiled at run time with NVRTC (scripts/nvrtc_probe.py shows the
-// compile path; the run-time loader is not wired into the C-ABI yet).  u, y: the raw vectors of the step; p: the
-// parameter vector `p` of the filter; additive dynamics noise N(0,R1) is still drawn by the engine.
+// filter with those functions inlined into the sweep — compiled at run time with NVRTC by llpf_create_user (llpf_api.cu:
+// compile_user_kernel; scripts/nvrtc_probe.py compiles the same source offline).  u, y: the raw vectors of the step; p: the
+// parameter vector `p` of the filter; the dynamics noise L1*z is drawn by the engine (added, or handed to the add_noise hook).
 // Everything below that serves DYN == 2 is compiled only with -DLLPF_USER_MODEL, so that the kernels of the shipped library
 // are byte-for-byte what was measured (the extra kernel-parameter / shared-memory fields alone perturb register allocation).
 // ------------------------------------------------------------------------------------------------
