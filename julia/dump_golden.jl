@@ -10,7 +10,8 @@
 #   * dynamics noise vectors    rand!(pf.rng, dynamics_density, noise)           src/PFtypes.jl:135,153 ; ext/...DistributionsExt.jl:90
 #   * the resampling uniforms   rand()                                           src/resample.jl:23,49,106
 #     (recovered by copying the task-local RNG state right before predict! and replaying it — shouldresample draws nothing)
-# together with everything the reference computes from them (x, w, we of every step, ll, j).  tests/test_reference_golden.py
+# together with everything the reference computes from them (x, w, we of every step, ll, j) — for the particle filters and,
+# in the `rbpf` section, for the Rao-Blackwellized filter (oracle/rbpf_ref.py is its consumer).  tests/test_reference_golden.py
 # feeds the recorded variates to the oracle restatement (oracle/pyref.py, `inject=`) and demands the same outputs:
 # indices and resample decisions exactly, floating-point values to 1e-12 relative (SLEEFPirates.exp / Distributions.logpdf
 # differ from libm / the Cholesky form in the last bits).
@@ -159,6 +160,67 @@ function resample_vectors()
     out
 end
 
+# ---- RBPF (src/rbpf.jl): the mixed linear / nonlinear model of test/test_rbpf.jl:5-34 (An != 0) ---------------------------
+# rbpf.jl reads the fields μ and Σ of the nonlinear-state distributions (:217, :292-295) and draws rand(pf.rng, d) from them
+# (:136-150 reset!, :203 / :222 predict!): a distribution with those fields that logs what it hands out records every variate.
+struct RecordingMvN{M,S}
+    μ::M
+    Σ::S
+    log::Vector{Vector{Float64}}
+end
+Base.length(d::RecordingMvN) = length(d.μ)
+Base.eltype(d::RecordingMvN) = Float64
+function Base.rand(rng::Random.AbstractRNG, d::RecordingMvN)
+    x = d.μ + cholesky(Symmetric(Matrix(d.Σ))).L * randn(rng, length(d.μ))
+    push!(d.log, collect(Float64, x))
+    typeof(d.μ)(x)
+end
+flat(p) = vcat(collect(Float64, p.xn), collect(Float64, p.xl), [Float64(p.R[r, c]) for r in 1:size(p.R, 1) for c in 1:r])
+
+function rbpf_case(; N=150, T=40, threshold=0.5, seed=7)
+    Random.seed!(seed)
+    An = SA[0.5;;]; A = SA[0.95;;]; C2 = SA[1.0;;]; B = @SMatrix zeros(1, 0)
+    R1n = SA[0.01;;]; R1l = SA[0.01;;]; R2 = SA[0.1;;]
+    x0n = SA[1.0]; x0l = SA[1.0]; R0 = SA[1.0;;]
+    fn(xn, args...) = xn
+    h(xn, args...) = xn
+    dn = RecordingMvN(SA[0.0], R1n, Vector{Float64}[])
+    d0n = RecordingMvN(x0n, R1n, Vector{Float64}[])
+    kf = KalmanFilter(A, B, C2, 0, R1l, R2, LLPF.SimpleMvNormal(x0l, R0))
+    mm = RBMeasurementModel(h, R2, 1)
+    pf = RBPF(N, kf, fn, mm, dn, d0n; nu=0, An=An, Ts=1.0, resample_threshold=threshold,
+              names=SignalNames(x=["x1", "x2"], u=String[], y=["y1"], name="RBPF"))
+    # data from the model itself, written out (no recording wrapper consumed)
+    xn, xl = 1.0, 1.0; y = Vector{Vector{Float64}}()
+    for t in 1:T
+        push!(y, [xn + xl + sqrt(0.1) * randn()])
+        xn, xl = xn + 0.5 * xl + 0.1 * randn(), 0.95 * xl + 0.1 * randn()
+    end
+    us = [SA_F64[] for _ in 1:T]; ys = [SVector{1}(v) for v in y]
+    empty!(d0n.log); empty!(dn.log)
+    reset!(pf)
+    x0 = copy(d0n.log)
+    xs = Vector{Vector{Vector{Float64}}}(); ws = Vector{Vector{Float64}}(); wes = Vector{Vector{Float64}}()
+    lls = Float64[]; ures = Vector{Vector{Float64}}(); noise = Vector{Vector{Vector{Float64}}}(); resampled = Int[]
+    for t in 1:T
+        ti = (t - 1) * pf.Ts                                       # forward_trajectory  src/filtering.jl:352
+        push!(lls, correct!(pf, us[t], ys[t], LLPF.parameters(pf), ti)[1])
+        push!(xs, [flat(p) for p in LLPF.particles(pf)])
+        push!(ws, copy(LLPF.weights(pf))); push!(wes, copy(LLPF.expweights(pf)))
+        empty!(dn.log)
+        draws = replay_uniforms(1)
+        did = LLPF.shouldresample(pf)
+        predict!(pf, us[t], LLPF.parameters(pf), ti)
+        push!(ures, did ? draws : Float64[]); push!(resampled, did ? 1 : 0)
+        push!(noise, copy(dn.log))
+    end
+    Dict("name" => "rbpf_mixed", "N" => N, "T" => T, "threshold" => threshold, "Ts" => 1.0,
+         "A" => Matrix(A), "An" => Matrix(An), "C" => Matrix(C2), "R1l" => Matrix(R1l), "R1n" => Matrix(R1n), "R2" => Matrix(R2),
+         "x0n" => collect(x0n), "x0l" => collect(x0l), "R0" => Matrix(R0), "y" => y,
+         "x0" => x0, "noise" => noise, "u_res" => ures, "x" => xs, "w" => ws, "we" => wes, "ll_steps" => lls, "ll" => sum(lls),
+         "resampled" => resampled, "j_final" => copy(LLPF.state(pf).j), "x_final" => [flat(p) for p in LLPF.particles(pf)])
+end
+
 function main()
     out = length(ARGS) >= 1 ? ARGS[1] : joinpath(@__DIR__, "..", "tests", "golden", "reference_v1.json")
     cases = [
@@ -169,7 +231,7 @@ function main()
         lg_case("apf_sys_lg4", 4, 2, 2, 150, 20; aux=true, seed=5),
     ]
     doc = Dict("version" => 1, "julia" => string(VERSION), "package" => (isdefined(Base, :pkgversion) ? string(pkgversion(LLPF)) : "unknown"),
-               "cases" => cases, "ranges" => range_vectors(), "resample" => resample_vectors())
+               "cases" => cases, "ranges" => range_vectors(), "resample" => resample_vectors(), "rbpf" => [rbpf_case()])
     open(out, "w") do io
         write(io, js(doc))
     end

@@ -98,7 +98,10 @@ class RBPFRef(P.Filter):
     kf = dict(A, B, C, R1, R2, mu0, Sigma0) (KalmanFilter(A,B,C,0,R1l,R2,d0l)); fn(xn,u,t), g(xn,u,t) Python callables;
     An a matrix or None; d0n = (mu0n, Sigma0n)."""
 
-    def __init__(self, N, kf, fn, g, R1n, d0n, An=None, resample_threshold=0.1, Ts=1.0, seed=0):
+    def __init__(self, N, kf, fn, g, R1n, d0n, An=None, resample_threshold=0.1, Ts=1.0, seed=0, inject=None, record=None):
+        """inject / record as in pyref.Filter: dict(x0 = initial nonlinear states [N][nxn], noise = [K][N][nxn] the draws
+        rand(rng, R1n) of every predict!, u_res = [K][...] the rand() of resample) — recorded from the reference itself by
+        julia/dump_golden.jl (`rbpf` section) and consumed in place of the counter-based streams."""
         self.kf, self.fn, self.g = kf, fn, g
         self.R1n, self.An = [list(map(float, r)) for r in R1n], (None if An is None else [list(map(float, r)) for r in An])
         self.mu0n, self.Sigma0n = list(map(float, d0n[0])), [list(map(float, r)) for r in d0n[1]]
@@ -107,19 +110,25 @@ class RBPFRef(P.Filter):
         self.L1n = P.cholesky_lower(self.R1n) if any(v != 0 for r in self.R1n for v in r) else [[0.0] * self.nxn for _ in range(self.nxn)]
         self.L0n = P.cholesky_lower(self.Sigma0n) if any(v != 0 for r in self.Sigma0n for v in r) else [[0.0] * self.nxn for _ in range(self.nxn)]
         self.L2 = P.cholesky_lower(kf["R2"])
-        super().__init__(_Dims(self.NX), N, kind=P.PF, resampling=0, resample_threshold=resample_threshold, Ts=Ts, seed=seed)
+        super().__init__(_Dims(self.NX), N, kind=P.PF, resampling=0, resample_threshold=resample_threshold, Ts=Ts, seed=seed,
+                         inject=inject, record=record)
 
     # reset!(pf::RBPF)  rbpf.jl:136-150
     def reset(self, epoch=0):
         self.epoch, self.k = epoch, 0
         N = self.N
         for i in range(N):
-            z = P.normals(self.seed, epoch, P.ST_INIT, 0, i, self.NX)[:self.nxn]
-            lz = P.lower_times(self.L0n, z)
-            xn = [self.mu0n[r] + lz[r] for r in range(self.nxn)]         # rand(pf.rng, pf.d0n)
+            if self.inject is not None:
+                xn = list(map(float, self.inject["x0"][i]))
+            else:
+                z = P.normals(self.seed, epoch, P.ST_INIT, 0, i, self.NX)[:self.nxn]
+                lz = P.lower_times(self.L0n, z)
+                xn = [self.mu0n[r] + lz[r] for r in range(self.nxn)]     # rand(pf.rng, pf.d0n)
             part = (xn, list(map(float, self.kf["mu0"])), [list(map(float, r)) for r in self.kf["Sigma0"]])
             self.x[i] = part
             self.xprev[i] = part
+        if self.record is not None:
+            self.record.update(x0=[list(p[0]) for p in self.x], noise=[], u_res=[])
         self.w = [-math.log(N)] * N
         self.we = [1 / N] * N
         self.t = 1
@@ -132,7 +141,14 @@ class RBPFRef(P.Filter):
         zeroAn = _is_zero(self.An)
         for i in range(self.N):
             xn, xl, R = self.xprev[self.j[i] - 1 if use_j else i]
-            noise = P.lower_times(self.L1n, P.normals(self.seed, self.epoch, P.ST_DYN, self.t, i, self.NX)[:self.nxn])
+            if self.inject is not None:
+                noise = list(map(float, self.inject["noise"][self.k][i]))
+            else:
+                noise = P.lower_times(self.L1n, P.normals(self.seed, self.epoch, P.ST_DYN, self.t, i, self.NX)[:self.nxn])
+            if self.record is not None:
+                while len(self.record["noise"]) <= self.k:
+                    self.record["noise"].append([])
+                self.record["noise"][self.k].append(list(noise))
             fi = list(self.fn(xn, u, t))
             Axl_l = _matvec(Al, xl)
             Bu = _matvec(Bl, u) if len(u) else [0.0] * self.nxl

@@ -96,6 +96,68 @@ def check_resample(doc):
         assert j == list(r["j"]), r["strategy"]
 
 
+def check_rbpf(c, exact=False):
+    """`rbpf` section: the mixed model of test/test_rbpf.jl (fn = xn, g = xn, An != 0) driven like forward_trajectory with the
+    variates the reference consumed; state after every correct! as flat particles [xn; xl; tril(R)]."""
+    from oracle import rbpf_ref as R
+    kf = dict(A=c["A"], B=[[] for _ in c["A"]], C=c["C"], R1=c["R1l"], R2=c["R2"], mu0=c["x0l"], Sigma0=c["R0"])
+    pf = R.RBPFRef(c["N"], kf, lambda xn, u, t: list(xn), lambda xn, u, t: list(xn), c["R1n"], (c["x0n"], c["R1n"]),
+                   An=c["An"], resample_threshold=c["threshold"], Ts=c["Ts"],
+                   inject=dict(x0=c["x0"], noise=c["noise"], u_res=c["u_res"]))
+    pf.reset(0)
+    xs, ws, wes, lls, res = [], [], [], [], []
+    for t in range(1, c["T"] + 1):
+        ti = (t - 1) * pf.Ts
+        lls.append(pf.correct([], c["y"][t - 1], ti))
+        xs.append(pf.particles_flat()); ws.append(list(pf.w)); wes.append(list(pf.we))
+        n0 = pf.nres
+        pf.predict([], ti)
+        res.append(pf.nres - n0)
+    assert res == list(c["resampled"]) and pf.j == list(c["j_final"])
+    if exact:
+        assert xs == c["x"] and ws == c["w"] and wes == c["we"] and lls == c["ll_steps"]
+    else:
+        assert _close(xs, c["x"], rtol=1e-11, atol=1e-12) and _close(ws, c["w"], rtol=1e-10, atol=1e-10)
+        assert _close(wes, c["we"], rtol=1e-9, atol=1e-300) and _close(lls, c["ll_steps"], rtol=1e-10, atol=1e-10)
+    assert _close(pf.particles_flat(), c["x_final"], rtol=1e-11, atol=1e-12)
+
+
+def _python_rbpf_dump():
+    """the `rbpf` section with the schema of julia/dump_golden.jl, written by the restatement with its own variates"""
+    from oracle import rbpf_ref as R
+    rng = np.random.default_rng(5)
+    T, N = 25, 80
+    xn, xl, y = 1.0, 1.0, []
+    for _ in range(T):
+        y.append([xn + xl + math.sqrt(0.1) * rng.standard_normal()])
+        xn, xl = xn + 0.5 * xl + 0.1 * rng.standard_normal(), 0.95 * xl + 0.1 * rng.standard_normal()
+    c = dict(name="rbpf_mixed", N=N, T=T, threshold=0.5, Ts=1.0, A=[[0.95]], An=[[0.5]], C=[[1.0]], R1l=[[0.01]], R1n=[[0.01]],
+             R2=[[0.1]], x0n=[1.0], x0l=[1.0], R0=[[1.0]], y=y)
+    rec = {}
+    kf = dict(A=c["A"], B=[[]], C=c["C"], R1=c["R1l"], R2=c["R2"], mu0=c["x0l"], Sigma0=c["R0"])
+    pf = R.RBPFRef(N, kf, lambda xn, u, t: list(xn), lambda xn, u, t: list(xn), c["R1n"], (c["x0n"], c["R1n"]), An=c["An"],
+                   resample_threshold=0.5, seed=3, record=rec)
+    pf.reset(1)
+    xs, ws, wes, lls, res = [], [], [], [], []
+    for t in range(1, T + 1):
+        lls.append(pf.correct([], y[t - 1], (t - 1) * 1.0))
+        xs.append(pf.particles_flat()); ws.append(list(pf.w)); wes.append(list(pf.we))
+        n0 = pf.nres
+        pf.predict([], (t - 1) * 1.0)
+        res.append(pf.nres - n0)
+    c.update(x0=rec["x0"], noise=rec["noise"], u_res=rec["u_res"], x=xs, w=ws, we=wes, ll_steps=lls, ll=sum(lls), resampled=res,
+             j_final=list(pf.j), x_final=pf.particles_flat())
+    return c
+
+
+def test_rbpf_dump_schema_round_trip(tmp_path):
+    c = _python_rbpf_dump()
+    assert sum(c["resampled"]) >= 2
+    path = tmp_path / "rbpf.json"
+    path.write_text(json.dumps(dict(rbpf=[c])))
+    check_rbpf(json.loads(path.read_text())["rbpf"][0], exact=True)
+
+
 def _python_dump():
     """A dump with the schema of julia/dump_golden.jl, produced by the Python restatement with its own (Philox) variates."""
     from models import lg_model
@@ -186,6 +248,15 @@ def test_restatement_reproduces_the_reference_trajectories():
     assert doc["version"] == 1 and len(doc["cases"]) >= 4
     for c in doc["cases"]:
         check_case(c)
+
+
+@needs_ref
+def test_restatement_reproduces_the_reference_rbpf():
+    doc = json.load(open(REF))
+    if not doc.get("rbpf"):
+        pytest.skip("this dump has no `rbpf` section (written by an older julia/dump_golden.jl)")
+    for c in doc["rbpf"]:
+        check_rbpf(c)
 
 
 @needs_ref
