@@ -111,3 +111,122 @@ def exact_scan(w, return_stats=False):
     if return_stats:
         return B, dict(special=int(special.sum()), n=n)
     return B
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The same algorithm in the decomposition a GPU would run (blocks of `chunk` consecutive elements, nothing but block-local
+# work, scans over per-block aggregates, and ONE sequential walk over the special elements):
+#   A  fixed-point block scan -> block totals -> exclusive block offsets            (what resample_indices does today)
+#   B  per element: certify the binade from the global fixed-point prefix, r_i = RN(w_i / u) or "special"
+#   C  segmented integer scan of r (restarting after every special): block-local scan + a segmented scan over the block
+#      aggregates (carry = units accumulated since the last special, which is in the same binade by construction);
+#      alongside, a max-scan of "index of the last special <= i"
+#   D  one thread walks the specials in index order: B_before = B_(previous special) + u * (units accumulated before s),
+#      B_s = fl(B_before + w_s)                                                      (one f64 add per special)
+#   E  per element: B_i = B_(last special <= i) + u_i * (units since it)
+# ---------------------------------------------------------------------------------------------------------------------
+def exact_scan_blocked(w, chunk=3544, return_stats=False):
+    w = np.asarray(w, dtype=np.float64)
+    n = w.size
+    if n == 0:
+        return (w.copy(), dict(special=0)) if return_stats else w.copy()
+    nb = (n + chunk - 1) // chunk
+    blocks = [(b * chunk, min(n, (b + 1) * chunk)) for b in range(nb)]
+    # ---- A
+    q = [int(round(float(v) * 2.0 ** FIX_BITS)) for v in w]
+    loc = [0] * n                         # block-local inclusive prefix
+    tot = [0] * nb
+    for b, (s, e) in enumerate(blocks):
+        acc = 0
+        for i in range(s, e):
+            acc += q[i]
+            loc[i] = acc
+        tot[b] = acc
+    off = [0] * nb
+    for b in range(1, nb):
+        off[b] = off[b - 1] + tot[b - 1]
+    # ---- B (element-parallel; needs only off[block], loc[i], loc[i-1], w[i], i)
+    special = [False] * n
+    e_of = [0] * n
+    r = [0] * n
+    for b, (s, e) in enumerate(blocks):
+        for i in range(s, e):
+            a_hi = (off[b] + loc[i]) / 2.0 ** FIX_BITS
+            a_lo = (off[b] + loc[i] - q[i]) / 2.0 ** FIX_BITS
+            d_hi = (i + 1) * 2.0 ** -53 * a_hi + (i + 1) * 2.0 ** -63
+            d_lo = i * 2.0 ** -53 * a_lo + i * 2.0 ** -63
+            lo, hi = a_lo - d_lo, a_hi + d_hi
+            if not (lo > 0.0):
+                special[i] = True
+                continue
+            eb = _binade(lo)
+            if not (hi < 2.0 ** (eb + 1)) or lo <= 2.0 ** eb:
+                special[i] = True
+                continue
+            m, ex = math.frexp(float(w[i]))
+            mi = int(m * 2.0 ** 53)
+            sh = (eb - 52) - (ex - 53)
+            if sh <= 0:
+                ri = mi << (-sh)
+            else:
+                ri, rem = mi >> sh, mi & ((1 << sh) - 1)
+                half = 1 << (sh - 1)
+                if rem == half:
+                    special[i] = True
+                    continue
+                if rem > half:
+                    ri += 1
+            e_of[i], r[i] = eb, ri
+    # ---- C: segmented scan, block-local part
+    seg = [0] * n                         # units since the last special at or before i (0 at a special), block-local
+    last = [-1] * n                       # index of the last special <= i inside the block, -1 if none
+    agg_units = [0] * nb                  # units after the block's last special (or of the whole block if it has none)
+    agg_has = [False] * nb
+    agg_last = [-1] * nb
+    for b, (s, e) in enumerate(blocks):
+        acc, ls = 0, -1
+        for i in range(s, e):
+            if special[i]:
+                acc, ls = 0, i
+            else:
+                acc += r[i]
+            seg[i], last[i] = acc, ls
+        agg_units[b], agg_has[b], agg_last[b] = acc, ls >= 0, ls
+    # segmented scan over the block aggregates: what every block inherits from its predecessors
+    carry_units = [0] * nb
+    carry_last = [-1] * nb
+    for b in range(1, nb):
+        if agg_has[b - 1]:
+            carry_units[b], carry_last[b] = agg_units[b - 1], agg_last[b - 1]
+        else:
+            carry_units[b], carry_last[b] = carry_units[b - 1] + agg_units[b - 1], carry_last[b - 1]
+    units = [0] * n                       # units since the globally last special <= i
+    glast = [-1] * n
+    for b, (s, e) in enumerate(blocks):
+        for i in range(s, e):
+            if last[i] >= 0:
+                units[i], glast[i] = seg[i], last[i]
+            else:
+                units[i], glast[i] = carry_units[b] + seg[i], carry_last[b]
+    # ---- D: the sequential walk
+    spec_idx = [i for i in range(n) if special[i]]
+    Bs = {}
+    b_prev = 0.0                          # B before the first element
+    for s_ in spec_idx:
+        if s_ > 0 and not special[s_ - 1]:
+            base = Bs[glast[s_ - 1]] if glast[s_ - 1] >= 0 else 0.0
+            b_before = base + units[s_ - 1] * 2.0 ** (e_of[s_ - 1] - 52)
+        else:
+            b_before = Bs[s_ - 1] if s_ > 0 else 0.0
+        Bs[s_] = b_before + float(w[s_])
+    # ---- E
+    out = np.empty(n)
+    for i in range(n):
+        if special[i]:
+            out[i] = Bs[i]
+        else:
+            base = Bs[glast[i]] if glast[i] >= 0 else 0.0
+            out[i] = base + units[i] * 2.0 ** (e_of[i] - 52)
+    if return_stats:
+        return out, dict(special=len(spec_idx), n=n, blocks=nb)
+    return out

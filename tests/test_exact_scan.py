@@ -49,3 +49,15 @@ def test_fixed_point_scan_is_not_bit_identical_but_the_exact_scan_is():
     assert (fast != ref).mean() > 0.05
     assert np.abs(fast - ref).max() < 1e-11
     assert np.array_equal(X.exact_scan(w), ref)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "softmax", "degenerate", "ties", "dyadic"])
+@pytest.mark.parametrize("n,chunk", [(1, 8), (37, 8), (1000, 64), (20000, 3544), (20000, 257)])
+def test_blocked_decomposition_equals_serial_cumsum_bit_for_bit(kind, n, chunk):
+    """the same algorithm in the decomposition a GPU would run: block-local scans, scans over block aggregates, one walk over
+    the specials — independent of the block size"""
+    w = _weights(kind, n, seed=n + 1)
+    ref = X.serial_cumsum(w)
+    got, st = X.exact_scan_blocked(w, chunk=chunk, return_stats=True)
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), (kind, n, chunk, int(np.argmax(got != ref)))
+    assert np.array_equal(got, X.exact_scan(w))
