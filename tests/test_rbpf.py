@@ -88,6 +88,34 @@ def test_generated_device_source_compiles_offline():
     assert rc == 0, log
 
 
+def test_source_generator_flags_dimensions_and_literals():
+    import llpf_b200 as L
+    src = L.rbpf_source(2, 1, 1, 1, A=[[0.0]], B=[[0.3]], C=[[0.0]], An=None, R1l=[[1.0]], R1n=[[0.1, 0.02], [0.02, 0.3]],
+                        R2=[[10.0]], fn_body="fn[0] = xn[0]; fn[1] = xn[1];", g_body="yn[0] = xn[0];")
+    assert "llpf_rbpf::Consts<2, 1, 1, 1>" in src and "dynamics<4>" in src and "correct_state<4>" in src   # 2 + 1 + 1 components
+    consts = src.split("const RB k = {")[1].split("}; return k;")[0]
+    assert consts.rstrip().endswith(", 1, 1")                       # iszero(An) and iszero(C)  (rbpf.jl:179,247)
+    assert float.fromhex("0x1.999999999999ap-4") == 0.1 and "0x1.999999999999ap-4" in consts   # exact hexadecimal literals
+    src2 = L.rbpf_source(1, 2, 1, 0, A=[[1, 0.1], [0, 1]], B=None, C=[[1.0, 0]], An=[[0.5, 0]], R1l=[[1, 0], [0, 1]],
+                         R1n=[[0.01]], R2=[[0.1]], fn_body="fn[0] = xn[0];", g_body="yn[0] = 0.0;")
+    assert "dynamics<6>" in src2 and src2.split("const RB k = {")[1].split("}; return k;")[0].rstrip().endswith(", 0, 0")
+
+
+def test_device_filters_fail_loudly_without_a_gpu(built):
+    """no CPU fallback behind the new constructors either: without a device they raise, they do not compute on the host"""
+    import ctypes as C
+    import llpf_b200 as L
+    n = C.c_int()
+    if L.load_library().llpf_device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a CUDA device is visible")
+    kf, u, y, fn_c, g_c, fn_p, g_p, R1n, d0n, An = CASES["mixed"](3)
+    with pytest.raises(L.LLPFError):
+        _device_filter(L, 16, kf, fn_c, g_c, R1n, d0n, An, 0, 1)
+    with pytest.raises(L.LLPFError):
+        L.EnsembleKalmanFilter(L.LinearDynamics(np.eye(2), np.zeros((2, 1))), L.LinearMeasurement(np.eye(2)), np.eye(2), np.eye(2),
+                               L.MvNormal(np.zeros(2), np.eye(2)), 16)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU
 # ---------------------------------------------------------------------------------------------------------------------
