@@ -11,7 +11,8 @@
 #   * the resampling uniforms   rand()                                           src/resample.jl:23,49,106
 #     (recovered by copying the task-local RNG state right before predict! and replaying it — shouldresample draws nothing)
 # together with everything the reference computes from them (x, w, we of every step, ll, j) — for the particle filters and,
-# in the `rbpf` section, for the Rao-Blackwellized filter (oracle/rbpf_ref.py is its consumer).  tests/test_reference_golden.py
+# in the `rbpf` / `enkf` sections, for the Rao-Blackwellized and the ensemble Kalman filter (consumers: oracle/rbpf_ref.py,
+# oracle/enkf_ref.py).  tests/test_reference_golden.py
 # feeds the recorded variates to the oracle restatement (oracle/pyref.py, `inject=`) and demands the same outputs:
 # indices and resample decisions exactly, floating-point values to 1e-12 relative (SLEEFPirates.exp / Distributions.logpdf
 # differ from libm / the Cholesky form in the last bits).
@@ -221,6 +222,60 @@ function rbpf_case(; N=150, T=40, threshold=0.5, seed=7)
          "resampled" => resampled, "j_final" => copy(LLPF.state(pf).j), "x_final" => [flat(p) for p in LLPF.particles(pf)])
 end
 
+# ---- EnKF (src/enkf.jl): the linear test system of test/test_enkf.jl:13-31 -------------------------------------------------
+# enkf.jl builds its noise distributions inside predict! / correct! (:245, :337), so wrappers cannot see the draws; an RNG that
+# logs every standard normal it hands out can: SimpleMvNormal's rand is mu + cholesky(Sigma).L * randn(rng, n) (src/utils.jl:260).
+mutable struct RecordingRNG <: Random.AbstractRNG
+    r::Random.Xoshiro
+    log::Vector{Float64}
+end
+Random.randn(g::RecordingRNG) = (v = randn(g.r); push!(g.log, v); v)
+Random.randn(g::RecordingRNG, ::Type{Float64}) = randn(g)
+Random.rand(g::RecordingRNG, ::Type{T}) where {T} = rand(g.r, T)           # anything else passes through unrecorded
+rows(v, n) = [v[(i-1)*n+1:i*n] for i in 1:(length(v) ÷ n)]
+
+function enkf_case(; N=120, T=30, inflation=1.0, seed=11)
+    Random.seed!(seed)
+    nx, nu, ny = 2, 2, 2
+    A = SA[0.99 0.1; 0.0 0.2]; B = SA[-0.74 1.61; -1.44 1.75]; C = SMatrix{2,2}(1.0I(2))
+    dynamics(x, u, p, t) = A * x .+ B * u
+    measurement(x, u, p, t) = C * x
+    R1 = SMatrix{2,2}(1.0I(2)); R2 = SMatrix{2,2}(1.0I(2))
+    mu0 = randn(nx); S0 = Matrix(4.0I, nx, nx)
+    d0 = LLPF.SimpleMvNormal(SVector{2}(mu0), SMatrix{2,2}(S0))
+    g = RecordingRNG(Random.Xoshiro(seed), Float64[])
+    enkf = EnsembleKalmanFilter(dynamics, measurement, R1, R2, d0, N; nu, ny, inflation, rng=g)
+    u = [randn(nu) for _ in 1:T]
+    xt = mu0 .+ 2 .* randn(nx); y = Vector{Vector{Float64}}()
+    for t in 1:T
+        push!(y, collect(C * xt) .+ randn(ny))
+        xt = collect(A * xt .+ B * u[t]) .+ randn(nx)
+    end
+    us = [SVector{nu}(v) for v in u]; ys = [SVector{ny}(v) for v in y]
+    empty!(g.log); reset!(enkf); z0 = rows(copy(g.log), nx)
+    xs = Vector{Vector{Float64}}(); Rs = Vector{Vector{Vector{Float64}}}(); xts = Vector{Vector{Float64}}()
+    Rts = Vector{Vector{Vector{Float64}}}(); es = Vector{Vector{Float64}}(); lls = Float64[]
+    Ss = Vector{Vector{Vector{Float64}}}(); Ks = Vector{Vector{Vector{Float64}}}()
+    zobs = Vector{Vector{Vector{Float64}}}(); zdyn = Vector{Vector{Vector{Float64}}}()
+    mrows(M) = [collect(Float64, M[i, :]) for i in 1:size(M, 1)]
+    for k in 1:T                                                   # forward_trajectory(kf, u, y)  src/filtering.jl:292-318
+        ti = (k - 1) * enkf.Ts
+        push!(xs, collect(Float64, LLPF.state(enkf))); push!(Rs, mrows(LLPF.covariance(enkf)))
+        empty!(g.log)
+        ret = correct!(enkf, us[k], ys[k], LLPF.parameters(enkf), ti)
+        push!(zobs, rows(copy(g.log), ny))
+        push!(lls, ret.ll); push!(es, collect(Float64, ret.e)); push!(Ss, mrows(ret.S)); push!(Ks, mrows(ret.K))
+        push!(xts, collect(Float64, LLPF.state(enkf))); push!(Rts, mrows(LLPF.covariance(enkf)))
+        empty!(g.log)
+        predict!(enkf, us[k], LLPF.parameters(enkf), ti)
+        push!(zdyn, rows(copy(g.log), nx))
+    end
+    Dict("name" => "enkf_lin2", "N" => N, "T" => T, "Ts" => 1.0, "inflation" => inflation, "A" => Matrix(A), "B" => Matrix(B),
+         "C" => Matrix(C), "R1" => Matrix(R1), "R2" => Matrix(R2), "mu0" => mu0, "Sigma0" => S0, "u" => u, "y" => y,
+         "z0" => z0, "zobs" => zobs, "zdyn" => zdyn, "x" => xs, "R" => Rs, "xt" => xts, "Rt" => Rts, "e" => es, "S" => Ss, "K" => Ks,
+         "ll_steps" => lls, "ll" => sum(lls), "ensemble_final" => [collect(Float64, p) for p in LLPF.particles(enkf)])
+end
+
 function main()
     out = length(ARGS) >= 1 ? ARGS[1] : joinpath(@__DIR__, "..", "tests", "golden", "reference_v1.json")
     cases = [
@@ -231,7 +286,8 @@ function main()
         lg_case("apf_sys_lg4", 4, 2, 2, 150, 20; aux=true, seed=5),
     ]
     doc = Dict("version" => 1, "julia" => string(VERSION), "package" => (isdefined(Base, :pkgversion) ? string(pkgversion(LLPF)) : "unknown"),
-               "cases" => cases, "ranges" => range_vectors(), "resample" => resample_vectors(), "rbpf" => [rbpf_case()])
+               "cases" => cases, "ranges" => range_vectors(), "resample" => resample_vectors(), "rbpf" => [rbpf_case()],
+               "enkf" => [enkf_case(), enkf_case(inflation=1.05, seed=12)])
     open(out, "w") do io
         write(io, js(doc))
     end

@@ -15,8 +15,13 @@ ST_ENKF_OBS = 8
 
 
 class EnKFRef:
-    def __init__(self, dynamics, C, R1, R2, mu0, Sigma0, N, Ts=1.0, inflation=1.0, seed=0):
-        """dynamics(x, u, t) -> list ; measurement h(x) = C x"""
+    def __init__(self, dynamics, C, R1, R2, mu0, Sigma0, N, Ts=1.0, inflation=1.0, seed=0, inject=None, record=None):
+        """dynamics(x, u, t) -> list ; measurement h(x) = C x.
+        inject / record: dict(z0 = [N][nx], zdyn = [K][N][nx], zobs = [K][N][ny]) — the STANDARD NORMALS behind the initial
+        ensemble, the process noise of the K-th predict! and the observation perturbations of the K-th correct! (what a recording
+        RNG sees inside the reference: julia/dump_golden.jl, `enkf` section), consumed in place of the counter-based streams."""
+        self.inject, self.record = inject, record
+        self.kp = self.kc = 0
         self.f, self.C = dynamics, [list(map(float, r)) for r in C]
         self.R2 = [list(map(float, r)) for r in R2]
         self.L1, self.L2, self.L0 = P.cholesky_lower(R1), P.cholesky_lower(R2), P.cholesky_lower(Sigma0)
@@ -42,17 +47,35 @@ class EnKFRef:
 
     def reset(self, epoch=0):                                           # reset!  enkf.jl:205-224
         self.epoch = epoch
+        self.kp = self.kc = 0
         self.X = []
+        if self.record is not None:
+            self.record.update(z0=[], zdyn=[], zobs=[])
         for i in range(self.N):
-            lz = P.lower_times(self.L0, P.normals(self.seed, epoch, P.ST_INIT, 0, i, self.nx))
+            z = self._z("z0", None, i, P.ST_INIT, 0, self.nx)
+            lz = P.lower_times(self.L0, z)
             self.X.append([self.mu0[r] + lz[r] for r in range(self.nx)])
         self.t = 0
         self._stats()
 
+    def _z(self, key, k, i, stream, step, n):
+        if self.inject is not None:
+            z = list(map(float, self.inject[key][i] if k is None else self.inject[key][k][i]))
+        else:
+            z = P.normals(self.seed, self.epoch, stream, step, i, n)
+        if self.record is not None:
+            tab = self.record[key]
+            if k is not None:
+                while len(tab) <= k:
+                    tab.append([])
+                tab = tab[k]
+            tab.append(list(z))
+        return z
+
     def predict(self, u, t):                                            # predict!  enkf.jl:228-272
         N, nx = self.N, self.nx
         for i in range(N):
-            nz = P.lower_times(self.L1, P.normals(self.seed, self.epoch, P.ST_DYN, self.t, i, nx))
+            nz = P.lower_times(self.L1, self._z("zdyn", self.kp, i, P.ST_DYN, self.t, nx))
             fx = self.f(self.X[i], u, t)
             self.X[i] = [fx[r] + nz[r] for r in range(nx)]              # :256
         if self.inflation > 1.0:                                        # :261-266
@@ -63,6 +86,7 @@ class EnKFRef:
             for i in range(N):
                 self.X[i] = [xb[r] + self.inflation * (self.X[i][r] - xb[r]) for r in range(nx)]
         self.t += 1
+        self.kp += 1
         self._stats()
 
     def correct(self, u, y, t):                                         # correct!  enkf.jl:281-356
@@ -79,11 +103,12 @@ class EnKFRef:
         K = _right_divide_chol(Rxy, Ls)                                 # :331
         e = [y[a] - yb[a] for a in range(ny)]                           # :334
         for i in range(N):                                              # :340-349
-            eps = P.lower_times(self.L2, P.normals(self.seed, self.epoch, ST_ENKF_OBS, self.t, i, ny))
+            eps = P.lower_times(self.L2, self._z("zobs", self.kc, i, ST_ENKF_OBS, self.t, ny))
             d = [(y[a] + eps[a]) - Y[i][a] for a in range(ny)]
             Kd = P.matvec(K, d)
             self.X[i] = [self.X[i][r] + Kd[r] for r in range(nx)]
         ll = _logpdf_chol(Ls, e)                                        # :352
+        self.kc += 1
         self._stats()
         return dict(ll=ll, e=e, S=S, K=K)
 

@@ -158,6 +158,44 @@ def test_rbpf_dump_schema_round_trip(tmp_path):
     check_rbpf(json.loads(path.read_text())["rbpf"][0], exact=True)
 
 
+def _enkf_ref(c, **kw):
+    from oracle import enkf_ref as E
+    A, B = c["A"], c["B"]
+
+    def dyn(x, u, t):                     # dynamics(x,u,p,t) = A*x .+ B*u  (StaticArrays: left-to-right sums)
+        return [P.matvec(A, x)[r] + P.matvec(B, u)[r] for r in range(len(x))]
+    return E.EnKFRef(dyn, c["C"], c["R1"], c["R2"], c["mu0"], c["Sigma0"], c["N"], Ts=c["Ts"], inflation=c["inflation"], **kw)
+
+
+def check_enkf(c, exact=False):
+    """`enkf` section: forward_trajectory of the ensemble Kalman filter on the recorded standard normals"""
+    ref = _enkf_ref(c, inject=dict(z0=c["z0"], zdyn=c["zdyn"], zobs=c["zobs"]))
+    out = ref.forward_trajectory(c["u"], c["y"])
+    for key in ("x", "R", "xt", "Rt", "e", "S", "K", "ll_steps"):
+        if exact:
+            assert out[key] == c[key], key
+        else:
+            assert _close(out[key], c[key], rtol=1e-10, atol=1e-11), key     # the reference's BLAS / mean() sum in other orders
+    assert abs(out["ll"] - c["ll"]) <= 1e-10 * max(1.0, abs(c["ll"]))
+    assert _close(ref.X, c["ensemble_final"], rtol=1e-10, atol=1e-11)
+
+
+def test_enkf_dump_schema_round_trip(tmp_path):
+    rng = np.random.default_rng(2)
+    T = 12
+    c = dict(name="enkf_lin2", N=60, T=T, Ts=1.0, inflation=1.05, A=[[0.99, 0.1], [0.0, 0.2]], B=[[-0.74, 1.61], [-1.44, 1.75]],
+             C=[[1.0, 0.0], [0.0, 1.0]], R1=[[1.0, 0.0], [0.0, 1.0]], R2=[[1.0, 0.0], [0.0, 1.0]], mu0=[0.3, -0.2],
+             Sigma0=[[4.0, 0.0], [0.0, 4.0]], u=rng.standard_normal((T, 2)).tolist(), y=rng.standard_normal((T, 2)).tolist())
+    rec = {}
+    ref = _enkf_ref(c, seed=4, record=rec)
+    out = ref.forward_trajectory(c["u"], c["y"], epoch=1)
+    c.update({k: out[k] for k in ("x", "R", "xt", "Rt", "e", "S", "K", "ll_steps", "ll")})
+    c.update(z0=rec["z0"], zdyn=rec["zdyn"], zobs=rec["zobs"], ensemble_final=[list(v) for v in ref.X])
+    path = tmp_path / "enkf.json"
+    path.write_text(json.dumps(dict(enkf=[c])))
+    check_enkf(json.loads(path.read_text())["enkf"][0], exact=True)
+
+
 def _python_dump():
     """A dump with the schema of julia/dump_golden.jl, produced by the Python restatement with its own (Philox) variates."""
     from models import lg_model
@@ -257,6 +295,15 @@ def test_restatement_reproduces_the_reference_rbpf():
         pytest.skip("this dump has no `rbpf` section (written by an older julia/dump_golden.jl)")
     for c in doc["rbpf"]:
         check_rbpf(c)
+
+
+@needs_ref
+def test_restatement_reproduces_the_reference_enkf():
+    doc = json.load(open(REF))
+    if not doc.get("enkf"):
+        pytest.skip("this dump has no `enkf` section (written by an older julia/dump_golden.jl)")
+    for c in doc["enkf"]:
+        check_enkf(c)
 
 
 @needs_ref
